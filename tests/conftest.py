@@ -1,0 +1,30 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_fk():
+    return dict(np.load(os.path.join(GOLDEN, "fk.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_dq():
+    return dict(np.load(os.path.join(GOLDEN, "dq.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_quat():
+    return dict(np.load(os.path.join(GOLDEN, "quat.npz")))

@@ -1,0 +1,143 @@
+/*
+ * pymotion_b200 -- C ABI of the B200-native (sm_100a) forward-kinematics /
+ * root dual-quaternion engine.  Drop-in boundary for the hot path of
+ * UPC-ViRVIG/pymotion v0.2.3:
+ *
+ *   pymotion/ops/skeleton.py        fk :16, from_root_dual_quat :173, to_root_dual_quat :207,
+ *                                   from_global_rotations :64
+ *   pymotion/rotations/quat.py      mul :337, mul_vec :320, length :364, inverse :379,
+ *                                   conjugate :396, normalize :411, to_matrix :276, from_matrix :85
+ *   pymotion/rotations/dual_quat.py from_rotation_translation :12, from_translation :39,
+ *                                   to_rotation_translation :62
+ *
+ * The reference has no FFI layer of its own (it is pure NumPy / PyTorch); these
+ * are the entry points a ctypes / cffi stub inside those modules would bind
+ * (INTEGRATION.md shows the stub).  Conventions:
+ *
+ *  - plain pointers and sizes only; no torch / CUDA types in any signature;
+ *  - every array pointer is a DEVICE pointer on the current CUDA device unless
+ *    the parameter name ends in `_host`;
+ *  - arrays are dense row-major float32: quaternion = 4 floats (w,x,y,z),
+ *    dual quaternion = 8 floats (real wxyz | dual wxyz), rotation matrix = 9
+ *    floats m[r][c], vector = 3 floats; `_f64` twins take double;
+ *  - the caller owns every buffer; the library never allocates user-visible
+ *    memory, never frees and never writes an input;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    calls are asynchronous on it and never synchronise;
+ *  - return value 0 = PMB_OK, negative = pmb_status; pmb_last_error() returns a
+ *    thread-local message for the last failing call on this thread;
+ *  - `parents_host` is a HOST array of n_joints int64.  parents[0] is ignored
+ *    (0 and -1 both accepted, like the reference); parents[i] must satisfy
+ *    0 <= parents[i] < i for i >= 1 (BVH depth-first order, io/bvh.py:77-85),
+ *    otherwise PMB_ERR_TOPOLOGY (the reference silently returns a non-FK result
+ *    for such tables; see DESIGN.md "deliberate deviations");
+ *  - a `*_frame_stride` is the distance in ELEMENTS between consecutive frames
+ *    of that operand; 0 means one row shared by every frame (NumPy broadcasting).
+ */
+#ifndef PYMOTION_B200_H_
+#define PYMOTION_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMB_VERSION 100          /* 0.1.0 */
+#define PMB_MAX_JOINTS 512       /* joint programs travel as kernel parameters */
+
+typedef enum pmb_status {
+    PMB_OK = 0,
+    PMB_ERR_NULL = -1,           /* a required pointer is NULL */
+    PMB_ERR_SHAPE = -2,          /* n_frames < 0, n_joints < 1 or > PMB_MAX_JOINTS, bad stride */
+    PMB_ERR_ALIGN = -3,          /* quaternion / dual-quaternion pointer not 16-byte aligned */
+    PMB_ERR_TOPOLOGY = -4,       /* parents[i] outside [0, i) for some i >= 1 */
+    PMB_ERR_CUDA = -5,           /* CUDA runtime / launch error (message has the cudaError string) */
+    PMB_ERR_ROOT_OFFSET = -6     /* to_root_dual_quat: offsets[0] != 0 (AssertionError in the reference, skeleton.py:227) */
+} pmb_status;
+
+int pmb_version(void);
+const char *pmb_last_error(void);
+const char *pmb_status_string(int status);
+
+/* Number of SMs / name of the current device (diagnostics, used by bench.py). */
+int pmb_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);
+
+/* ---- skeleton ops ------------------------------------------------------- */
+
+/* ops/skeleton.py:16-61  fk(rot, global_pos, offsets, parents) -> (positions, rotmats)
+ *   rot          [n_frames][n_joints][4]   local rotations, normalised inside (quat.py:411)
+ *   global_pos   [n_frames][3]             (gpos_frame_stride = 3) or one shared row (0)
+ *   offsets      [n_joints][3]             (offsets_frame_stride = 0) or per frame (3*n_joints)
+ *   positions    [n_frames][n_joints][3]   out
+ *   rotmats      [n_frames][n_joints][3][3] out
+ * offsets[0] is ignored: the root translation is global_pos (skeleton.py:49). */
+int pmb_fk_f32(const float *rot, const float *global_pos, int64_t gpos_frame_stride,
+               const float *offsets, int64_t offsets_frame_stride, const int64_t *parents_host,
+               int64_t n_frames, int32_t n_joints, float *positions, float *rotmats, void *stream);
+
+/* Variant that emits global QUATERNIONS instead of matrices (SURVEY 8f rank 1:
+ * fk -> quat.from_matrix fused away; 44J instead of 64J bytes per pose).
+ *   global_rots  [n_frames][n_joints][4]   out; equals quat.from_matrix(rotmats) up to sign */
+int pmb_fk_quat_f32(const float *rot, const float *global_pos, int64_t gpos_frame_stride,
+                    const float *offsets, int64_t offsets_frame_stride, const int64_t *parents_host,
+                    int64_t n_frames, int32_t n_joints, float *positions, float *global_rots, void *stream);
+
+/* ops/skeleton.py:207-244  to_root_dual_quat(rotations, global_pos, parents, offsets) -> dq
+ *   offsets      [n_joints][3] shared; offsets_host0 = its first row read by the caller
+ *                (host, 3 floats) so the reference's `offsets[0] == 0` assert can be
+ *                enforced without a device sync; pass NULL to skip the check.
+ *   dq           [n_frames][n_joints][8]   out */
+int pmb_to_root_dual_quat_f32(const float *rotations, const float *global_pos, int64_t gpos_frame_stride,
+                              const int64_t *parents_host, const float *offsets, const float *offsets_host0,
+                              int64_t n_frames, int32_t n_joints, float *dq, void *stream);
+
+/* ops/skeleton.py:173-204  from_root_dual_quat(dq, parents) -> (translations, rotations) */
+int pmb_from_root_dual_quat_f32(const float *dq, const int64_t *parents_host, int64_t n_frames,
+                                int32_t n_joints, float *translations, float *rotations, void *stream);
+
+/* ops/skeleton.py:64-93  from_global_rotations(global_quats, parents) -> local_quats */
+int pmb_from_global_rotations_f32(const float *global_quats, const int64_t *parents_host, int64_t n_frames,
+                                  int32_t n_joints, float *local_quats, void *stream);
+
+/* ---- host-buffer (end-to-end) entry point -------------------------------- */
+
+/* fk on HOST buffers: splits the frame axis into chunks of `chunk_frames`
+ * (0 = library default) and pipelines H2D copy / kernel / D2H copy over two
+ * internal streams and device staging buffers owned by the library (freed by
+ * pmb_release_workspace()).  Blocks until the outputs are in host memory.
+ * Host buffers should be page-locked for full PCIe rate. */
+int pmb_fk_f32_host(const float *rot_host, const float *global_pos_host, const float *offsets_host,
+                    const int64_t *parents_host, int64_t n_frames, int32_t n_joints,
+                    float *positions_host, float *rotmats_host, int64_t chunk_frames);
+void pmb_release_workspace(void);
+
+/* ---- element-wise quaternion primitives (n = number of quaternions) ----- */
+int pmb_quat_mul_f32(const float *q0, const float *q1, float *out, int64_t n, void *stream);          /* quat.py:337 */
+int pmb_quat_mul_vec_f32(const float *q, const float *v, float *out, int64_t n, void *stream);        /* quat.py:320 */
+int pmb_quat_length_f32(const float *q, float *out, int64_t n, void *stream);                         /* quat.py:364 */
+int pmb_quat_normalize_f32(const float *q, float eps, float *out, int64_t n, void *stream);           /* quat.py:411 */
+int pmb_quat_conjugate_f32(const float *q, float *out, int64_t n, void *stream);                      /* quat.py:396 (= inverse :379) */
+int pmb_quat_to_matrix_f32(const float *q, float *out, int64_t n, void *stream);                      /* quat.py:276 */
+int pmb_quat_from_matrix_f32(const float *m, float *out, int64_t n, void *stream);                    /* quat.py:85 */
+
+/* ---- element-wise dual-quaternion primitives ---------------------------- */
+int pmb_dq_from_rotation_translation_f32(const float *rotations, const float *translations, float *dq,
+                                         int64_t n, void *stream);                                    /* dual_quat.py:12 */
+int pmb_dq_from_translation_f32(const float *translations, float *dq, int64_t n, void *stream);       /* dual_quat.py:39 */
+int pmb_dq_to_rotation_translation_f32(const float *dq, float *rotations, float *translations,
+                                       int64_t n, void *stream);                                      /* dual_quat.py:62 */
+
+/* ---- introspection of the host-side joint program (tests) ---- */
+
+/* Builds the per-joint program the chain kernels execute for `parents_host`:
+ * codes_out[i] bits 0-7 = slot the parent transform is fetched from (0xFF: the
+ * previous joint's registers), bits 8-15 = slot this joint is saved to (0xFF:
+ * none), bits 16-30 = parent index.  Returns the number of slots (>= 0) or a
+ * negative pmb_status. */
+int pmb_build_joint_program(const int64_t *parents_host, int32_t n_joints, uint32_t *codes_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMOTION_B200_H_ */

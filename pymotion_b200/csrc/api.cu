@@ -1,0 +1,501 @@
+// extern "C" entry points of libpymotion_b200.so (see include/pymotion_b200.h).
+// Host side only validates, builds the joint program, picks a launch
+// configuration and launches; nothing here computes on the CPU.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+#include "dq_kernels.cuh"
+#include "elementwise.cuh"
+#include "fk_kernel.cuh"
+#include "joint_program.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int status, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    return fail(PMB_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define PMB_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct DeviceProps {
+    int sm_count = 0;
+    int smem_optin = 0;
+    int cc_major = 0, cc_minor = 0;
+    bool ok = false;
+};
+
+int device_props(DeviceProps &out) {
+    // per-device cache; the table is tiny and devices are few
+    static std::mutex mu;
+    static DeviceProps cache[64];
+    int dev = 0;
+    PMB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64) return fail(PMB_ERR_CUDA, "device ordinal %d out of range", dev);
+    DeviceProps &p = cache[dev];
+    if (!p.ok) {
+        PMB_CUDA(cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        PMB_CUDA(cudaDeviceGetAttribute(&p.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        PMB_CUDA(cudaDeviceGetAttribute(&p.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        PMB_CUDA(cudaDeviceGetAttribute(&p.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+        p.ok = true;
+    }
+    out = p;
+    return PMB_OK;
+}
+
+int check_program(const int64_t *parents_host, int32_t n_joints, bool detach, pmb::JointProgram &prog, int &n_slots) {
+    if (!parents_host) return fail(PMB_ERR_NULL, "parents_host is NULL");
+    if (n_joints < 1 || n_joints > PMB_MAX_JOINTS)
+        return fail(PMB_ERR_SHAPE, "n_joints = %d outside [1, %d]", n_joints, PMB_MAX_JOINTS);
+    const pmb::ProgramInfo info = pmb::build_joint_program(parents_host, n_joints, detach, prog.code);
+    if (info.status == PMB_ERR_TOPOLOGY)
+        return fail(PMB_ERR_TOPOLOGY,
+                    "parents[%d] = %lld is not in [0, %d): joints must come after their parent (BVH order)",
+                    info.bad_joint, static_cast<long long>(parents_host[info.bad_joint]), info.bad_joint);
+    if (info.status != PMB_OK) return fail(info.status, "cannot build the joint program");
+    n_slots = info.n_slots;
+    return PMB_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+    if (bytes > 48 * 1024) PMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return PMB_OK;
+}
+
+// ---- fk launch ----------------------------------------------------------------
+struct FkArgs {
+    const float *rot, *gpos, *offsets;
+    long long gstride, ostride;
+    float *pos, *rout;
+    long long n_frames;
+    int n_joints, n_slots;
+    const pmb::JointProgram *prog;
+    cudaStream_t stream;
+};
+
+template <int C, int WARPS, bool PF, bool QO>
+int launch_fk_cfg(const FkArgs &a, int smem) {
+    auto kernel = pmb::fk_chain_kernel<C, WARPS, PF, QO>;
+    int rc = set_smem(kernel, smem);
+    if (rc) return rc;
+    const long long tiles = (a.n_frames + 31) / 32;
+    const long long blocks = (tiles + WARPS - 1) / WARPS;
+    if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
+    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(
+        reinterpret_cast<const float4 *>(a.rot), a.gpos, a.gstride, a.offsets, a.ostride, a.pos, a.rout, a.n_frames,
+        a.n_joints, a.n_slots, *a.prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+template <int RW>
+int fk_smem(int C, int warps, int n_joints, int n_slots) {
+    const int tab = (n_joints * 16 + 127) & ~127;
+    const int sr = (RW * C) | 1, sp = (3 * C) | 1;
+    return tab + warps * (32 * (sr + sp) * 4 + n_slots * 3 * 32 * 16);
+}
+
+template <bool PF, bool QO>
+int launch_fk(const FkArgs &a, const DeviceProps &dp) {
+    constexpr int RW = QO ? 4 : 9;
+    // Pick the joints-per-chunk C and warps per block that keep the most warps resident
+    // (shared memory is the limiter: 48*C bytes of staging + 48 bytes per slot per frame).
+    static const int kC[3] = {7, 5, 3};
+    int best_c = 0, best_w = 0, best_res = -1, best_smem = 0;
+    for (int ci = 0; ci < 3; ++ci) {
+        for (int w = 4; w >= 1; w >>= 1) {
+            const int smem = fk_smem<RW>(kC[ci], w, a.n_joints, a.n_slots);
+            if (smem > dp.smem_optin) continue;
+            const int blocks = std::min(32, (228 * 1024) / (smem + 1024));
+            const int res = std::min(blocks * w, 20);  // beyond ~20 warps registers are the limit anyway
+            if (res > best_res) best_res = res, best_c = kC[ci], best_w = w, best_smem = smem;
+        }
+    }
+    if (best_res <= 0)
+        return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
+#define PMB_FK_CASE(CC, WW) \
+    if (best_c == CC && best_w == WW) return launch_fk_cfg<CC, WW, PF, QO>(a, best_smem);
+    PMB_FK_CASE(7, 4) PMB_FK_CASE(7, 2) PMB_FK_CASE(7, 1)
+    PMB_FK_CASE(5, 4) PMB_FK_CASE(5, 2) PMB_FK_CASE(5, 1)
+    PMB_FK_CASE(3, 4) PMB_FK_CASE(3, 2) PMB_FK_CASE(3, 1)
+#undef PMB_FK_CASE
+    return fail(PMB_ERR_CUDA, "no fk configuration selected");
+}
+
+int fk_common(const float *rot, const float *gpos, int64_t gstride, const float *offsets, int64_t ostride,
+              const int64_t *parents_host, int64_t n_frames, int32_t n_joints, float *pos, float *rout,
+              bool quat_out, void *stream) {
+    if (!rot || !gpos || !offsets || !pos || !rout) return fail(PMB_ERR_NULL, "fk: NULL array pointer");
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
+    if (gstride != 0 && gstride != 3) return fail(PMB_ERR_SHAPE, "gpos_frame_stride must be 0 or 3");
+    if (ostride != 0 && ostride != 3LL * n_joints)
+        return fail(PMB_ERR_SHAPE, "offsets_frame_stride must be 0 or 3*n_joints");
+    if (!aligned16(rot)) return fail(PMB_ERR_ALIGN, "rot must be 16-byte aligned");
+    if (quat_out && !aligned16(rout)) return fail(PMB_ERR_ALIGN, "global_rots must be 16-byte aligned");
+    pmb::JointProgram prog;
+    int n_slots = 0;
+    int rc = check_program(parents_host, n_joints, false, prog, n_slots);
+    if (rc) return rc;
+    if (n_frames == 0) return PMB_OK;
+    DeviceProps dp;
+    if ((rc = device_props(dp))) return rc;
+    FkArgs a{rot, gpos, offsets, gstride, ostride, pos, rout, n_frames, n_joints, n_slots, &prog,
+             static_cast<cudaStream_t>(stream)};
+    if (ostride == 0) return quat_out ? launch_fk<false, true>(a, dp) : launch_fk<false, false>(a, dp);
+    return quat_out ? launch_fk<true, true>(a, dp) : launch_fk<true, false>(a, dp);
+}
+
+inline int ew_grid(int64_t n, int threads, const DeviceProps &dp) {
+    const int64_t want = (n + threads - 1) / threads;
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(dp.sm_count) * 16)));
+}
+
+int tile_frames(int n_joints, int cap_elems) {
+    int fb = (cap_elems / n_joints) & ~3;
+    return std::max(4, std::min(64, fb));
+}
+
+// ---- host-buffer pipeline workspace -------------------------------------------
+struct HostPipe {
+    std::mutex mu;
+    int device = -1;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    float *rot[2] = {nullptr, nullptr}, *gpos[2] = {nullptr, nullptr}, *pos[2] = {nullptr, nullptr},
+          *rotm[2] = {nullptr, nullptr};
+    float *offsets = nullptr;
+    size_t cap_frames = 0, cap_joints = 0;
+    void release() {
+        for (int s = 0; s < 2; ++s) {
+            if (rot[s]) cudaFree(rot[s]);
+            if (gpos[s]) cudaFree(gpos[s]);
+            if (pos[s]) cudaFree(pos[s]);
+            if (rotm[s]) cudaFree(rotm[s]);
+            rot[s] = gpos[s] = pos[s] = rotm[s] = nullptr;
+            if (stream[s]) cudaStreamDestroy(stream[s]);
+            stream[s] = nullptr;
+        }
+        if (offsets) cudaFree(offsets);
+        offsets = nullptr;
+        cap_frames = cap_joints = 0;
+        device = -1;
+    }
+};
+HostPipe g_pipe;
+
+}  // namespace
+
+extern "C" {
+
+int pmb_version(void) { return PMB_VERSION; }
+const char *pmb_last_error(void) { return g_err; }
+
+const char *pmb_status_string(int status) {
+    switch (status) {
+        case PMB_OK: return "ok";
+        case PMB_ERR_NULL: return "null pointer";
+        case PMB_ERR_SHAPE: return "bad shape";
+        case PMB_ERR_ALIGN: return "misaligned pointer";
+        case PMB_ERR_TOPOLOGY: return "bad parents table";
+        case PMB_ERR_CUDA: return "CUDA error";
+        case PMB_ERR_ROOT_OFFSET: return "offsets[0] != 0";
+        default: return "unknown status";
+    }
+}
+
+int pmb_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len) {
+    DeviceProps dp;
+    int rc = device_props(dp);
+    if (rc) return rc;
+    if (sm_count) *sm_count = dp.sm_count;
+    if (cc_major) *cc_major = dp.cc_major;
+    if (cc_minor) *cc_minor = dp.cc_minor;
+    if (name && name_len > 0) {
+        int dev = 0;
+        cudaDeviceProp prop;
+        PMB_CUDA(cudaGetDevice(&dev));
+        PMB_CUDA(cudaGetDeviceProperties(&prop, dev));
+        snprintf(name, static_cast<size_t>(name_len), "%s", prop.name);
+    }
+    return PMB_OK;
+}
+
+int pmb_build_joint_program(const int64_t *parents_host, int32_t n_joints, uint32_t *codes_out) {
+    if (!codes_out) return fail(PMB_ERR_NULL, "codes_out is NULL");
+    pmb::JointProgram prog;
+    int n_slots = 0;
+    int rc = check_program(parents_host, n_joints, false, prog, n_slots);
+    if (rc) return rc;
+    memcpy(codes_out, prog.code, sizeof(uint32_t) * static_cast<size_t>(n_joints));
+    return n_slots;
+}
+
+int pmb_fk_f32(const float *rot, const float *global_pos, int64_t gpos_frame_stride, const float *offsets,
+               int64_t offsets_frame_stride, const int64_t *parents_host, int64_t n_frames, int32_t n_joints,
+               float *positions, float *rotmats, void *stream) {
+    return fk_common(rot, global_pos, gpos_frame_stride, offsets, offsets_frame_stride, parents_host, n_frames,
+                     n_joints, positions, rotmats, false, stream);
+}
+
+int pmb_fk_quat_f32(const float *rot, const float *global_pos, int64_t gpos_frame_stride, const float *offsets,
+                    int64_t offsets_frame_stride, const int64_t *parents_host, int64_t n_frames, int32_t n_joints,
+                    float *positions, float *global_rots, void *stream) {
+    return fk_common(rot, global_pos, gpos_frame_stride, offsets, offsets_frame_stride, parents_host, n_frames,
+                     n_joints, positions, global_rots, true, stream);
+}
+
+int pmb_to_root_dual_quat_f32(const float *rotations, const float *global_pos, int64_t gpos_frame_stride,
+                              const int64_t *parents_host, const float *offsets, const float *offsets_host0,
+                              int64_t n_frames, int32_t n_joints, float *dq, void *stream) {
+    if (!rotations || !global_pos || !offsets || !dq) return fail(PMB_ERR_NULL, "to_root_dual_quat: NULL array pointer");
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
+    if (gpos_frame_stride != 0 && gpos_frame_stride != 3) return fail(PMB_ERR_SHAPE, "gpos_frame_stride must be 0 or 3");
+    if (!aligned16(rotations) || !aligned16(dq)) return fail(PMB_ERR_ALIGN, "rotations and dq must be 16-byte aligned");
+    if (offsets_host0 && (offsets_host0[0] != 0.f || offsets_host0[1] != 0.f || offsets_host0[2] != 0.f))
+        return fail(PMB_ERR_ROOT_OFFSET, "offsets[0] must be zero (ops/skeleton.py:227)");
+    pmb::JointProgram prog;
+    int n_slots = 0;
+    int rc = check_program(parents_host, n_joints, true, prog, n_slots);
+    if (rc) return rc;
+    if (n_frames == 0) return PMB_OK;
+    DeviceProps dp;
+    if ((rc = device_props(dp))) return rc;
+    constexpr int C = 8;
+    using Tile = pmb::DqTile<C>;
+    const int tab = (n_joints * 16 + 127) & ~127;
+    const long long tiles = (n_frames + 31) / 32;
+    auto launch = [&](auto kernel, int warps) -> int {
+        const int smem = tab + warps * Tile::warp_bytes(n_slots);
+        int r = set_smem(kernel, smem);
+        if (r) return r;
+        const long long blocks = (tiles + warps - 1) / warps;
+        if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
+        kernel<<<static_cast<unsigned>(blocks), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4 *>(rotations), global_pos, gpos_frame_stride, offsets,
+            reinterpret_cast<float4 *>(dq), n_frames, n_joints, n_slots, prog);
+        PMB_CUDA(cudaGetLastError());
+        return PMB_OK;
+    };
+    if (tab + 4 * Tile::warp_bytes(n_slots) <= dp.smem_optin) return launch(pmb::to_root_dq_kernel<C, 4>, 4);
+    if (tab + Tile::warp_bytes(n_slots) <= dp.smem_optin) return launch(pmb::to_root_dq_kernel<C, 1>, 1);
+    return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", n_slots);
+}
+
+int pmb_from_root_dual_quat_f32(const float *dq, const int64_t *parents_host, int64_t n_frames, int32_t n_joints,
+                                float *translations, float *rotations, void *stream) {
+    if (!dq || !translations || !rotations) return fail(PMB_ERR_NULL, "from_root_dual_quat: NULL array pointer");
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
+    if (!aligned16(dq) || !aligned16(rotations) || !aligned16(translations))
+        return fail(PMB_ERR_ALIGN, "dq, rotations and translations must be 16-byte aligned");
+    pmb::JointProgram prog;
+    int n_slots = 0;
+    int rc = check_program(parents_host, n_joints, true, prog, n_slots);
+    if (rc) return rc;
+    if (n_frames == 0) return PMB_OK;
+    constexpr int THREADS = 256;
+    const int fb = tile_frames(n_joints, 4096);
+    const int smem = ((fb * n_joints * 12 + 15) & ~15) + ((n_joints * 2 + 15) & ~15);
+    auto kernel = pmb::from_root_dq_kernel<THREADS>;
+    if ((rc = set_smem(kernel, smem))) return rc;
+    const long long blocks = (n_frames + fb - 1) / fb;
+    if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
+    const uint32_t magic = static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(n_joints)) + 1u;
+    kernel<<<static_cast<unsigned>(blocks), THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4 *>(dq), translations, reinterpret_cast<float4 *>(rotations), n_frames, n_joints,
+        fb, magic, prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+int pmb_from_global_rotations_f32(const float *global_quats, const int64_t *parents_host, int64_t n_frames,
+                                  int32_t n_joints, float *local_quats, void *stream) {
+    if (!global_quats || !local_quats) return fail(PMB_ERR_NULL, "from_global_rotations: NULL array pointer");
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
+    if (!aligned16(global_quats) || !aligned16(local_quats))
+        return fail(PMB_ERR_ALIGN, "quaternion arrays must be 16-byte aligned");
+    pmb::JointProgram prog;
+    int n_slots = 0;
+    int rc = check_program(parents_host, n_joints, false, prog, n_slots);
+    if (rc) return rc;
+    if (n_frames == 0) return PMB_OK;
+    constexpr int THREADS = 256;
+    const int fb = tile_frames(n_joints, 4096);
+    const int smem = (n_joints * 2 + 15) & ~15;
+    const long long blocks = (n_frames + fb - 1) / fb;
+    if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
+    const uint32_t magic = static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(n_joints)) + 1u;
+    pmb::from_global_rotations_kernel<THREADS><<<static_cast<unsigned>(blocks), THREADS, smem,
+                                                 static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4 *>(global_quats), reinterpret_cast<float4 *>(local_quats), n_frames, n_joints, fb,
+        magic, prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// ---- host-buffer pipeline -------------------------------------------------------
+void pmb_release_workspace(void) {
+    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    g_pipe.release();
+}
+
+int pmb_fk_f32_host(const float *rot_host, const float *global_pos_host, const float *offsets_host,
+                    const int64_t *parents_host, int64_t n_frames, int32_t n_joints, float *positions_host,
+                    float *rotmats_host, int64_t chunk_frames) {
+    if (!rot_host || !global_pos_host || !offsets_host || !positions_host || !rotmats_host)
+        return fail(PMB_ERR_NULL, "fk_host: NULL array pointer");
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames < 0");
+    if (n_joints < 1 || n_joints > PMB_MAX_JOINTS) return fail(PMB_ERR_SHAPE, "n_joints = %d out of range", n_joints);
+    if (chunk_frames <= 0) chunk_frames = 1 << 16;
+    chunk_frames = (chunk_frames + 31) & ~31LL;
+    std::lock_guard<std::mutex> lock(g_pipe.mu);
+    HostPipe &w = g_pipe;
+    int dev = 0;
+    PMB_CUDA(cudaGetDevice(&dev));
+    const size_t J = static_cast<size_t>(n_joints);
+    if (w.device != dev || w.cap_frames < static_cast<size_t>(chunk_frames) || w.cap_joints < J) {
+        w.release();
+        const size_t F = static_cast<size_t>(chunk_frames);
+        for (int s = 0; s < 2; ++s) {
+            PMB_CUDA(cudaStreamCreateWithFlags(&w.stream[s], cudaStreamNonBlocking));
+            PMB_CUDA(cudaMalloc(&w.rot[s], F * J * 16));
+            PMB_CUDA(cudaMalloc(&w.gpos[s], F * 12));
+            PMB_CUDA(cudaMalloc(&w.pos[s], F * J * 12));
+            PMB_CUDA(cudaMalloc(&w.rotm[s], F * J * 36));
+        }
+        PMB_CUDA(cudaMalloc(&w.offsets, static_cast<size_t>(PMB_MAX_JOINTS) * 12));
+        w.device = dev, w.cap_frames = F, w.cap_joints = J;
+    }
+    PMB_CUDA(cudaMemcpyAsync(w.offsets, offsets_host, J * 12, cudaMemcpyHostToDevice, w.stream[0]));
+    PMB_CUDA(cudaStreamSynchronize(w.stream[0]));
+    int slot = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, slot ^= 1) {
+        const size_t n = static_cast<size_t>(std::min<int64_t>(chunk_frames, n_frames - f0));
+        cudaStream_t st = w.stream[slot];  // stream order makes the slot's buffers safe to reuse
+        PMB_CUDA(cudaMemcpyAsync(w.rot[slot], rot_host + f0 * J * 4, n * J * 16, cudaMemcpyHostToDevice, st));
+        PMB_CUDA(cudaMemcpyAsync(w.gpos[slot], global_pos_host + f0 * 3, n * 12, cudaMemcpyHostToDevice, st));
+        int rc = pmb_fk_f32(w.rot[slot], w.gpos[slot], 3, w.offsets, 0, parents_host, static_cast<int64_t>(n), n_joints,
+                            w.pos[slot], w.rotm[slot], st);
+        if (rc) return rc;
+        PMB_CUDA(cudaMemcpyAsync(positions_host + f0 * J * 3, w.pos[slot], n * J * 12, cudaMemcpyDeviceToHost, st));
+        PMB_CUDA(cudaMemcpyAsync(rotmats_host + f0 * J * 9, w.rotm[slot], n * J * 36, cudaMemcpyDeviceToHost, st));
+    }
+    PMB_CUDA(cudaStreamSynchronize(w.stream[0]));
+    PMB_CUDA(cudaStreamSynchronize(w.stream[1]));
+    return PMB_OK;
+}
+
+// ---- element-wise ---------------------------------------------------------------
+#define PMB_EW_PROLOGUE(n, ...)                                                                      \
+    const void *ptrs_[] = {__VA_ARGS__};                                                             \
+    for (const void *p_ : ptrs_)                                                                     \
+        if (!p_) return fail(PMB_ERR_NULL, "%s: NULL array pointer", __func__);                      \
+    if ((n) < 0) return fail(PMB_ERR_SHAPE, "%s: n < 0", __func__);                                  \
+    if ((n) == 0) return PMB_OK;                                                                     \
+    DeviceProps dp_;                                                                                 \
+    {                                                                                                \
+        int rc_ = device_props(dp_);                                                                 \
+        if (rc_) return rc_;                                                                         \
+    }                                                                                                \
+    const int grid_ = ew_grid((n), 256, dp_);                                                        \
+    cudaStream_t st_ = static_cast<cudaStream_t>(stream)
+
+#define PMB_NEED16(p) \
+    if (!aligned16(p)) return fail(PMB_ERR_ALIGN, "%s: " #p " must be 16-byte aligned", __func__)
+
+int pmb_quat_mul_f32(const float *q0, const float *q1, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q0, q1, out);
+    PMB_NEED16(q0); PMB_NEED16(q1); PMB_NEED16(out);
+    pmb::quat_mul_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q0, (const float4 *)q1, (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_mul_vec_f32(const float *q, const float *v, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q, v, out);
+    PMB_NEED16(q);
+    pmb::quat_mul_vec_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, v, out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_length_f32(const float *q, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q, out);
+    PMB_NEED16(q);
+    pmb::quat_length_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_normalize_f32(const float *q, float eps, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q, out);
+    PMB_NEED16(q); PMB_NEED16(out);
+    pmb::quat_normalize_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, eps, (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_conjugate_f32(const float *q, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q, out);
+    PMB_NEED16(q); PMB_NEED16(out);
+    pmb::quat_conjugate_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_to_matrix_f32(const float *q, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q, out);
+    PMB_NEED16(q);
+    pmb::quat_to_matrix_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_from_matrix_f32(const float *m, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, m, out);
+    PMB_NEED16(out);
+    pmb::quat_from_matrix_kernel<<<grid_, 256, 0, st_>>>(m, (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_dq_from_rotation_translation_f32(const float *rotations, const float *translations, float *dq, int64_t n,
+                                         void *stream) {
+    PMB_EW_PROLOGUE(n, rotations, translations, dq);
+    PMB_NEED16(rotations); PMB_NEED16(dq);
+    pmb::dq_from_rt_kernel<<<grid_, 256, 0, st_>>>((const float4 *)rotations, translations, (float4 *)dq, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_dq_from_translation_f32(const float *translations, float *dq, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, translations, dq);
+    PMB_NEED16(dq);
+    pmb::dq_from_t_kernel<<<grid_, 256, 0, st_>>>(translations, (float4 *)dq, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_dq_to_rotation_translation_f32(const float *dq, float *rotations, float *translations, int64_t n,
+                                       void *stream) {
+    PMB_EW_PROLOGUE(n, dq, rotations, translations);
+    PMB_NEED16(dq); PMB_NEED16(rotations);
+    pmb::dq_to_rt_kernel<<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)rotations, translations, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Element-wise quaternion / dual-quaternion primitives (pymotion/rotations/quat.py,
+// dual_quat.py).  One thread per element, grid-stride, 16-byte accesses for the
+// quaternion operands.  Pure streaming kernels: the roofline is the byte count of
+// their operands.
+#pragma once
+#include "common.cuh"
+
+namespace pmb {
+
+__device__ __forceinline__ Quat<float> ldq(const float4 *p, long long i) {
+    const float4 a = __ldcs(p + i);
+    return {a.x, a.y, a.z, a.w};
+}
+__device__ __forceinline__ void stq(float4 *p, long long i, const Quat<float> &q) {
+    __stcs(p + i, make_float4(q.w, q.x, q.y, q.z));
+}
+__device__ __forceinline__ Vec3<float> ldv(const float *p, long long i) {
+    return {__ldcs(p + 3 * i), __ldcs(p + 3 * i + 1), __ldcs(p + 3 * i + 2)};
+}
+__device__ __forceinline__ void stv(float *p, long long i, const Vec3<float> &v) {
+    p[3 * i] = v.x, p[3 * i + 1] = v.y, p[3 * i + 2] = v.z;
+}
+
+#define PMB_GRID_STRIDE(i, n)                                                                     \
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < (n);    \
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+
+__global__ void quat_mul_kernel(const float4 *a, const float4 *b, float4 *o, long long n) {
+    PMB_GRID_STRIDE(i, n) stq(o, i, q_mul(ldq(a, i), ldq(b, i)));
+}
+__global__ void quat_mul_vec_kernel(const float4 *q, const float *v, float *o, long long n) {
+    PMB_GRID_STRIDE(i, n) stv(o, i, q_rotate(ldq(q, i), ldv(v, i)));
+}
+__global__ void quat_length_kernel(const float4 *q, float *o, long long n) {
+    PMB_GRID_STRIDE(i, n) o[i] = q_length(ldq(q, i));
+}
+__global__ void quat_normalize_kernel(const float4 *q, float eps, float4 *o, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        // true divisions, like quat.py:423, so the result is the correctly rounded quotient
+        const Quat<float> a = ldq(q, i);
+        const float d = q_length(a) + eps;
+        stq(o, i, Quat<float>{a.w / d, a.x / d, a.y / d, a.z / d});
+    }
+}
+__global__ void quat_conjugate_kernel(const float4 *q, float4 *o, long long n) {
+    PMB_GRID_STRIDE(i, n) stq(o, i, q_conj(ldq(q, i)));
+}
+__global__ void quat_to_matrix_kernel(const float4 *q, float *o, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        float m[9];
+        q_to_matrix(ldq(q, i), m);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o[9 * i + k] = m[k];
+    }
+}
+__global__ void quat_from_matrix_kernel(const float *m, float4 *o, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        float a[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a[k] = __ldcs(m + 9 * i + k);
+        stq(o, i, q_from_matrix(a));
+    }
+}
+// dual_quat.py:12-36
+__global__ void dq_from_rt_kernel(const float4 *r, const float *t, float4 *dq, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        const Quat<float> qr = ldq(r, i);
+        const Vec3<float> v = ldv(t, i);
+        const Quat<float> d = q_mul(Quat<float>{0.f, v.x, v.y, v.z}, qr);
+        stq(dq, 2 * i, qr);
+        stq(dq, 2 * i + 1, Quat<float>{0.5f * d.w, 0.5f * d.x, 0.5f * d.y, 0.5f * d.z});
+    }
+}
+// dual_quat.py:39-59
+__global__ void dq_from_t_kernel(const float *t, float4 *dq, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        const Vec3<float> v = ldv(t, i);
+        stq(dq, 2 * i, Quat<float>{1.f, 0.f, 0.f, 0.f});
+        stq(dq, 2 * i + 1, Quat<float>{0.f, v.x * 0.5f, v.y * 0.5f, v.z * 0.5f});
+    }
+}
+// dual_quat.py:62-83
+__global__ void dq_to_rt_kernel(const float4 *dq, float4 *r, float *t, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        const Quat<float> qr = ldq(dq, 2 * i), qd = ldq(dq, 2 * i + 1);
+        const Quat<float> m = q_mul(qd, q_conj(qr));
+        stq(r, i, qr);
+        stv(t, i, Vec3<float>{2.f * m.x, 2.f * m.y, 2.f * m.z});
+    }
+}
+
+}  // namespace pmb

@@ -1,0 +1,394 @@
+"""Parity of the CUDA path (through the C ABI) against the fixtures written by the
+real reference and against the oracle on seeded inputs.  Needs a B200: -m gpu.
+
+Tolerance: BASELINE.json's north_star asks for positions / rotmats within 1e-5
+relative in fp32 of the reference's NumPy output; RTOL = ATOL = 1e-5 below.  The
+reference tests' hand-written goldens are checked at their own atol (1e-6)."""
+import numpy as np
+import pytest
+import torch
+from numpy.testing import assert_allclose
+
+from oracle import oracle_c
+from oracle import pymotion_oracle as orc
+from pymotion_b200.topologies import TOPOLOGIES, parents_of, synth_numpy, synth_torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = ATOL = 1e-5
+TOL = dict(rtol=RTOL, atol=ATOL)
+SKELS = ("body22", "smplh52", "deep65")
+
+
+@pytest.fixture(scope="module")
+def sk():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pymotion_b200.ops.skeleton as mod
+
+    return mod
+
+
+@pytest.fixture(scope="module")
+def quat(sk):
+    import pymotion_b200.rotations.quat as mod
+
+    return mod
+
+
+@pytest.fixture(scope="module")
+def dquat(sk):
+    import pymotion_b200.rotations.dual_quat as mod
+
+    return mod
+
+
+# ---------------------------------------------------------------- fk vs reference fixtures
+@pytest.mark.parametrize("case", ["chain3_ident", "chain3_rot"])
+def test_fk_chain3_goldens(sk, golden_fk, case):
+    g = golden_fk
+    rot = g[f"{case}/rot"].astype(np.float32)
+    pos, rotm = sk.fk(rot, g["chain3/gpos"], g["chain3/offsets"], g["chain3/parents"])
+    assert isinstance(pos, np.ndarray) and pos.dtype == np.float32 and pos.shape == (2, 3, 3)
+    assert rotm.shape == (2, 3, 3, 3)
+    assert_allclose(pos, g[f"{case}/pos"], **TOL)
+    assert_allclose(rotm, g[f"{case}/rotm"], **TOL)
+    assert_allclose(pos, g[f"{case}/hand_pos"], atol=1e-6)  # ops/tests/test_skeleton.py:270, :372
+    if case == "chain3_rot":
+        assert_allclose(rotm, g["chain3_rot/hand_rotm"], atol=1e-6)  # :373
+    # per-frame offsets accepted (:267)
+    pos2, rotm2 = sk.fk(rot, g["chain3/gpos"], np.tile(g["chain3/offsets"], (2, 1, 1)), g["chain3/parents"])
+    assert_allclose(pos2, pos, atol=0)
+    assert_allclose(rotm2, rotm, atol=0)
+
+
+def test_fk_nd_leading_dims(sk, golden_fk):
+    g = golden_fk
+    pos, rotm = sk.fk(g["chain3_nd/rot"].astype(np.float32), g["chain3_nd/gpos"], g["chain3/offsets"], g["chain3/parents"])
+    assert pos.shape == (4, 3, 4, 3, 3) and rotm.shape == (4, 3, 4, 3, 3, 3)
+    assert_allclose(pos, g["chain3_nd/pos"], **TOL)
+    assert_allclose(rotm, g["chain3_nd/rotm"], **TOL)
+
+
+@pytest.mark.parametrize("name", SKELS)
+def test_fk_skeleton_fixtures(sk, golden_fk, name):
+    g = golden_fk
+    par, rot, gp, off = (g[f"{name}/{k}"] for k in ("parents", "rot", "gpos", "offsets"))
+    pos, rotm = sk.fk(rot, gp, off, par)  # non-unit and one zero quaternion inside
+    assert_allclose(pos, g[f"{name}/pos"], **TOL)
+    assert_allclose(rotm, g[f"{name}/rotm"], **TOL)
+    pos, rotm = sk.fk(rot, gp, g[f"{name}/offsets_pf"], par)  # per-frame offsets, offsets[:,0] != 0 ignored
+    assert_allclose(pos, g[f"{name}/pos_pf"], **TOL)
+    assert_allclose(rotm, g[f"{name}/rotm_pf"], **TOL)
+    # torch CUDA tensors in -> torch CUDA tensors out, same values
+    dev = torch.device("cuda")
+    tp, tr = sk.fk(torch.from_numpy(rot).to(dev), torch.from_numpy(gp).to(dev), torch.from_numpy(off).to(dev),
+                   torch.from_numpy(par))
+    assert tp.is_cuda and tp.dtype == torch.float32 and tr.is_contiguous()
+    assert_allclose(tp.cpu().numpy(), g[f"{name}/pos"], **TOL)
+    # float64 in -> float64 out (computed in fp32, documented)
+    p64, r64 = sk.fk(rot.astype(np.float64), gp.astype(np.float64), off.astype(np.float64), par)
+    assert p64.dtype == np.float64
+    assert_allclose(p64, g[f"{name}/pos_f64"], **TOL)
+    assert_allclose(r64, g[f"{name}/rotm_f64"], **TOL)
+
+
+def test_fk_edge_shapes(sk, golden_fk):
+    g = golden_fk
+    pos, rotm = sk.fk(g["unbatched/rot"], g["unbatched/gpos"], g["unbatched/offsets"], g["unbatched/parents"])
+    assert pos.shape == (22, 3) and rotm.shape == (22, 3, 3)  # unbatched, parents[0] = -1
+    assert_allclose(pos, g["unbatched/pos"], **TOL)
+    assert_allclose(rotm, g["unbatched/rotm"], **TOL)
+    pos, rotm = sk.fk(g["single/rot"], g["single/gpos"], g["single/offsets"], np.array([0]))
+    assert_allclose(pos, g["single/pos"], **TOL)
+    assert_allclose(rotm, g["single/rotm"], **TOL)
+    pos, rotm = sk.fk(g["bcast/rot"], np.zeros((1, 3), dtype=np.float32), g["bcast/offsets"], g["body22/parents"])
+    assert_allclose(pos, g["bcast/pos"], **TOL)
+    assert_allclose(rotm, g["bcast/rotm"], **TOL)
+    # empty batch
+    pos, rotm = sk.fk(np.zeros((0, 22, 4), np.float32), np.zeros((0, 3), np.float32), g["bcast/offsets"], g["body22/parents"])
+    assert pos.shape == (0, 22, 3) and rotm.shape == (0, 22, 3, 3)
+
+
+def test_fk_input_not_mutated_and_errors(sk, golden_fk):
+    g = golden_fk
+    dev = torch.device("cuda")
+    rot = torch.from_numpy(g["body22/rot"]).to(dev)
+    keep = rot.clone()
+    sk.fk(rot, torch.from_numpy(g["body22/gpos"]).to(dev), torch.from_numpy(g["body22/offsets"]).to(dev), g["body22/parents"])
+    assert torch.equal(rot, keep)
+    bad = g["body22/parents"].copy()
+    bad[3] = 7
+    with pytest.raises(ValueError):
+        sk.fk(rot, torch.from_numpy(g["body22/gpos"]).to(dev), torch.from_numpy(g["body22/offsets"]).to(dev), bad)
+    with pytest.raises(ValueError):
+        sk.fk(rot[:, :5], torch.from_numpy(g["body22/gpos"]).to(dev), torch.from_numpy(g["body22/offsets"]).to(dev), g["body22/parents"])
+
+
+# ---------------------------------------------------------------- fk vs oracle on seeded inputs, ragged sizes
+@pytest.mark.parametrize("name", SKELS)
+@pytest.mark.parametrize("n_frames", [1, 31, 32, 33, 127, 1000])
+def test_fk_vs_numpy_oracle_ragged(sk, name, n_frames):
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=100 + n_frames)
+    pos, rotm = sk.fk(rot, gp, off, par)
+    want_pos, want_rotm = orc.fk(rot, gp, off, par)
+    assert_allclose(pos, want_pos, **TOL)
+    assert_allclose(rotm, want_rotm, **TOL)
+
+
+def test_fk_random_trees_vs_oracle(sk):
+    rng = np.random.default_rng(5)
+    for n_joints in (2, 7, 8, 40, 129, 512):
+        par = np.zeros(n_joints, dtype=np.int64)
+        for i in range(1, n_joints):
+            par[i] = rng.integers(max(0, i - 6), i)  # bounded look-back keeps the slot count small
+        rot, gp, off = synth_numpy(70, par, seed=n_joints)
+        pos, rotm = sk.fk(rot, gp, off, par)
+        want_pos, want_rotm = orc.fk(rot, gp, off, par)
+        # deep chains accumulate: scale atol with depth * |offset|
+        assert_allclose(pos, want_pos, rtol=RTOL, atol=ATOL * max(1.0, np.abs(want_pos).max()))
+        assert_allclose(rotm, want_rotm, rtol=RTOL, atol=5 * ATOL)
+
+
+def test_fk_full_size_1m_x_22_vs_c_oracle(sk):
+    """BASELINE config 2 at full size against the C restatement (float32 locals,
+    float64 chain), plus size-independent invariants on the whole batch."""
+    par = parents_of("body22")
+    dev = torch.device("cuda")
+    n = 1_000_000
+    rot, gp, off = synth_torch(n, par, dev)
+    pos, rotm = sk.fk(rot, gp, off, par)
+    torch.cuda.synchronize()
+    # invariants on all 22M joints: orthonormal rotations, bone lengths preserved
+    eye = torch.eye(3, device=dev)
+    err = (rotm @ rotm.transpose(-1, -2) - eye).abs().amax().item()
+    assert err < 1e-5
+    assert (torch.linalg.det(rotm[::97]) - 1).abs().amax().item() < 1e-5
+    ptorch = torch.as_tensor(par, device=dev)
+    bone = (pos[:, 1:] - pos[:, ptorch[1:]]).norm(dim=-1)
+    assert_allclose(bone.amax(0).cpu().numpy(), off[1:].norm(dim=-1).cpu().numpy(), rtol=1e-5, atol=1e-5)
+    assert_allclose(bone.amin(0).cpu().numpy(), off[1:].norm(dim=-1).cpu().numpy(), rtol=1e-5, atol=1e-5)
+    assert_allclose(pos[:, 0].cpu().numpy(), gp.cpu().numpy(), atol=0)
+    # element-wise against the oracle, in four slabs to bound host memory
+    off_h = off.cpu().numpy()
+    for lo in range(0, n, 250_000):
+        sl = slice(lo, lo + 250_000)
+        want_pos, want_rotm = oracle_c.fk(rot[sl].cpu().numpy(), gp[sl].cpu().numpy(), off_h, par)
+        assert_allclose(pos[sl].cpu().numpy(), want_pos, **TOL)
+        assert_allclose(rotm[sl].cpu().numpy(), want_rotm, **TOL)
+
+
+def test_fk_4m_x_65_invariants_and_slabs(sk):
+    """BASELINE config 4 (4M x 65, deep hierarchy): invariants on the full batch,
+    oracle on the first / last / a middle 64k-frame window."""
+    par = parents_of("deep65")
+    dev = torch.device("cuda")
+    n = 4_000_000
+    rot, gp, off = synth_torch(n, par, dev, seed=4321)
+    pos, rotm = sk.fk(rot, gp, off, par)
+    torch.cuda.synchronize()
+    ptorch = torch.as_tensor(par, device=dev)
+    want_len = off[1:].norm(dim=-1)
+    worst = 0.0
+    for lo in range(0, n, 500_000):  # slabs keep the temporaries small
+        sl = slice(lo, lo + 500_000)
+        bone = (pos[sl, 1:] - pos[sl][:, ptorch[1:]]).norm(dim=-1)
+        worst = max(worst, (bone - want_len).abs().amax().item())
+        r = rotm[sl]
+        worst_r = (r @ r.transpose(-1, -2) - torch.eye(3, device=dev)).abs().amax().item()
+        assert worst_r < 2e-5
+    assert worst < 2e-5
+    off_h = off.cpu().numpy()
+    for lo in (0, 1_777_777, n - 65_536):
+        sl = slice(lo, lo + 65_536)
+        want_pos, want_rotm = oracle_c.fk(rot[sl].cpu().numpy(), gp[sl].cpu().numpy(), off_h, par)
+        assert_allclose(pos[sl].cpu().numpy(), want_pos, **TOL)
+        assert_allclose(rotm[sl].cpu().numpy(), want_rotm, **TOL)
+
+
+def test_fk_quat_matches_from_matrix_of_fk(sk, quat, golden_fk):
+    g = golden_fk
+    for name in SKELS:
+        par, rot, gp, off = (g[f"{name}/{k}"] for k in ("parents", "rot", "gpos", "offsets"))
+        pos, grot = sk.fk_quat(rot, gp, off, par)
+        assert_allclose(pos, g[f"{name}/pos"], **TOL)
+        want = orc.quat_from_matrix(g[f"{name}/rotm"])
+        # same rotation; sign may flip only where the branch test of from_matrix is within rounding of a tie
+        dots = np.abs(np.sum(grot * want, axis=-1))
+        assert_allclose(dots, 1.0, atol=1e-5)
+        same_sign = np.sum(grot * want, axis=-1) > 0
+        assert same_sign.mean() > 0.99
+
+
+def test_fk_on_side_stream(sk, golden_fk):
+    g = golden_fk
+    dev = torch.device("cuda")
+    par = g["body22/parents"]
+    rot, gp, off = (torch.from_numpy(g[f"body22/{k}"]).to(dev) for k in ("rot", "gpos", "offsets"))
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        pos, rotm = sk.fk(rot, gp, off, par)
+    s.synchronize()
+    assert_allclose(pos.cpu().numpy(), g["body22/pos"], **TOL)
+
+
+# ---------------------------------------------------------------- dual quaternions
+@pytest.mark.parametrize("case", ["chain3_ident", "chain3_rot"])
+def test_dq_chain3_goldens(sk, dquat, quat, golden_dq, case):
+    g = golden_dq
+    par, off, gp = g["chain3/parents"], g["chain3/offsets"], g["chain3/gpos"]
+    rot = g[f"{case}/rot"].astype(np.float32)
+    dq = sk.to_root_dual_quat(rot, gp, par, off)
+    assert dq.shape == (2, 3, 8) and dq.dtype == np.float32
+    assert_allclose(dq, g[f"{case}/dq"], **TOL)
+    rr, tt = dquat.to_rotation_translation(dq)
+    assert_allclose(tt[:, 1:], g[f"{case}/hand_root_trans"][:, 1:], atol=1e-6)  # test_skeleton.py:59, :170
+    assert_allclose(tt[:, 0], gp, atol=1e-6)
+    if case == "chain3_rot":
+        assert_allclose(rr, orc.quat_from_matrix(g["chain3_rot/hand_root_rotm"]), atol=1e-6)  # :169
+    trans, rots = sk.from_root_dual_quat(dq, par)  # (translations, rotations) order, skeleton.py:204
+    assert trans.shape == (2, 3, 3) and rots.shape == (2, 3, 4)
+    assert_allclose(rots, rot, atol=1e-6)  # :71, :184
+    assert_allclose(trans[:, 1:], np.tile(off[1:], (2, 1, 1)), atol=1e-6)
+    assert_allclose(trans[:, 0], gp, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", SKELS)
+def test_dq_skeleton_fixtures(sk, golden_dq, name):
+    g = golden_dq
+    par, rot, gp, off = (g[f"{name}/{k}"] for k in ("parents", "rot", "gpos", "offsets"))
+    dq = sk.to_root_dual_quat(rot, gp, par, off)  # slightly non-unit quaternions: no normalisation inside
+    assert_allclose(dq, g[f"{name}/dq"], **TOL)
+    trans, rots = sk.from_root_dual_quat(g[f"{name}/dq"].astype(np.float32), par)
+    assert_allclose(trans, g[f"{name}/back_trans_f32in"], **TOL)
+    assert_allclose(rots, g[f"{name}/back_rot_f32in"], **TOL)
+    # N-D leading dims use shape[-2] as the joint count (documented deviation from skeleton.py:228)
+    dq_nd = sk.to_root_dual_quat(rot.reshape((1,) + rot.shape), gp.reshape((1,) + gp.shape), par, off)
+    assert_allclose(dq_nd[0], dq, atol=0)
+
+
+@pytest.mark.parametrize("n_frames", [1, 33, 64, 65, 1000])
+def test_dq_vs_oracle_ragged(sk, n_frames):
+    for name in SKELS:
+        par = parents_of(name)
+        rot, gp, off = synth_numpy(n_frames, par, seed=300 + n_frames)
+        dq = sk.to_root_dual_quat(rot, gp, par, off)
+        want = orc.to_root_dual_quat(rot, gp, par, off)
+        assert_allclose(dq, want, **TOL)
+        trans, rots = sk.from_root_dual_quat(want.astype(np.float32), par)
+        wt, wr = orc.from_root_dual_quat(want, par)
+        assert_allclose(trans, wt, **TOL)
+        assert_allclose(rots, wr, **TOL)
+
+
+def test_dq_asserts_like_reference(sk, golden_dq):
+    g = golden_dq
+    off = g["body22/offsets"].copy()
+    off[0, 2] = 1.0
+    with pytest.raises(AssertionError):  # ops/skeleton.py:227
+        sk.to_root_dual_quat(g["body22/rot"], g["body22/gpos"], g["body22/parents"], off)
+    with pytest.raises(AssertionError):  # per-frame offsets are rejected by the same assert
+        sk.to_root_dual_quat(g["body22/rot"], g["body22/gpos"], g["body22/parents"], np.tile(g["body22/offsets"], (37, 1, 1)))
+
+
+def test_dq_round_trip_1m_x_22(sk):
+    """BASELINE config 3 at full size: to_root_dual_quat -> from_root_dual_quat gives
+    back (offsets | global_pos, rotations) -- the identity the reference test checks
+    (test_skeleton.py:70-77) -- plus the oracle on slabs."""
+    par = parents_of("body22")
+    dev = torch.device("cuda")
+    n = 1_000_000
+    rot, gp, off = synth_torch(n, par, dev, seed=99)
+    dq = sk.to_root_dual_quat(rot, gp, par, off)
+    trans, rots = sk.from_root_dual_quat(dq, par)
+    torch.cuda.synchronize()
+    assert (rots - rot).abs().amax().item() < 1e-5
+    assert (trans[:, 1:] - off[1:]).abs().amax().item() < 1e-5
+    assert (trans[:, 0] - gp).abs().amax().item() < 1e-5
+    # unit dual quaternions: |q_r| = 1, q_r . q_d = 0
+    assert (dq[..., :4].norm(dim=-1) - 1).abs().amax().item() < 1e-5
+    assert (dq[..., :4] * dq[..., 4:]).sum(-1).abs().amax().item() < 1e-5
+    off_h = off.cpu().numpy()
+    for lo in (0, 500_000, n - 100_000):
+        sl = slice(lo, lo + 100_000)
+        want = oracle_c.to_root_dual_quat(rot[sl].cpu().numpy(), gp[sl].cpu().numpy(), par, off_h)
+        assert_allclose(dq[sl].cpu().numpy(), want, **TOL)
+        wt, wr = oracle_c.from_root_dual_quat(want, par)
+        assert_allclose(trans[sl].cpu().numpy(), wt, **TOL)
+        assert_allclose(rots[sl].cpu().numpy(), wr, **TOL)
+
+
+def test_from_global_rotations(sk, golden_dq):
+    g = golden_dq
+    got = sk.from_global_rotations(g["fgr/global"], g["fgr/parents"])
+    assert_allclose(got, g["fgr/local"], **TOL)
+    # fk_quat -> from_global_rotations recovers the (normalised) local rotations up to sign
+    par = parents_of("body22")
+    rot, gp, off = synth_numpy(50, par, seed=77)
+    _, grot = sk.fk_quat(rot, gp, off, par)
+    local = sk.from_global_rotations(grot, par)
+    assert_allclose(np.abs(np.sum(local * rot, axis=-1)), 1.0, atol=1e-5)
+
+
+# ---------------------------------------------------------------- primitives
+def test_quat_primitives_vs_reference(quat, dquat, golden_quat):
+    g = golden_quat
+    q0, q1, v, qu, t = (g[f"f32/{k}"] for k in ("q0", "q1", "v", "qu", "t"))
+    assert_allclose(quat.mul(q0, q1), g["f32/mul"], **TOL)
+    assert_allclose(quat.mul(q0[:, :1], q1), g["f32/mul_bcast"], **TOL)
+    assert_allclose(quat.mul_vec(q0, v), g["f32/mul_vec"], rtol=1e-5, atol=5e-5)  # |q|^2 up to ~20 scales the result
+    assert_allclose(quat.length(q0), g["f32/length"], **TOL)
+    assert quat.length(q0).shape == (3, 41)
+    assert_allclose(quat.normalize(q0), g["f32/normalize"], **TOL)
+    assert_allclose(quat.normalize(q0, eps=1e-2), g["f32/normalize_eps"], **TOL)
+    assert_allclose(quat.conjugate(q0), g["f32/conjugate"], atol=0)
+    assert_allclose(quat.inverse(q0), g["f32/inverse"], atol=0)
+    assert_allclose(quat.to_matrix(q0), g["f32/to_matrix"], rtol=1e-5, atol=5e-5)
+    assert quat.to_matrix(q0).shape == (3, 41, 3, 3)
+    assert_allclose(quat.to_matrix(qu), g["f32/unit_matrix"], **TOL)
+    assert_allclose(quat.from_matrix(g["f32/unit_matrix"].astype(np.float32)), g["f32/from_matrix"], **TOL)
+    assert_allclose(quat.from_matrix(g["branches/matrix"].astype(np.float32)), g["branches/quat"], **TOL)
+    dq = dquat.from_rotation_translation(qu, t)
+    assert_allclose(dq, g["f32/dq"], **TOL)
+    rr, tt = dquat.to_rotation_translation(g["f32/dq"].astype(np.float32))
+    assert_allclose(rr, g["f32/dq_rot"], **TOL)
+    assert_allclose(tt, g["f32/dq_trans"], **TOL)
+    assert_allclose(tt, t, atol=1e-5)  # test_dual_quat.py:37-40 round trip
+    assert_allclose(dquat.from_translation(t), g["f32/dq_from_translation"], **TOL)
+    # hand-written goldens of rotations/tests/test_quat.py
+    assert_allclose(quat.mul(g["hand/qa"], g["hand/qb"]), g["hand/mul_ab"], atol=1e-6)
+    assert_allclose(quat.mul(g["hand/qb"], g["hand/qa"]), g["hand/mul_ba"], atol=1e-6)
+    assert_allclose(quat.mul_vec(g["hand/qa"], g["hand/v"]), g["hand/mul_vec"], atol=1e-6)
+    assert_allclose(quat.to_matrix(g["hand/qa"]), g["hand/matrix"], atol=1e-6)
+    assert_allclose(quat.from_matrix(g["hand/matrix"]), g["hand/qa"], atol=1e-6)
+
+
+def test_quat_large_flat_batch(quat):
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((300_001, 4)).astype(np.float32)
+    b = rng.standard_normal((300_001, 4)).astype(np.float32)
+    assert_allclose(quat.mul(a, b), orc.quat_mul(a, b), rtol=1e-5, atol=1e-5)
+    assert_allclose(quat.normalize(a), orc.quat_normalize(a), **TOL)
+    m = orc.quat_to_matrix(orc.quat_normalize(a)).astype(np.float32)
+    assert_allclose(quat.from_matrix(m), orc.quat_from_matrix(m), **TOL)
+
+
+def test_host_buffer_entry_point(sk, golden_fk):
+    """pmb_fk_f32_host: pinned host buffers in, host buffers out, chunked pipeline."""
+    from pymotion_b200 import _lib
+
+    lib = _lib.load()
+    par = parents_of("body22")
+    rot, gp, off = synth_numpy(10_000, par, seed=8)
+    rot_t, gp_t = torch.from_numpy(rot).pin_memory(), torch.from_numpy(gp).pin_memory()
+    pos = torch.empty((10_000, 22, 3), dtype=torch.float32).pin_memory()
+    rotm = torch.empty((10_000, 22, 3, 3), dtype=torch.float32).pin_memory()
+    rc = lib.pmb_fk_f32_host(rot_t.data_ptr(), gp_t.data_ptr(), off.ctypes.data, par.ctypes.data, 10_000, 22,
+                             pos.data_ptr(), rotm.data_ptr(), 3000)  # ragged chunks: 3008, 3008, 3008, 976
+    _lib.check(rc)
+    want_pos, want_rotm = orc.fk(rot, gp, off, par)
+    assert_allclose(pos.numpy(), want_pos, **TOL)
+    assert_allclose(rotm.numpy(), want_rotm, **TOL)
+    lib.pmb_release_workspace()

@@ -263,6 +263,18 @@ def run_ours(args):
     ms_max = float(t.item())
     value = world * frames * args.steps / (ms_max * 1e-3)
 
+    if args.kernel_only:
+        if rank == 0:
+            bytes_per_launch = fk_bytes_per_pose(n_joints) * frames
+            kernel_ms = ms_max / args.steps
+            print(json.dumps({"workload": args.workload, "ms_per_step": kernel_ms, "value": value,
+                              "GBps": bytes_per_launch / (kernel_ms * 1e-3) / 1e9,
+                              "env_chunk": os.environ.get("PMB_FK_CHUNK")}), flush=True)
+        sampler.stop_flag.set()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- end to end through the public host-buffer API (pinned host memory both ways)
     e2e_steps = max(1, min(args.steps, 5))
     h_rot = torch.empty((frames, n_joints, 4), dtype=torch.float32, pin_memory=True).copy_(rot)
@@ -370,6 +382,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fk_1m_x_22", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="development: skip the e2e and CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,8 +1,10 @@
 // extern "C" entry points of libpymotion_b200.so (see include/pymotion_b200.h).
 // Host side only validates, builds the joint program, picks a launch
 // configuration and launches; nothing here computes on the CPU.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -86,6 +88,44 @@ int set_smem(K kernel, int bytes) {
     return PMB_OK;
 }
 
+// ---- TMA descriptor for the quaternion input -------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_fn(EncodeTiledFn &out) {
+    static std::mutex mu;
+    static EncodeTiledFn cached = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!cached) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        PMB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(PMB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        cached = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    out = cached;
+    return PMB_OK;
+}
+
+// rot viewed as a 2-D float tensor [n_frames][4 * n_joints]; box = 32 frames x C joints, hardware swizzle
+// matched to the box row (64 B for C = 4, 128 B for C = 8) so thread-per-frame 16-byte reads are conflict free.
+int make_rot_map(CUtensorMap &tm, const float *rot, int64_t n_frames, int32_t n_joints, int chunk) {
+    EncodeTiledFn enc;
+    int rc = encode_fn(enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(4) * n_joints, static_cast<cuuint64_t>(n_frames)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(16) * n_joints};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(4 * chunk), 32};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = chunk == 8 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(rot), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PMB_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+    return PMB_OK;
+}
+
 // ---- fk launch ----------------------------------------------------------------
 struct FkArgs {
     const float *rot, *gpos, *offsets;
@@ -97,53 +137,46 @@ struct FkArgs {
     cudaStream_t stream;
 };
 
-template <int C, int WARPS, bool PF, bool QO>
-int launch_fk_cfg(const FkArgs &a, int smem) {
-    auto kernel = pmb::fk_chain_kernel<C, WARPS, PF, QO>;
+template <int C, int WARPS, int VEC, bool PF, bool QO>
+int launch_fk_cfg(const FkArgs &a) {
+    using Tile = pmb::FkTile<C, VEC, QO ? 4 : 9>;
+    auto kernel = pmb::fk_chain_kernel<C, WARPS, VEC, PF, QO>;
+    const int smem = Tile::block_bytes(WARPS, a.n_joints, a.n_slots);
     int rc = set_smem(kernel, smem);
     if (rc) return rc;
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, C))) return rc;
     const long long tiles = (a.n_frames + 31) / 32;
     const long long blocks = (tiles + WARPS - 1) / WARPS;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
-    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(
-        reinterpret_cast<const float4 *>(a.rot), a.gpos, a.gstride, a.offsets, a.ostride, a.pos, a.rout, a.n_frames,
-        a.n_joints, a.n_slots, *a.prog);
+    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.ostride,
+                                                                        a.pos, a.rout, a.n_frames, a.n_joints,
+                                                                        a.n_slots, *a.prog);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
 
-template <int RW>
-int fk_smem(int C, int warps, int n_joints, int n_slots) {
-    const int tab = (n_joints * 16 + 127) & ~127;
-    const int sr = (RW * C) | 1, sp = (3 * C) | 1;
-    return tab + warps * (32 * (sr + sp) * 4 + n_slots * 3 * 32 * 16);
+template <int C, int VEC, bool PF, bool QO>
+int launch_fk_warps(const FkArgs &a, const DeviceProps &dp) {
+    using Tile = pmb::FkTile<C, VEC, QO ? 4 : 9>;
+    if (Tile::block_bytes(4, a.n_joints, a.n_slots) <= dp.smem_optin) return launch_fk_cfg<C, 4, VEC, PF, QO>(a);
+    if (Tile::block_bytes(1, a.n_joints, a.n_slots) <= dp.smem_optin) return launch_fk_cfg<C, 1, VEC, PF, QO>(a);
+    return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
 }
 
 template <bool PF, bool QO>
 int launch_fk(const FkArgs &a, const DeviceProps &dp) {
-    constexpr int RW = QO ? 4 : 9;
-    // Pick the joints-per-chunk C and warps per block that keep the most warps resident
-    // (shared memory is the limiter: 48*C bytes of staging + 48 bytes per slot per frame).
-    static const int kC[3] = {7, 5, 3};
-    int best_c = 0, best_w = 0, best_res = -1, best_smem = 0;
-    for (int ci = 0; ci < 3; ++ci) {
-        for (int w = 4; w >= 1; w >>= 1) {
-            const int smem = fk_smem<RW>(kC[ci], w, a.n_joints, a.n_slots);
-            if (smem > dp.smem_optin) continue;
-            const int blocks = std::min(32, (228 * 1024) / (smem + 1024));
-            const int res = std::min(blocks * w, 20);  // beyond ~20 warps registers are the limit anyway
-            if (res > best_res) best_res = res, best_c = kC[ci], best_w = w, best_smem = smem;
-        }
+    // 64-bit staging / stores need 8-byte aligned rows: even joint count.
+    const bool vec2 = (a.n_joints % 2) == 0;
+    // Joints per chunk.  Measured on B200 (1M x 22, 4M x 52, 4M x 65): 8 beats 4 by 25-50 % -- fewer TMA
+    // round trips and barriers per frame outweigh the larger remainder chunk and the lower occupancy.
+    int chunk = 8;
+    if (const char *env = getenv("PMB_FK_CHUNK")) {
+        const int v = atoi(env);
+        if (v == 4 || v == 8) chunk = v;
     }
-    if (best_res <= 0)
-        return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
-#define PMB_FK_CASE(CC, WW) \
-    if (best_c == CC && best_w == WW) return launch_fk_cfg<CC, WW, PF, QO>(a, best_smem);
-    PMB_FK_CASE(7, 4) PMB_FK_CASE(7, 2) PMB_FK_CASE(7, 1)
-    PMB_FK_CASE(5, 4) PMB_FK_CASE(5, 2) PMB_FK_CASE(5, 1)
-    PMB_FK_CASE(3, 4) PMB_FK_CASE(3, 2) PMB_FK_CASE(3, 1)
-#undef PMB_FK_CASE
-    return fail(PMB_ERR_CUDA, "no fk configuration selected");
+    if (chunk == 8) return vec2 ? launch_fk_warps<8, 2, PF, QO>(a, dp) : launch_fk_warps<8, 1, PF, QO>(a, dp);
+    return vec2 ? launch_fk_warps<4, 2, PF, QO>(a, dp) : launch_fk_warps<4, 1, PF, QO>(a, dp);
 }
 
 int fk_common(const float *rot, const float *gpos, int64_t gstride, const float *offsets, int64_t ostride,
@@ -151,11 +184,12 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
               bool quat_out, void *stream) {
     if (!rot || !gpos || !offsets || !pos || !rout) return fail(PMB_ERR_NULL, "fk: NULL array pointer");
     if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
+    if (n_frames > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames must be below 2^31 per call");
     if (gstride != 0 && gstride != 3) return fail(PMB_ERR_SHAPE, "gpos_frame_stride must be 0 or 3");
     if (ostride != 0 && ostride != 3LL * n_joints)
         return fail(PMB_ERR_SHAPE, "offsets_frame_stride must be 0 or 3*n_joints");
     if (!aligned16(rot)) return fail(PMB_ERR_ALIGN, "rot must be 16-byte aligned");
-    if (quat_out && !aligned16(rout)) return fail(PMB_ERR_ALIGN, "global_rots must be 16-byte aligned");
+    if (!aligned16(rout) || !aligned16(pos)) return fail(PMB_ERR_ALIGN, "output arrays must be 16-byte aligned");
     pmb::JointProgram prog;
     int n_slots = 0;
     int rc = check_program(parents_host, n_joints, false, prog, n_slots);

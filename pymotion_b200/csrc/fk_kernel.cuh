@@ -1,52 +1,182 @@
 // Forward kinematics, one fused kernel (ops/skeleton.py:16-61 of the reference).
 //
-// Mapping: one THREAD per frame, one WARP per tile of 32 consecutive frames.
-//   * the joint table (offsets + per-joint program word) is staged in shared
-//     memory once per block;
-//   * a thread streams its frame's quaternions from HBM as float4 (C joints =
-//     C independent 16-byte loads in flight per thread), normalises, builds the
-//     local 3x3 and composes it with its parent's global transform, which is
-//     either still in registers (parent == previous joint: the chain case) or in
-//     a per-warp shared-memory slot written when the parent was computed (branch
-//     points of the tree; slots are allocated on the host, see joint_program.cuh);
-//   * results of C joints are staged in a per-warp shared-memory tile with an
-//     ODD row stride (conflict-free for the thread-per-frame writes), then
-//     written to HBM as fully coalesced 128-byte runs by the whole warp.
-// Warps never synchronise with each other after the table load: each walks its
-// own load / compose / store phases so the SM overlaps them across warps.
+// Mapping: one THREAD per frame, one WARP per tile of 32 consecutive frames; warps
+// are autonomous (own staging buffers, own mbarrier) so load / compose / store
+// phases of different warps overlap on the SM.
 //
-// Algorithmic HBM traffic: 64*J + 12 bytes per pose (16J in, 48J + 12 ... out),
+//   in   the tile's quaternions arrive chunk by chunk (C joints x 32 frames) through
+//        TMA (cp.async.bulk.tensor.2d, hardware swizzle so the thread-per-frame
+//        16-byte reads are bank-conflict free); the copy of chunk c+1 is in flight
+//        while chunk c is composed;
+//   walk the joint table (offsets + per-joint program word) sits in shared memory;
+//        a thread composes joint after joint in registers; the parent transform is
+//        either still in registers (parent == previous joint, the chain case) or in
+//        a per-warp shared-memory slot written when the parent was computed (branch
+//        points of the tree; slots are allocated on the host, joint_program.h);
+//   out  the C joints' results are staged per warp in shared memory with a row
+//        stride that makes the thread-per-frame writes conflict free, then written
+//        to HBM by the whole warp as fully coalesced 128/256-byte runs (64-bit
+//        accesses when the joint count is even, i.e. rows are 8-byte aligned).
+//        The (row, column) a lane serves repeats with a short period, so the lane's
+//        offsets are computed once per chunk and each store costs LDS + STG only.
+//
+// Algorithmic HBM traffic: 64*J + 12 bytes per pose (16J + 12 in, 12J + 36J out),
 // no scratch in global memory.  See DESIGN.md for the roofline.
 #pragma once
+#include <cuda.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pmb {
 
-template <int C, int RW>
+// ---- mbarrier / TMA (PTX) -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+
+__host__ __device__ constexpr int ce_gcd(int a, int b) { return b == 0 ? a : ce_gcd(b, a % b); }
+__host__ __device__ constexpr int ce_lcm(int a, int b) { return a / ce_gcd(a, b) * b; }
+
+// Shared-memory geometry of one warp's buffers, shared by host (sizing) and device.
+template <int C, int VEC, int RW>
 struct FkTile {
-    static constexpr int SR = (RW * C) | 1;  // row stride (words) of the rotation stage, odd
-    static constexpr int SP = (3 * C) | 1;   // row stride (words) of the position stage, odd
-    static constexpr int kStageBytesPerWarp = kWarp * (SR + SP) * 4;
-    static constexpr int kSlotBytesPerWarp = 3 * kWarp * 16;  // one slot = 12 floats x 32 lanes
-    __host__ __device__ static constexpr int warp_bytes(int n_slots) {
-        return kStageBytesPerWarp + n_slots * kSlotBytesPerWarp;
+    static constexpr int WR = RW * C, WP = 3 * C;  // words per full piece of a row
+    // row stride (words): VEC == 1 -> odd; VEC == 2 -> even with an odd number of 8-byte pairs
+    __host__ __device__ static constexpr int pad(int w) { return VEC == 1 ? (w | 1) : (((w / 2) & 1) ? w : w + 2); }
+    static constexpr int SR = pad(WR), SP = pad(WP);
+    static constexpr int kInBytes = kWarp * C * 16;            // TMA box, dense (swizzled) [32][C] float4
+    static constexpr int kStageBytes = kWarp * (SR + SP) * 4;
+    static constexpr int kSlotBytes = 3 * kWarp * 16;          // one slot = 12 floats x 32 lanes
+    __host__ __device__ static constexpr int warp_bytes(int n_slots) { return kStageBytes + n_slots * kSlotBytes; }
+    // total dynamic shared memory of a block (1 KB slack to align the TMA buffers to 1024)
+    __host__ __device__ static constexpr int block_bytes(int warps, int n_joints, int n_slots) {
+        return 1024 + warps * kInBytes + ((n_joints * 16 + 127) & ~127) + warps * warp_bytes(n_slots) + warps * 8 +
+               warps * kWarp * 4;
     }
 };
 
-// QUAT_OUT = false: rout is rotmats [F][J][9];  true: rout is global quaternions [F][J][4].
-template <int C, int WARPS, bool PF_OFFSETS, bool QUAT_OUT>
+// Warp-cooperative copy of a FULL stage (32 rows x W words, row stride S) to global rows of pitch
+// `pitch` words, in units of VEC words.  Store k of the warp serves flat unit 32k + lane -> (row,
+// column); that map repeats every P stores / RPP rows, so a lane computes its P offsets once and each
+// store costs LDS + STG.
+template <int W, int S, int VEC>
+__device__ __forceinline__ void copy_out_periodic(const float *__restrict__ stage, float *__restrict__ gtile, int pitch,
+                                                  int lane) {
+    constexpr int WV = W / VEC;
+    constexpr int L = ce_lcm(32, WV);
+    constexpr int P = L / 32;     // stores per period
+    constexpr int RPP = L / WV;   // rows per period
+    static_assert(32 % RPP == 0 && P <= 9, "chunk geometry must give a short period");
+    using V = typename std::conditional<VEC == 2, float2, float>::type;
+    int soff[P], goff[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        const int i = 32 * k + lane;
+        const int dr = i / WV, col = i - dr * WV;
+        soff[k] = dr * S + col * VEC;
+        goff[k] = dr * pitch + col * VEC;
+    }
+#pragma unroll
+    for (int g = 0; g < 32 / RPP; ++g) {
+        V v[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) v[k] = *reinterpret_cast<const V *>(stage + g * RPP * S + soff[k]);
+        float *gp = gtile + static_cast<long long>(g * RPP) * pitch;
+#pragma unroll
+        for (int k = 0; k < P; ++k) __stcs(reinterpret_cast<V *>(gp + goff[k]), v[k]);
+    }
+}
+
+// Remainder chunk (w < W words per row) and remainder tile (nrows < 32): one row at a time, lanes
+// across the row.  MAXU = column slots a lane may serve.
+template <int WMAX, int S, int VEC>
+__device__ __forceinline__ void copy_out_rows(const float *__restrict__ stage, float *__restrict__ gtile, int pitch,
+                                              int nrows, int w, int lane) {
+    using V = typename std::conditional<VEC == 2, float2, float>::type;
+    constexpr int MAXU = (WMAX / VEC + 31) / 32;
+    const int wv = w / VEC;
+    const V *sp = reinterpret_cast<const V *>(stage) + lane;
+    V *gp = reinterpret_cast<V *>(gtile) + lane;
+#pragma unroll 4
+    for (int r = 0; r < nrows; ++r) {
+        V v[MAXU];
+#pragma unroll
+        for (int u = 0; u < MAXU; ++u)
+            if (lane + 32 * u < wv) v[u] = sp[32 * u];
+#pragma unroll
+        for (int u = 0; u < MAXU; ++u)
+            if (lane + 32 * u < wv) __stcs(gp + 32 * u, v[u]);
+        sp += S / VEC;
+        gp += pitch / VEC;
+    }
+}
+
+// QO = false: rout is rotmats [F][J][9];  true: rout is global quaternions [F][J][4].
+template <int C, int WARPS, int VEC, bool PF_OFFSETS, bool QO>
 __global__ void __launch_bounds__(WARPS *kWarp)
-fk_chain_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, long long gstride,
+fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                 const float *__restrict__ offsets, long long ostride, float *__restrict__ pos,
                 float *__restrict__ rout, long long n_frames, int n_joints, int n_slots,
                 const __grid_constant__ JointProgram prog) {
-    constexpr int RW = QUAT_OUT ? 4 : 9;
-    using Tile = FkTile<C, RW>;
+    constexpr int RW = QO ? 4 : 9;
+    using Tile = FkTile<C, VEC, RW>;
     constexpr int SR = Tile::SR, SP = Tile::SP;
+    static_assert(C == 4 || C == 8, "swizzle decode below assumes a 64- or 128-byte TMA box row");
+    static_assert(VEC == 1 || (C % 2 == 0), "64-bit staging needs an even chunk");
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *tab = reinterpret_cast<float4 *>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    // align by OFFSETTING the array (pointer arithmetic keeps the shared address space; an integer round trip
+    // would demote every access below to generic LD/ST)
+    unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+
+    float4 *in_stage = reinterpret_cast<float4 *>(smem_raw + warp * Tile::kInBytes);
+    float4 *tab = reinterpret_cast<float4 *>(smem_raw + WARPS * Tile::kInBytes);
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(tab) + ((n_joints * 16 + 127) & ~127) + warp * Tile::warp_bytes(n_slots);
+    float *Rst = reinterpret_cast<float *>(wbase);
+    float *Pst = Rst + kWarp * SR;
+    float4 *slots = reinterpret_cast<float4 *>(Pst + kWarp * SP);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(tab) + ((n_joints * 16 + 127) & ~127) +
+                                                  WARPS * Tile::warp_bytes(n_slots));
+    const uint32_t bar = smem_u32(bars + warp);
+    const uint32_t fence_word = smem_u32(reinterpret_cast<uint32_t *>(bars + WARPS) + threadIdx.x);  // see the chunk loop
+
+    const long long f0 = (static_cast<long long>(blockIdx.x) * WARPS + warp) * kWarp;
+    const bool active = f0 < n_frames;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (active && lane == 0) {  // first chunk's quaternions: in flight while the block loads its joint table
+        mbar_arrive_expect_tx(bar, Tile::kInBytes);
+        tma_load_2d(smem_u32(in_stage), &tm_rot, 0, static_cast<int>(f0), bar);
+    }
     for (int j = threadIdx.x; j < n_joints; j += WARPS * kWarp) {
         float4 e;
         if (PF_OFFSETS) {
@@ -58,28 +188,47 @@ fk_chain_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, 
         tab[j] = e;
     }
     __syncthreads();
+    if (!active) return;
 
-    const long long f0 = (static_cast<long long>(blockIdx.x) * WARPS + warp) * kWarp;
-    if (f0 >= n_frames) return;
     const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
     const long long f = f0 + min(lane, nrows - 1);  // tail lanes recompute the last frame, never stored
-
-    unsigned char *wbase = smem_raw + ((n_joints * 16 + 127) & ~127) + warp * Tile::warp_bytes(n_slots);
-    float *Rst = reinterpret_cast<float *>(wbase);
-    float *Pst = Rst + kWarp * SR;
-    float4 *slots = reinterpret_cast<float4 *>(Pst + kWarp * SP);
-
-    const float4 *qrow = rot + f * n_joints;
     const float *orow = PF_OFFSETS ? offsets + f * ostride : nullptr;
+    // TMA swizzle: 16-byte chunk jj of row r lands at chunk jj ^ x (128B mode: x = r & 7; 64B mode: x = (r >> 1) & 3)
+    const int swz = (C == 8) ? (lane & 7) : ((lane >> 1) & 3);
+    const float4 *in_row = in_stage + lane * C;
+    const int rpitch = n_joints * RW, ppitch = n_joints * 3;
+
     Xform<float> cur;
+    {
+        const float *g = gpos + f * gstride;
+        cur.p[0] = __ldg(g), cur.p[1] = __ldg(g + 1), cur.p[2] = __ldg(g + 2);
+    }
+    uint32_t phase = 0;
 
     for (int c0 = 0; c0 < n_joints; c0 += C) {
         const int cnt = min(C, n_joints - c0);
+        mbar_wait(bar, phase);
+        phase ^= 1;
         float4 q[C];
 #pragma unroll
-        for (int jj = 0; jj < C; ++jj)
-            if (jj < cnt) q[jj] = __ldg(qrow + c0 + jj);
+        for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
+        // The refill below goes through the async proxy and is not ordered after shared-memory loads that
+        // have merely been ISSUED (measured: ~1e-5 of the tiles read the next chunk's data).  A store whose
+        // operand depends on every loaded register cannot issue before all of them have landed, and the TMA
+        // instruction issues after it.
+        {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int jj = 0; jj < C; ++jj) acc |= __float_as_uint(q[jj].x) | __float_as_uint(q[jj].w);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
+        }
+        __syncwarp();  // every lane has its quaternions in registers: the buffer can be refilled
+        if (c0 + C < n_joints && lane == 0) {
+            mbar_arrive_expect_tx(bar, Tile::kInBytes);
+            tma_load_2d(smem_u32(in_stage), &tm_rot, 4 * (c0 + C), static_cast<int>(f0), bar);
+        }
 
+        float carry_r = 0.f, carry_p = 0.f;  // VEC == 2: odd word waiting for its 8-byte partner
 #pragma unroll
         for (int jj = 0; jj < C; ++jj) {
             if (jj < cnt) {
@@ -94,9 +243,7 @@ fk_chain_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, 
                 q_to_matrix(q_normalize(Quat<float>{q[jj].x, q[jj].y, q[jj].z, q[jj].w}, 1e-8f), l);
                 if (jj == 0 && c0 == 0) {
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) cur.r[k] = l[k];
-                    const float *g = gpos + f * gstride;
-                    cur.p[0] = __ldg(g), cur.p[1] = __ldg(g + 1), cur.p[2] = __ldg(g + 2);
+                    for (int k = 0; k < 9; ++k) cur.r[k] = l[k];  // root: [R | global_pos] (skeleton.py:49)
                 } else {
                     const uint32_t src = prog_src(code);
                     if (src != kSrcReg) {  // warp-uniform: every lane runs the same program
@@ -115,33 +262,51 @@ fk_chain_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, 
                     s[kWarp] = make_float4(cur.r[4], cur.r[5], cur.r[6], cur.r[7]);
                     s[2 * kWarp] = make_float4(cur.r[8], cur.p[0], cur.p[1], cur.p[2]);
                 }
-                float *rs = Rst + lane * SR + RW * jj;
-                if (QUAT_OUT) {
+                float o[RW];
+                if (QO) {
                     const Quat<float> gq = q_from_matrix(cur.r);
-                    rs[0] = gq.w, rs[1] = gq.x, rs[2] = gq.y, rs[3] = gq.z;
+                    o[0] = gq.w, o[1] = gq.x, o[2] = gq.y, o[3] = gq.z;
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) rs[k] = cur.r[k];
+                    for (int k = 0; k < RW; ++k) o[k] = cur.r[k];
                 }
+                float *rs = Rst + lane * SR + RW * jj;
                 float *ps = Pst + lane * SP + 3 * jj;
-                ps[0] = cur.p[0], ps[1] = cur.p[1], ps[2] = cur.p[2];
+                if (VEC == 1) {
+#pragma unroll
+                    for (int k = 0; k < RW; ++k) rs[k] = o[k];
+                    ps[0] = cur.p[0], ps[1] = cur.p[1], ps[2] = cur.p[2];
+                } else {
+                    // 8-byte stores; a row piece starts 8-byte aligned and joints alternate parity when RW is odd
+                    if ((RW * jj) % 2 == 0) {
+#pragma unroll
+                        for (int k = 0; k + 1 < RW; k += 2) *reinterpret_cast<float2 *>(rs + k) = make_float2(o[k], o[k + 1]);
+                        if (RW % 2) carry_r = o[RW - 1];
+                    } else {
+                        *reinterpret_cast<float2 *>(rs - 1) = make_float2(carry_r, o[0]);
+#pragma unroll
+                        for (int k = 1; k + 1 < RW; k += 2) *reinterpret_cast<float2 *>(rs + k) = make_float2(o[k], o[k + 1]);
+                    }
+                    if ((3 * jj) % 2 == 0) {
+                        *reinterpret_cast<float2 *>(ps) = make_float2(cur.p[0], cur.p[1]);
+                        carry_p = cur.p[2];
+                    } else {
+                        *reinterpret_cast<float2 *>(ps - 1) = make_float2(carry_p, cur.p[0]);
+                        *reinterpret_cast<float2 *>(ps + 1) = make_float2(cur.p[1], cur.p[2]);
+                    }
+                }
             }
         }
         __syncwarp();
 
-        // coalesced copy-out: each warp store covers one contiguous run of a frame's row
-        const int wr = RW * cnt, wp = 3 * cnt;
-        float *rg = rout + (f0 * n_joints + c0) * RW + lane;
-        float *pg = pos + (f0 * n_joints + c0) * 3 + lane;
-        const long long rrow = static_cast<long long>(n_joints) * RW, prow = static_cast<long long>(n_joints) * 3;
-        const float *rsm = Rst + lane, *psm = Pst + lane;
-#pragma unroll 4
-        for (int r = 0; r < nrows; ++r) {
-#pragma unroll
-            for (int u = 0; u < (RW * C + 31) / 32; ++u)
-                if (lane + 32 * u < wr) __stcs(rg + 32 * u, rsm[32 * u]);
-            if (lane < wp) __stcs(pg, psm[0]);
-            rg += rrow, pg += prow, rsm += SR, psm += SP;
+        float *rg = rout + (f0 * n_joints + c0) * RW;
+        float *pg = pos + (f0 * n_joints + c0) * 3;
+        if (cnt == C && nrows == kWarp) {
+            copy_out_periodic<RW * C, SR, VEC>(Rst, rg, rpitch, lane);
+            copy_out_periodic<3 * C, SP, VEC>(Pst, pg, ppitch, lane);
+        } else {  // VEC == 2 only ever sees even counts (even joint count, even C)
+            copy_out_rows<RW * C, SR, VEC>(Rst, rg, rpitch, nrows, RW * cnt, lane);
+            copy_out_rows<3 * C, SP, VEC>(Pst, pg, ppitch, nrows, 3 * cnt, lane);
         }
         __syncwarp();
     }

@@ -138,7 +138,7 @@ struct FkArgs {
 };
 
 template <int C, int WARPS, int VEC, bool PF, bool QO>
-int launch_fk_cfg(const FkArgs &a) {
+int launch_fk_cfg(const FkArgs &a, int sm_count) {
     using Tile = pmb::FkTile<C, VEC, QO ? 4 : 9>;
     auto kernel = pmb::fk_chain_kernel<C, WARPS, VEC, PF, QO>;
     const int smem = Tile::block_bytes(WARPS, a.n_joints, a.n_slots);
@@ -146,12 +146,18 @@ int launch_fk_cfg(const FkArgs &a) {
     if (rc) return rc;
     CUtensorMap tm;
     if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, C))) return rc;
+    // persistent grid: as many blocks as are resident at once; warps walk the tiles round robin
     const long long tiles = (a.n_frames + 31) / 32;
-    const long long blocks = (tiles + WARPS - 1) / WARPS;
-    if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
+    int per_sm = 0;
+    PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk kernel does not fit on an SM (%d bytes of shared memory)", smem);
+    if (const char *env = getenv("PMB_FK_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(env)));
+    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * sm_count);
+    int stagger_ns = 0;
+    if (const char *env = getenv("PMB_FK_STAGGER_NS")) stagger_ns = atoi(env);
     kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.ostride,
                                                                         a.pos, a.rout, a.n_frames, a.n_joints,
-                                                                        a.n_slots, *a.prog);
+                                                                        a.n_slots, stagger_ns, *a.prog);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
@@ -159,8 +165,8 @@ int launch_fk_cfg(const FkArgs &a) {
 template <int C, int VEC, bool PF, bool QO>
 int launch_fk_warps(const FkArgs &a, const DeviceProps &dp) {
     using Tile = pmb::FkTile<C, VEC, QO ? 4 : 9>;
-    if (Tile::block_bytes(4, a.n_joints, a.n_slots) <= dp.smem_optin) return launch_fk_cfg<C, 4, VEC, PF, QO>(a);
-    if (Tile::block_bytes(1, a.n_joints, a.n_slots) <= dp.smem_optin) return launch_fk_cfg<C, 1, VEC, PF, QO>(a);
+    if (Tile::block_bytes(4, a.n_joints, a.n_slots) <= dp.smem_optin) return launch_fk_cfg<C, 4, VEC, PF, QO>(a, dp.sm_count);
+    if (Tile::block_bytes(1, a.n_joints, a.n_slots) <= dp.smem_optin) return launch_fk_cfg<C, 1, VEC, PF, QO>(a, dp.sm_count);
     return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
 }
 

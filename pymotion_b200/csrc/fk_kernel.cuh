@@ -29,7 +29,23 @@
 
 #include "common.cuh"
 
+#ifndef PMB_ST_POLICY
+#define PMB_ST_POLICY 0
+#endif
+
 namespace pmb {
+
+// Output store policy (measured): 0 = default (write-back, normal L2 priority),
+// 1 = .cs streaming / evict-first.
+template <typename V>
+__device__ __forceinline__ void out_store(V *p, const V &v) {
+#if PMB_ST_POLICY == 1
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+#define PMB_ST(p, v) out_store(p, v)
 
 // ---- mbarrier / TMA (PTX) -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -108,7 +124,7 @@ __device__ __forceinline__ void copy_out_periodic(const float *__restrict__ stag
         for (int k = 0; k < P; ++k) v[k] = *reinterpret_cast<const V *>(stage + g * RPP * S + soff[k]);
         float *gp = gtile + static_cast<long long>(g * RPP) * pitch;
 #pragma unroll
-        for (int k = 0; k < P; ++k) __stcs(reinterpret_cast<V *>(gp + goff[k]), v[k]);
+        for (int k = 0; k < P; ++k) PMB_ST(reinterpret_cast<V *>(gp + goff[k]), v[k]);
     }
 }
 
@@ -130,7 +146,7 @@ __device__ __forceinline__ void copy_out_rows(const float *__restrict__ stage, f
             if (lane + 32 * u < wv) v[u] = sp[32 * u];
 #pragma unroll
         for (int u = 0; u < MAXU; ++u)
-            if (lane + 32 * u < wv) __stcs(gp + 32 * u, v[u]);
+            if (lane + 32 * u < wv) PMB_ST(gp + 32 * u, v[u]);
         sp += S / VEC;
         gp += pitch / VEC;
     }
@@ -138,10 +154,10 @@ __device__ __forceinline__ void copy_out_rows(const float *__restrict__ stage, f
 
 // QO = false: rout is rotmats [F][J][9];  true: rout is global quaternions [F][J][4].
 template <int C, int WARPS, int VEC, bool PF_OFFSETS, bool QO>
-__global__ void __launch_bounds__(WARPS *kWarp)
+__global__ void __launch_bounds__(WARPS *kWarp, (WARPS == 4 ? (C == 8 ? 3 : 4) : 1))  // shared memory allows no more anyway
 fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                 const float *__restrict__ offsets, long long ostride, float *__restrict__ pos,
-                float *__restrict__ rout, long long n_frames, int n_joints, int n_slots,
+                float *__restrict__ rout, long long n_frames, int n_joints, int n_slots, int stagger_ns,
                 const __grid_constant__ JointProgram prog) {
     constexpr int RW = QO ? 4 : 9;
     using Tile = FkTile<C, VEC, RW>;
@@ -166,16 +182,18 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     const uint32_t bar = smem_u32(bars + warp);
     const uint32_t fence_word = smem_u32(reinterpret_cast<uint32_t *>(bars + WARPS) + threadIdx.x);  // see the chunk loop
 
-    const long long f0 = (static_cast<long long>(blockIdx.x) * WARPS + warp) * kWarp;
-    const bool active = f0 < n_frames;
+    // Persistent warps: tile t, t + stride, ... (all tiles cost the same, so a static round robin balances).
+    const long long n_tiles = (n_frames + kWarp - 1) / kWarp;
+    const long long tile_stride = static_cast<long long>(gridDim.x) * WARPS;
+    long long tile = static_cast<long long>(blockIdx.x) * WARPS + warp;
     if (lane == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
     }
     __syncwarp();
-    if (active && lane == 0) {  // first chunk's quaternions: in flight while the block loads its joint table
+    if (tile < n_tiles && lane == 0) {  // first chunk's quaternions: in flight while the block loads its joint table
         mbar_arrive_expect_tx(bar, Tile::kInBytes);
-        tma_load_2d(smem_u32(in_stage), &tm_rot, 0, static_cast<int>(f0), bar);
+        tma_load_2d(smem_u32(in_stage), &tm_rot, 0, static_cast<int>(tile * kWarp), bar);
     }
     for (int j = threadIdx.x; j < n_joints; j += WARPS * kWarp) {
         float4 e;
@@ -188,22 +206,30 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
         tab[j] = e;
     }
     __syncthreads();
-    if (!active) return;
+    if (stagger_ns > 0) {  // de-phase the persistent warps of an SM (they would otherwise load / compute / store in lockstep)
+        const int rank = static_cast<int>(blockIdx.x / 148u) * WARPS + warp;
+        __nanosleep(static_cast<unsigned>(rank * stagger_ns));
+    }
 
-    const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
-    const long long f = f0 + min(lane, nrows - 1);  // tail lanes recompute the last frame, never stored
-    const float *orow = PF_OFFSETS ? offsets + f * ostride : nullptr;
     // TMA swizzle: 16-byte chunk jj of row r lands at chunk jj ^ x (128B mode: x = r & 7; 64B mode: x = (r >> 1) & 3)
     const int swz = (C == 8) ? (lane & 7) : ((lane >> 1) & 3);
     const float4 *in_row = in_stage + lane * C;
     const int rpitch = n_joints * RW, ppitch = n_joints * 3;
-
-    Xform<float> cur;
-    {
-        const float *g = gpos + f * gstride;
-        cur.p[0] = __ldg(g), cur.p[1] = __ldg(g + 1), cur.p[2] = __ldg(g + 2);
-    }
     uint32_t phase = 0;
+    // root position of the warp's NEXT tile, fetched one chunk early like its quaternions
+    float gnext[3] = {0.f, 0.f, 0.f};
+    if (tile < n_tiles) {
+        const float *g = gpos + min(tile * kWarp + lane, n_frames - 1) * gstride;
+        gnext[0] = __ldg(g), gnext[1] = __ldg(g + 1), gnext[2] = __ldg(g + 2);
+    }
+
+    for (; tile < n_tiles; tile += tile_stride) {
+    const long long f0 = tile * kWarp;
+    const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
+    const long long f = f0 + min(lane, nrows - 1);  // tail lanes recompute the last frame, never stored
+    const float *orow = PF_OFFSETS ? offsets + f * ostride : nullptr;
+    Xform<float> cur;
+    cur.p[0] = gnext[0], cur.p[1] = gnext[1], cur.p[2] = gnext[2];
 
     for (int c0 = 0; c0 < n_joints; c0 += C) {
         const int cnt = min(C, n_joints - c0);
@@ -223,9 +249,19 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
         }
         __syncwarp();  // every lane has its quaternions in registers: the buffer can be refilled
-        if (c0 + C < n_joints && lane == 0) {
-            mbar_arrive_expect_tx(bar, Tile::kInBytes);
-            tma_load_2d(smem_u32(in_stage), &tm_rot, 4 * (c0 + C), static_cast<int>(f0), bar);
+        if (lane == 0) {
+            // next chunk of this tile, or the first chunk of the warp's next tile (hides the tile-start latency)
+            const bool more = c0 + C < n_joints;
+            const long long nt = tile + tile_stride;
+            if (more || nt < n_tiles) {
+                mbar_arrive_expect_tx(bar, Tile::kInBytes);
+                tma_load_2d(smem_u32(in_stage), &tm_rot, more ? 4 * (c0 + C) : 0,
+                            static_cast<int>(more ? f0 : nt * kWarp), bar);
+            }
+        }
+        if (c0 + C >= n_joints && tile + tile_stride < n_tiles) {
+            const float *g = gpos + min((tile + tile_stride) * kWarp + lane, n_frames - 1) * gstride;
+            gnext[0] = __ldg(g), gnext[1] = __ldg(g + 1), gnext[2] = __ldg(g + 2);
         }
 
         float carry_r = 0.f, carry_p = 0.f;  // VEC == 2: odd word waiting for its 8-byte partner
@@ -310,6 +346,7 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
         }
         __syncwarp();
     }
+    }  // tiles
 }
 
 }  // namespace pmb

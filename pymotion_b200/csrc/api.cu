@@ -137,52 +137,71 @@ struct FkArgs {
     cudaStream_t stream;
 };
 
-template <int C, int WARPS, int VEC, bool PF, bool QO>
-int launch_fk_cfg(const FkArgs &a, int sm_count) {
-    using Tile = pmb::FkTile<C, VEC, QO ? 4 : 9>;
-    auto kernel = pmb::fk_chain_kernel<C, WARPS, VEC, PF, QO>;
-    const int smem = Tile::block_bytes(WARPS, a.n_joints, a.n_slots);
+int env_int(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : fallback;
+}
+
+template <int G, int WARPS, int VEC, bool PF, bool QO>
+int launch_fk_cfg(const FkArgs &a, const DeviceProps &dp) {
+    auto kernel = pmb::fk_chain_kernel<G, WARPS, VEC, PF, QO>;
+    const int smem = pmb::fk_geom(G, VEC, QO ? 4 : 9, WARPS, a.n_joints, a.n_slots).block_bytes;
     int rc = set_smem(kernel, smem);
     if (rc) return rc;
     CUtensorMap tm;
-    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, C))) return rc;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kFkChunk))) return rc;
     // persistent grid: as many blocks as are resident at once; warps walk the tiles round robin
     const long long tiles = (a.n_frames + 31) / 32;
     int per_sm = 0;
     PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
     if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk kernel does not fit on an SM (%d bytes of shared memory)", smem);
-    if (const char *env = getenv("PMB_FK_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(env)));
-    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * sm_count);
-    int stagger_ns = 0;
-    if (const char *env = getenv("PMB_FK_STAGGER_NS")) stagger_ns = atoi(env);
+    per_sm = std::max(1, std::min(per_sm, env_int("PMB_FK_BLOCKS_PER_SM", per_sm)));
+    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
     kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.ostride,
                                                                         a.pos, a.rout, a.n_frames, a.n_joints,
-                                                                        a.n_slots, stagger_ns, *a.prog);
+                                                                        a.n_slots, *a.prog);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
 
-template <int C, int VEC, bool PF, bool QO>
-int launch_fk_warps(const FkArgs &a, const DeviceProps &dp) {
-    using Tile = pmb::FkTile<C, VEC, QO ? 4 : 9>;
-    if (Tile::block_bytes(4, a.n_joints, a.n_slots) <= dp.smem_optin) return launch_fk_cfg<C, 4, VEC, PF, QO>(a, dp.sm_count);
-    if (Tile::block_bytes(1, a.n_joints, a.n_slots) <= dp.smem_optin) return launch_fk_cfg<C, 1, VEC, PF, QO>(a, dp.sm_count);
+inline bool fk_fits(int group, int vec, int rw, int warps, const FkArgs &a, const DeviceProps &dp) {
+    return pmb::fk_geom(group, vec, rw, warps, a.n_joints, a.n_slots).block_bytes <= dp.smem_optin;
+}
+
+// Output flush group (see fk_kernel.cuh): whole rows if a block of >= 4 warps fits, else the largest group
+// that does.  FULL = the main entry point gets every variant; the rarer ones (per-frame offsets, quaternion
+// output) get the two extremes only, to keep the build small.
+template <int VEC, bool PF, bool QO, bool FULL>
+int launch_fk_group(const FkArgs &a, const DeviceProps &dp) {
+    constexpr int RW = QO ? 4 : 9;
+    const int force_group = env_int("PMB_FK_GROUP", -1);
+    const int force_warps = env_int("PMB_FK_WARPS", -1);
+    auto want = [&](int group, int warps) {
+        if (force_group >= 0 && force_group != group) return false;
+        if (force_warps >= 0 && force_warps != warps) return false;
+        return fk_fits(group, VEC, RW, warps, a, dp);
+    };
+    if constexpr (FULL) {
+        if (want(0, 8)) return launch_fk_cfg<0, 8, VEC, PF, QO>(a, dp);
+        if (want(0, 6)) return launch_fk_cfg<0, 6, VEC, PF, QO>(a, dp);
+        if (want(0, 5)) return launch_fk_cfg<0, 5, VEC, PF, QO>(a, dp);
+    }
+    if (want(0, 4)) return launch_fk_cfg<0, 4, VEC, PF, QO>(a, dp);
+    if constexpr (FULL) {
+        if (want(32, 4)) return launch_fk_cfg<32, 4, VEC, PF, QO>(a, dp);
+        if (want(16, 4)) return launch_fk_cfg<16, 4, VEC, PF, QO>(a, dp);
+    }
+    if (want(8, 4)) return launch_fk_cfg<8, 4, VEC, PF, QO>(a, dp);
+    if (want(8, 1)) return launch_fk_cfg<8, 1, VEC, PF, QO>(a, dp);
+    if (force_group >= 0 || force_warps >= 0) return fail(PMB_ERR_SHAPE, "PMB_FK_GROUP / PMB_FK_WARPS select no available variant");
     return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
 }
 
 template <bool PF, bool QO>
 int launch_fk(const FkArgs &a, const DeviceProps &dp) {
     // 64-bit staging / stores need 8-byte aligned rows: even joint count.
-    const bool vec2 = (a.n_joints % 2) == 0;
-    // Joints per chunk.  Measured on B200 (1M x 22, 4M x 52, 4M x 65): 8 beats 4 by 25-50 % -- fewer TMA
-    // round trips and barriers per frame outweigh the larger remainder chunk and the lower occupancy.
-    int chunk = 8;
-    if (const char *env = getenv("PMB_FK_CHUNK")) {
-        const int v = atoi(env);
-        if (v == 4 || v == 8) chunk = v;
-    }
-    if (chunk == 8) return vec2 ? launch_fk_warps<8, 2, PF, QO>(a, dp) : launch_fk_warps<8, 1, PF, QO>(a, dp);
-    return vec2 ? launch_fk_warps<4, 2, PF, QO>(a, dp) : launch_fk_warps<4, 1, PF, QO>(a, dp);
+    if ((a.n_joints % 2) == 0) return launch_fk_group<2, PF, QO, !PF && !QO>(a, dp);
+    return launch_fk_group<1, PF, QO, !PF && !QO>(a, dp);
 }
 
 int fk_common(const float *rot, const float *gpos, int64_t gstride, const float *offsets, int64_t ostride,

@@ -1,27 +1,33 @@
 // Forward kinematics, one fused kernel (ops/skeleton.py:16-61 of the reference).
 //
-// Mapping: one THREAD per frame, one WARP per tile of 32 consecutive frames; warps
-// are autonomous (own staging buffers, own mbarrier) so load / compose / store
-// phases of different warps overlap on the SM.
+// Mapping: one THREAD per frame, one WARP per tile of 32 consecutive frames; warps are
+// persistent (tile t, t + stride, ...) and autonomous (own staging buffers, own mbarrier)
+// so load / compose / store phases of different warps overlap on the SM.
 //
-//   in   the tile's quaternions arrive chunk by chunk (C joints x 32 frames) through
-//        TMA (cp.async.bulk.tensor.2d, hardware swizzle so the thread-per-frame
-//        16-byte reads are bank-conflict free); the copy of chunk c+1 is in flight
-//        while chunk c is composed;
-//   walk the joint table (offsets + per-joint program word) sits in shared memory;
-//        a thread composes joint after joint in registers; the parent transform is
-//        either still in registers (parent == previous joint, the chain case) or in
-//        a per-warp shared-memory slot written when the parent was computed (branch
-//        points of the tree; slots are allocated on the host, joint_program.h);
-//   out  the C joints' results are staged per warp in shared memory with a row
-//        stride that makes the thread-per-frame writes conflict free, then written
-//        to HBM by the whole warp as fully coalesced 128/256-byte runs (64-bit
-//        accesses when the joint count is even, i.e. rows are 8-byte aligned).
-//        The (row, column) a lane serves repeats with a short period, so the lane's
-//        offsets are computed once per chunk and each store costs LDS + STG only.
+//   in   the tile's quaternions arrive 8 joints x 32 frames at a time through TMA
+//        (cp.async.bulk.tensor.2d, 128-byte hardware swizzle so the thread-per-frame
+//        16-byte reads are bank-conflict free); the copy of the next chunk -- or of the
+//        warp's next tile -- is in flight while the current chunk is composed;
+//   walk the joint table (offsets + per-joint program word) sits in shared memory; a
+//        thread composes joint after joint in registers; the parent transform is either
+//        still in registers (parent == previous joint, the chain case) or in a per-warp
+//        shared-memory slot written when the parent was computed (branch points of the
+//        tree; slots are allocated on the host, joint_program.h);
+//   out  results are staged per warp in shared memory and written to HBM by the whole
+//        warp.  HBM wants every 128-byte line -- better, every DRAM page -- written in
+//        one go (measured: flushing 8 joints at a time leaves DRAM ~90 % busy at ~45 % of
+//        its byte rate, because a 288-byte piece per frame row splits most lines between
+//        two flushes).  So the flush group is as large as shared memory allows:
+//          G == 0  whole rows: the stage is the dense image of the tile's output
+//                  (32 x 36J and 32 x 12J bytes, both multiples of 128), copied out as one
+//                  contiguous, line-aligned span with 16-byte accesses;
+//          G > 0   G joints per flush (32, 16 or 8), rows padded to a conflict-free stride,
+//                  copied out with the short-period lane map of copy_out_periodic.
+//        Thread-per-frame writes into the stage are 64-bit when the joint count is even
+//        (rows are then 8-byte aligned) and conflict free in both layouts.
 //
-// Algorithmic HBM traffic: 64*J + 12 bytes per pose (16J + 12 in, 12J + 36J out),
-// no scratch in global memory.  See DESIGN.md for the roofline.
+// Algorithmic HBM traffic: 64*J + 12 bytes per pose (16J + 12 in, 12J + 36J out), no scratch
+// in global memory.  See DESIGN.md for the roofline and the measurements behind the choices.
 #pragma once
 #include <cuda.h>
 
@@ -45,7 +51,6 @@ __device__ __forceinline__ void out_store(V *p, const V &v) {
     *p = v;
 #endif
 }
-#define PMB_ST(p, v) out_store(p, v)
 
 // ---- mbarrier / TMA (PTX) -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -53,7 +58,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -78,28 +82,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
 __host__ __device__ constexpr int ce_gcd(int a, int b) { return b == 0 ? a : ce_gcd(b, a % b); }
 __host__ __device__ constexpr int ce_lcm(int a, int b) { return a / ce_gcd(a, b) * b; }
 
-// Shared-memory geometry of one warp's buffers, shared by host (sizing) and device.
-template <int C, int VEC, int RW>
-struct FkTile {
-    static constexpr int WR = RW * C, WP = 3 * C;  // words per full piece of a row
-    // row stride (words): VEC == 1 -> odd; VEC == 2 -> even with an odd number of 8-byte pairs
-    __host__ __device__ static constexpr int pad(int w) { return VEC == 1 ? (w | 1) : (((w / 2) & 1) ? w : w + 2); }
-    static constexpr int SR = pad(WR), SP = pad(WP);
-    static constexpr int kInBytes = kWarp * C * 16;            // TMA box, dense (swizzled) [32][C] float4
-    static constexpr int kStageBytes = kWarp * (SR + SP) * 4;
-    static constexpr int kSlotBytes = 3 * kWarp * 16;          // one slot = 12 floats x 32 lanes
-    __host__ __device__ static constexpr int warp_bytes(int n_slots) { return kStageBytes + n_slots * kSlotBytes; }
-    // total dynamic shared memory of a block (1 KB slack to align the TMA buffers to 1024)
-    __host__ __device__ static constexpr int block_bytes(int warps, int n_joints, int n_slots) {
-        return 1024 + warps * kInBytes + ((n_joints * 16 + 127) & ~127) + warps * warp_bytes(n_slots) + warps * 8 +
-               warps * kWarp * 4;
-    }
-};
+constexpr int kFkChunk = 8;                              // joints per TMA box (128-byte rows, SWIZZLE_128B)
+constexpr int kFkInBytes = kWarp * kFkChunk * 16;        // one box: dense (swizzled) [32][8] float4
 
-// Warp-cooperative copy of a FULL stage (32 rows x W words, row stride S) to global rows of pitch
-// `pitch` words, in units of VEC words.  Store k of the warp serves flat unit 32k + lane -> (row,
-// column); that map repeats every P stores / RPP rows, so a lane computes its P offsets once and each
-// store costs LDS + STG.
+// Shared-memory geometry, shared by host (sizing) and device.  group = 0: dense rows of n_joints joints.
+struct FkGeom {
+    int sr, sp;         // row strides of the rotation / position stage, in words
+    int warp_bytes;     // stage + slots of one warp
+    int block_bytes;    // whole dynamic allocation of a block
+};
+__host__ __device__ constexpr int fk_pad(int w, int vec) { return vec == 1 ? (w | 1) : (((w / 2) & 1) ? w : w + 2); }
+__host__ __device__ inline FkGeom fk_geom(int group, int vec, int rw, int warps, int n_joints, int n_slots) {
+    FkGeom g;
+    g.sr = group ? fk_pad(rw * group, vec) : rw * n_joints;
+    g.sp = group ? fk_pad(3 * group, vec) : 3 * n_joints;
+    g.warp_bytes = ((kWarp * (g.sr + g.sp) * 4 + 15) & ~15) + n_slots * 3 * kWarp * 16;
+    // 1 KB slack to align the TMA boxes to 1024 | boxes | joint table | per-warp stage + slots | mbarriers | fence words
+    g.block_bytes = 1024 + warps * kFkInBytes + ((n_joints * 16 + 127) & ~127) + warps * g.warp_bytes + warps * 8 +
+                    warps * kWarp * 4;
+    return g;
+}
+
+// Warp-cooperative copy of a FULL padded stage (32 rows x W words, row stride S) to global rows of
+// pitch `pitch` words, in units of VEC words.  Store k of the warp serves flat unit 32k + lane ->
+// (row, column); that map repeats every P stores / RPP rows, so a lane computes its P offsets once
+// and each store costs LDS + STG.
 template <int W, int S, int VEC>
 __device__ __forceinline__ void copy_out_periodic(const float *__restrict__ stage, float *__restrict__ gtile, int pitch,
                                                   int lane) {
@@ -107,7 +114,7 @@ __device__ __forceinline__ void copy_out_periodic(const float *__restrict__ stag
     constexpr int L = ce_lcm(32, WV);
     constexpr int P = L / 32;     // stores per period
     constexpr int RPP = L / WV;   // rows per period
-    static_assert(32 % RPP == 0 && P <= 9, "chunk geometry must give a short period");
+    static_assert(32 % RPP == 0 && P <= 9, "group geometry must give a short period");
     using V = typename std::conditional<VEC == 2, float2, float>::type;
     int soff[P], goff[P];
 #pragma unroll
@@ -117,19 +124,19 @@ __device__ __forceinline__ void copy_out_periodic(const float *__restrict__ stag
         soff[k] = dr * S + col * VEC;
         goff[k] = dr * pitch + col * VEC;
     }
-#pragma unroll
+#pragma unroll 2
     for (int g = 0; g < 32 / RPP; ++g) {
         V v[P];
 #pragma unroll
         for (int k = 0; k < P; ++k) v[k] = *reinterpret_cast<const V *>(stage + g * RPP * S + soff[k]);
         float *gp = gtile + static_cast<long long>(g * RPP) * pitch;
 #pragma unroll
-        for (int k = 0; k < P; ++k) PMB_ST(reinterpret_cast<V *>(gp + goff[k]), v[k]);
+        for (int k = 0; k < P; ++k) out_store(reinterpret_cast<V *>(gp + goff[k]), v[k]);
     }
 }
 
-// Remainder chunk (w < W words per row) and remainder tile (nrows < 32): one row at a time, lanes
-// across the row.  MAXU = column slots a lane may serve.
+// Remainder group (w < W words per row) and remainder tile (nrows < 32) of the padded layout: one row
+// at a time, lanes across the row.
 template <int WMAX, int S, int VEC>
 __device__ __forceinline__ void copy_out_rows(const float *__restrict__ stage, float *__restrict__ gtile, int pitch,
                                               int nrows, int w, int lane) {
@@ -138,7 +145,7 @@ __device__ __forceinline__ void copy_out_rows(const float *__restrict__ stage, f
     const int wv = w / VEC;
     const V *sp = reinterpret_cast<const V *>(stage) + lane;
     V *gp = reinterpret_cast<V *>(gtile) + lane;
-#pragma unroll 4
+#pragma unroll 2
     for (int r = 0; r < nrows; ++r) {
         V v[MAXU];
 #pragma unroll
@@ -146,43 +153,58 @@ __device__ __forceinline__ void copy_out_rows(const float *__restrict__ stage, f
             if (lane + 32 * u < wv) v[u] = sp[32 * u];
 #pragma unroll
         for (int u = 0; u < MAXU; ++u)
-            if (lane + 32 * u < wv) PMB_ST(gp + 32 * u, v[u]);
+            if (lane + 32 * u < wv) out_store(gp + 32 * u, v[u]);
         sp += S / VEC;
         gp += pitch / VEC;
     }
 }
 
-// QO = false: rout is rotmats [F][J][9];  true: rout is global quaternions [F][J][4].
-template <int C, int WARPS, int VEC, bool PF_OFFSETS, bool QO>
-__global__ void __launch_bounds__(WARPS *kWarp, (WARPS == 4 ? (C == 8 ? 3 : 4) : 1))  // shared memory allows no more anyway
+// Dense layout: the stage IS the tile's output image -> one contiguous, 16-byte aligned span of n words.
+__device__ __forceinline__ void copy_out_flat(const float *__restrict__ stage, float *__restrict__ gtile, int n, int lane) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(stage);
+    float4 *g4 = reinterpret_cast<float4 *>(gtile);
+    const int n4 = n >> 2;
+    int i = lane;
+    for (; i + 96 < n4; i += 128) {  // 4 x 512 bytes in flight per warp
+        const float4 a = s4[i], b = s4[i + 32], c = s4[i + 64], d = s4[i + 96];
+        out_store(g4 + i, a), out_store(g4 + i + 32, b), out_store(g4 + i + 64, c), out_store(g4 + i + 96, d);
+    }
+    for (; i < n4; i += 32) out_store(g4 + i, s4[i]);
+    for (int k = 4 * n4 + lane; k < n; k += 32) gtile[k] = stage[k];  // only a remainder tile can leave 1..3 words
+}
+
+// G: joints per flush group (0 = whole rows, dense).  QO = false: rout is rotmats [F][J][9]; true: global
+// quaternions [F][J][4].
+template <int G, int WARPS, int VEC, bool PF_OFFSETS, bool QO>
+__global__ void __launch_bounds__(WARPS *kWarp)
 fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                 const float *__restrict__ offsets, long long ostride, float *__restrict__ pos,
-                float *__restrict__ rout, long long n_frames, int n_joints, int n_slots, int stagger_ns,
+                float *__restrict__ rout, long long n_frames, int n_joints, int n_slots,
                 const __grid_constant__ JointProgram prog) {
     constexpr int RW = QO ? 4 : 9;
-    using Tile = FkTile<C, VEC, RW>;
-    constexpr int SR = Tile::SR, SP = Tile::SP;
-    static_assert(C == 4 || C == 8, "swizzle decode below assumes a 64- or 128-byte TMA box row");
-    static_assert(VEC == 1 || (C % 2 == 0), "64-bit staging needs an even chunk");
+    constexpr int C = kFkChunk;
+    constexpr bool DENSE = (G == 0);
+    static_assert(G % C == 0, "a flush group is a whole number of TMA chunks");
 
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     // align by OFFSETTING the array (pointer arithmetic keeps the shared address space; an integer round trip
     // would demote every access below to generic LD/ST)
     unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const FkGeom geo = fk_geom(G, VEC, RW, WARPS, n_joints, n_slots);
+    const int SR = DENSE ? geo.sr : fk_pad(RW * G, VEC), SP = DENSE ? geo.sp : fk_pad(3 * G, VEC);
 
-    float4 *in_stage = reinterpret_cast<float4 *>(smem_raw + warp * Tile::kInBytes);
-    float4 *tab = reinterpret_cast<float4 *>(smem_raw + WARPS * Tile::kInBytes);
-    unsigned char *wbase = reinterpret_cast<unsigned char *>(tab) + ((n_joints * 16 + 127) & ~127) + warp * Tile::warp_bytes(n_slots);
-    float *Rst = reinterpret_cast<float *>(wbase);
+    float4 *in_stage = reinterpret_cast<float4 *>(smem_raw + warp * kFkInBytes);
+    float4 *tab = reinterpret_cast<float4 *>(smem_raw + WARPS * kFkInBytes);
+    unsigned char *after_tab = reinterpret_cast<unsigned char *>(tab) + ((n_joints * 16 + 127) & ~127);
+    float *Rst = reinterpret_cast<float *>(after_tab + warp * geo.warp_bytes);
     float *Pst = Rst + kWarp * SR;
-    float4 *slots = reinterpret_cast<float4 *>(Pst + kWarp * SP);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(tab) + ((n_joints * 16 + 127) & ~127) +
-                                                  WARPS * Tile::warp_bytes(n_slots));
+    float4 *slots = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Rst) + ((kWarp * (SR + SP) * 4 + 15) & ~15));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(after_tab + WARPS * geo.warp_bytes);
     const uint32_t bar = smem_u32(bars + warp);
     const uint32_t fence_word = smem_u32(reinterpret_cast<uint32_t *>(bars + WARPS) + threadIdx.x);  // see the chunk loop
 
-    // Persistent warps: tile t, t + stride, ... (all tiles cost the same, so a static round robin balances).
+    // Persistent warps: all tiles cost the same, so a static round robin balances.
     const long long n_tiles = (n_frames + kWarp - 1) / kWarp;
     const long long tile_stride = static_cast<long long>(gridDim.x) * WARPS;
     long long tile = static_cast<long long>(blockIdx.x) * WARPS + warp;
@@ -192,7 +214,7 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     }
     __syncwarp();
     if (tile < n_tiles && lane == 0) {  // first chunk's quaternions: in flight while the block loads its joint table
-        mbar_arrive_expect_tx(bar, Tile::kInBytes);
+        mbar_arrive_expect_tx(bar, kFkInBytes);
         tma_load_2d(smem_u32(in_stage), &tm_rot, 0, static_cast<int>(tile * kWarp), bar);
     }
     for (int j = threadIdx.x; j < n_joints; j += WARPS * kWarp) {
@@ -206,13 +228,9 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
         tab[j] = e;
     }
     __syncthreads();
-    if (stagger_ns > 0) {  // de-phase the persistent warps of an SM (they would otherwise load / compute / store in lockstep)
-        const int rank = static_cast<int>(blockIdx.x / 148u) * WARPS + warp;
-        __nanosleep(static_cast<unsigned>(rank * stagger_ns));
-    }
 
-    // TMA swizzle: 16-byte chunk jj of row r lands at chunk jj ^ x (128B mode: x = r & 7; 64B mode: x = (r >> 1) & 3)
-    const int swz = (C == 8) ? (lane & 7) : ((lane >> 1) & 3);
+    // TMA 128-byte swizzle: 16-byte chunk jj of row r lands at chunk jj ^ (r & 7)
+    const int swz = lane & 7;
     const float4 *in_row = in_stage + lane * C;
     const int rpitch = n_joints * RW, ppitch = n_joints * 3;
     uint32_t phase = 0;
@@ -224,129 +242,142 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     }
 
     for (; tile < n_tiles; tile += tile_stride) {
-    const long long f0 = tile * kWarp;
-    const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
-    const long long f = f0 + min(lane, nrows - 1);  // tail lanes recompute the last frame, never stored
-    const float *orow = PF_OFFSETS ? offsets + f * ostride : nullptr;
-    Xform<float> cur;
-    cur.p[0] = gnext[0], cur.p[1] = gnext[1], cur.p[2] = gnext[2];
+        const long long f0 = tile * kWarp;
+        const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
+        const long long f = f0 + min(lane, nrows - 1);  // tail lanes recompute the last frame, never stored
+        const float *orow = PF_OFFSETS ? offsets + f * ostride : nullptr;
+        Xform<float> cur;
+        cur.p[0] = gnext[0], cur.p[1] = gnext[1], cur.p[2] = gnext[2];
+        int gj = 0;  // joints already staged in the current flush group
 
-    for (int c0 = 0; c0 < n_joints; c0 += C) {
-        const int cnt = min(C, n_joints - c0);
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        float4 q[C];
+        for (int c0 = 0; c0 < n_joints; c0 += C) {
+            const int cnt = min(C, n_joints - c0);
+            const bool last_chunk = c0 + C >= n_joints;
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            float4 q[C];
 #pragma unroll
-        for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
-        // The refill below goes through the async proxy and is not ordered after shared-memory loads that
-        // have merely been ISSUED (measured: ~1e-5 of the tiles read the next chunk's data).  A store whose
-        // operand depends on every loaded register cannot issue before all of them have landed, and the TMA
-        // instruction issues after it.
-        {
-            uint32_t acc = 0;
+            for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
+            // The refill below goes through the async proxy and is not ordered after shared-memory loads that
+            // have merely been ISSUED (measured: ~1e-5 of the tiles read the next chunk's data).  A store whose
+            // operand depends on every loaded register cannot issue before all of them have landed, and the TMA
+            // instruction issues after it.
+            {
+                uint32_t acc = 0;
 #pragma unroll
-            for (int jj = 0; jj < C; ++jj) acc |= __float_as_uint(q[jj].x) | __float_as_uint(q[jj].w);
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
-        }
-        __syncwarp();  // every lane has its quaternions in registers: the buffer can be refilled
-        if (lane == 0) {
-            // next chunk of this tile, or the first chunk of the warp's next tile (hides the tile-start latency)
-            const bool more = c0 + C < n_joints;
-            const long long nt = tile + tile_stride;
-            if (more || nt < n_tiles) {
-                mbar_arrive_expect_tx(bar, Tile::kInBytes);
-                tma_load_2d(smem_u32(in_stage), &tm_rot, more ? 4 * (c0 + C) : 0,
-                            static_cast<int>(more ? f0 : nt * kWarp), bar);
+                for (int jj = 0; jj < C; ++jj) acc |= __float_as_uint(q[jj].x) | __float_as_uint(q[jj].w);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
+            }
+            __syncwarp();  // every lane has its quaternions in registers: the buffer can be refilled
+            const long long next_tile = tile + tile_stride;
+            if (lane == 0 && (!last_chunk || next_tile < n_tiles)) {
+                // next chunk of this tile, or the first chunk of the warp's next tile (hides the tile-start latency)
+                mbar_arrive_expect_tx(bar, kFkInBytes);
+                tma_load_2d(smem_u32(in_stage), &tm_rot, last_chunk ? 0 : 4 * (c0 + C),
+                            static_cast<int>(last_chunk ? next_tile * kWarp : f0), bar);
+            }
+            if (last_chunk && next_tile < n_tiles) {
+                const float *g = gpos + min(next_tile * kWarp + lane, n_frames - 1) * gstride;
+                gnext[0] = __ldg(g), gnext[1] = __ldg(g + 1), gnext[2] = __ldg(g + 2);
+            }
+
+            float *rs0 = Rst + lane * SR + RW * gj;
+            float *ps0 = Pst + lane * SP + 3 * gj;
+            float carry_r = 0.f, carry_p = 0.f;  // VEC == 2: odd word waiting for its 8-byte partner
+#pragma unroll
+            for (int jj = 0; jj < C; ++jj) {
+                if (jj < cnt) {
+                    const int j = c0 + jj;
+                    const float4 e = tab[j];
+                    const uint32_t code = __float_as_uint(e.w);
+                    float ox = e.x, oy = e.y, oz = e.z;
+                    if (PF_OFFSETS) {
+                        ox = __ldg(orow + 3 * j), oy = __ldg(orow + 3 * j + 1), oz = __ldg(orow + 3 * j + 2);
+                    }
+                    float l[9];
+                    q_to_matrix(q_normalize(Quat<float>{q[jj].x, q[jj].y, q[jj].z, q[jj].w}, 1e-8f), l);
+                    if (jj == 0 && c0 == 0) {
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) cur.r[k] = l[k];  // root: [R | global_pos] (skeleton.py:49)
+                    } else {
+                        const uint32_t src = prog_src(code);
+                        if (src != kSrcReg) {  // warp-uniform: every lane runs the same program
+                            const float4 *s = slots + src * 3 * kWarp + lane;
+                            const float4 a = s[0], b = s[kWarp], c = s[2 * kWarp];
+                            cur.r[0] = a.x, cur.r[1] = a.y, cur.r[2] = a.z, cur.r[3] = a.w;
+                            cur.r[4] = b.x, cur.r[5] = b.y, cur.r[6] = b.z, cur.r[7] = b.w;
+                            cur.r[8] = c.x, cur.p[0] = c.y, cur.p[1] = c.z, cur.p[2] = c.w;
+                        }
+                        xf_compose(cur, cur, l, ox, oy, oz);
+                    }
+                    const uint32_t sv = prog_save(code);
+                    if (sv != kNoSave) {
+                        float4 *s = slots + sv * 3 * kWarp + lane;
+                        s[0] = make_float4(cur.r[0], cur.r[1], cur.r[2], cur.r[3]);
+                        s[kWarp] = make_float4(cur.r[4], cur.r[5], cur.r[6], cur.r[7]);
+                        s[2 * kWarp] = make_float4(cur.r[8], cur.p[0], cur.p[1], cur.p[2]);
+                    }
+                    float o[RW];
+                    if (QO) {
+                        const Quat<float> gq = q_from_matrix(cur.r);
+                        o[0] = gq.w, o[1] = gq.x, o[2] = gq.y, o[3] = gq.z;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < RW; ++k) o[k] = cur.r[k];
+                    }
+                    float *rs = rs0 + RW * jj;
+                    float *ps = ps0 + 3 * jj;
+                    if (VEC == 1) {
+#pragma unroll
+                        for (int k = 0; k < RW; ++k) rs[k] = o[k];
+                        ps[0] = cur.p[0], ps[1] = cur.p[1], ps[2] = cur.p[2];
+                    } else {
+                        // 8-byte stores; a chunk starts 8-byte aligned (row strides and 8-joint chunks are even)
+                        // and joints alternate parity when RW is odd
+                        if ((RW * jj) % 2 == 0) {
+#pragma unroll
+                            for (int k = 0; k + 1 < RW; k += 2) *reinterpret_cast<float2 *>(rs + k) = make_float2(o[k], o[k + 1]);
+                            if (RW % 2) carry_r = o[RW - 1];
+                        } else {
+                            *reinterpret_cast<float2 *>(rs - 1) = make_float2(carry_r, o[0]);
+#pragma unroll
+                            for (int k = 1; k + 1 < RW; k += 2) *reinterpret_cast<float2 *>(rs + k) = make_float2(o[k], o[k + 1]);
+                        }
+                        if ((3 * jj) % 2 == 0) {
+                            *reinterpret_cast<float2 *>(ps) = make_float2(cur.p[0], cur.p[1]);
+                            carry_p = cur.p[2];
+                        } else {
+                            *reinterpret_cast<float2 *>(ps - 1) = make_float2(carry_p, cur.p[0]);
+                            *reinterpret_cast<float2 *>(ps + 1) = make_float2(cur.p[1], cur.p[2]);
+                        }
+                    }
+                }
+            }
+            gj += cnt;
+
+            if (DENSE ? last_chunk : (gj == G || last_chunk)) {
+                __syncwarp();
+                if (DENSE) {
+                    copy_out_flat(Rst, rout + f0 * rpitch, nrows * rpitch, lane);
+                    copy_out_flat(Pst, pos + f0 * ppitch, nrows * ppitch, lane);
+                } else {
+                    const int g0 = c0 + cnt - gj;  // first joint of the group
+                    float *rg = rout + (f0 * n_joints + g0) * RW;
+                    float *pg = pos + (f0 * n_joints + g0) * 3;
+                    constexpr int GG = DENSE ? C : G;  // (dense never gets here; keeps the templates well-formed)
+                    if (gj == GG && nrows == kWarp) {
+                        copy_out_periodic<RW * GG, fk_pad(RW * GG, VEC), VEC>(Rst, rg, rpitch, lane);
+                        copy_out_periodic<3 * GG, fk_pad(3 * GG, VEC), VEC>(Pst, pg, ppitch, lane);
+                    } else {  // VEC == 2 only ever sees even counts (even joint count, even chunks)
+                        copy_out_rows<RW * GG, fk_pad(RW * GG, VEC), VEC>(Rst, rg, rpitch, nrows, RW * gj, lane);
+                        copy_out_rows<3 * GG, fk_pad(3 * GG, VEC), VEC>(Pst, pg, ppitch, nrows, 3 * gj, lane);
+                    }
+                }
+                __syncwarp();
+                gj = 0;
             }
         }
-        if (c0 + C >= n_joints && tile + tile_stride < n_tiles) {
-            const float *g = gpos + min((tile + tile_stride) * kWarp + lane, n_frames - 1) * gstride;
-            gnext[0] = __ldg(g), gnext[1] = __ldg(g + 1), gnext[2] = __ldg(g + 2);
-        }
-
-        float carry_r = 0.f, carry_p = 0.f;  // VEC == 2: odd word waiting for its 8-byte partner
-#pragma unroll
-        for (int jj = 0; jj < C; ++jj) {
-            if (jj < cnt) {
-                const int j = c0 + jj;
-                const float4 e = tab[j];
-                const uint32_t code = __float_as_uint(e.w);
-                float ox = e.x, oy = e.y, oz = e.z;
-                if (PF_OFFSETS) {
-                    ox = __ldg(orow + 3 * j), oy = __ldg(orow + 3 * j + 1), oz = __ldg(orow + 3 * j + 2);
-                }
-                float l[9];
-                q_to_matrix(q_normalize(Quat<float>{q[jj].x, q[jj].y, q[jj].z, q[jj].w}, 1e-8f), l);
-                if (jj == 0 && c0 == 0) {
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) cur.r[k] = l[k];  // root: [R | global_pos] (skeleton.py:49)
-                } else {
-                    const uint32_t src = prog_src(code);
-                    if (src != kSrcReg) {  // warp-uniform: every lane runs the same program
-                        const float4 *s = slots + src * 3 * kWarp + lane;
-                        const float4 a = s[0], b = s[kWarp], c = s[2 * kWarp];
-                        cur.r[0] = a.x, cur.r[1] = a.y, cur.r[2] = a.z, cur.r[3] = a.w;
-                        cur.r[4] = b.x, cur.r[5] = b.y, cur.r[6] = b.z, cur.r[7] = b.w;
-                        cur.r[8] = c.x, cur.p[0] = c.y, cur.p[1] = c.z, cur.p[2] = c.w;
-                    }
-                    xf_compose(cur, cur, l, ox, oy, oz);
-                }
-                const uint32_t sv = prog_save(code);
-                if (sv != kNoSave) {
-                    float4 *s = slots + sv * 3 * kWarp + lane;
-                    s[0] = make_float4(cur.r[0], cur.r[1], cur.r[2], cur.r[3]);
-                    s[kWarp] = make_float4(cur.r[4], cur.r[5], cur.r[6], cur.r[7]);
-                    s[2 * kWarp] = make_float4(cur.r[8], cur.p[0], cur.p[1], cur.p[2]);
-                }
-                float o[RW];
-                if (QO) {
-                    const Quat<float> gq = q_from_matrix(cur.r);
-                    o[0] = gq.w, o[1] = gq.x, o[2] = gq.y, o[3] = gq.z;
-                } else {
-#pragma unroll
-                    for (int k = 0; k < RW; ++k) o[k] = cur.r[k];
-                }
-                float *rs = Rst + lane * SR + RW * jj;
-                float *ps = Pst + lane * SP + 3 * jj;
-                if (VEC == 1) {
-#pragma unroll
-                    for (int k = 0; k < RW; ++k) rs[k] = o[k];
-                    ps[0] = cur.p[0], ps[1] = cur.p[1], ps[2] = cur.p[2];
-                } else {
-                    // 8-byte stores; a row piece starts 8-byte aligned and joints alternate parity when RW is odd
-                    if ((RW * jj) % 2 == 0) {
-#pragma unroll
-                        for (int k = 0; k + 1 < RW; k += 2) *reinterpret_cast<float2 *>(rs + k) = make_float2(o[k], o[k + 1]);
-                        if (RW % 2) carry_r = o[RW - 1];
-                    } else {
-                        *reinterpret_cast<float2 *>(rs - 1) = make_float2(carry_r, o[0]);
-#pragma unroll
-                        for (int k = 1; k + 1 < RW; k += 2) *reinterpret_cast<float2 *>(rs + k) = make_float2(o[k], o[k + 1]);
-                    }
-                    if ((3 * jj) % 2 == 0) {
-                        *reinterpret_cast<float2 *>(ps) = make_float2(cur.p[0], cur.p[1]);
-                        carry_p = cur.p[2];
-                    } else {
-                        *reinterpret_cast<float2 *>(ps - 1) = make_float2(carry_p, cur.p[0]);
-                        *reinterpret_cast<float2 *>(ps + 1) = make_float2(cur.p[1], cur.p[2]);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-
-        float *rg = rout + (f0 * n_joints + c0) * RW;
-        float *pg = pos + (f0 * n_joints + c0) * 3;
-        if (cnt == C && nrows == kWarp) {
-            copy_out_periodic<RW * C, SR, VEC>(Rst, rg, rpitch, lane);
-            copy_out_periodic<3 * C, SP, VEC>(Pst, pg, ppitch, lane);
-        } else {  // VEC == 2 only ever sees even counts (even joint count, even C)
-            copy_out_rows<RW * C, SR, VEC>(Rst, rg, rpitch, nrows, RW * cnt, lane);
-            copy_out_rows<3 * C, SP, VEC>(Pst, pg, ppitch, nrows, 3 * cnt, lane);
-        }
-        __syncwarp();
     }
-    }  // tiles
 }
 
 }  // namespace pmb

@@ -65,6 +65,19 @@ __device__ __forceinline__ Quat<T> q_normalize(const Quat<T> &q, T eps) {
     return {q.w * inv, q.x * inv, q.y * inv, q.z * inv};
 }
 
+// Same value as q_normalize to ~3e-7 relative with two bare MUFU ops (no IEEE slow paths, no denormal
+// rescaling): |q| = n2 * rsqrt(n2), 1 / (|q| + eps) through the approximate reciprocal.  eps still joins
+// the NORM; squared norms below FLT_MIN (|q| < 1.1e-19) count as zero, where the reference's
+// q / (|q| + 1e-8) is below 1.1e-11, i.e. the same identity matrix.
+__device__ __forceinline__ Quat<float> q_normalize_fast(const Quat<float> &q, float eps) {
+    const float n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+    float r, inv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n2));
+    const float n = n2 >= 1.17549435e-38f ? n2 * r : 0.f;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(n + eps));
+    return {q.w * inv, q.x * inv, q.y * inv, q.z * inv};
+}
+
 // quat.py:337-361, same term order.
 template <typename T>
 __device__ __forceinline__ Quat<T> q_mul(const Quat<T> &a, const Quat<T> &b) {

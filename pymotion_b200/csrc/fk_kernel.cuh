@@ -38,6 +38,17 @@
 #ifndef PMB_ST_POLICY
 #define PMB_ST_POLICY 0
 #endif
+#ifndef PMB_FK_UNIFORM_CODE
+#define PMB_FK_UNIFORM_CODE 1
+#endif
+#ifndef PMB_FK_FAST_NORM
+#define PMB_FK_FAST_NORM 1
+#endif
+#if PMB_FK_FAST_NORM
+#define PMB_FK_NORMALIZE q_normalize_fast
+#else
+#define PMB_FK_NORMALIZE q_normalize
+#endif
 
 namespace pmb {
 
@@ -288,14 +299,16 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             for (int jj = 0; jj < C; ++jj) {
                 if (jj < cnt) {
                     const int j = c0 + jj;
+                    // program word from the kernel-parameter constant bank: j is warp-uniform, so the branches on
+                    // it are uniform branches (no divergence bookkeeping); offsets come from the shared table
+                    const uint32_t code = PMB_FK_UNIFORM_CODE ? prog.code[j] : __float_as_uint(tab[j].w);
                     const float4 e = tab[j];
-                    const uint32_t code = __float_as_uint(e.w);
                     float ox = e.x, oy = e.y, oz = e.z;
                     if (PF_OFFSETS) {
                         ox = __ldg(orow + 3 * j), oy = __ldg(orow + 3 * j + 1), oz = __ldg(orow + 3 * j + 2);
                     }
                     float l[9];
-                    q_to_matrix(q_normalize(Quat<float>{q[jj].x, q[jj].y, q[jj].z, q[jj].w}, 1e-8f), l);
+                    q_to_matrix(PMB_FK_NORMALIZE(Quat<float>{q[jj].x, q[jj].y, q[jj].z, q[jj].w}, 1e-8f), l);
                     if (jj == 0 && c0 == 0) {
 #pragma unroll
                         for (int k = 0; k < 9; ++k) cur.r[k] = l[k];  // root: [R | global_pos] (skeleton.py:49)

@@ -41,6 +41,9 @@
 #ifndef PMB_FK_UNIFORM_CODE
 #define PMB_FK_UNIFORM_CODE 1
 #endif
+#ifndef PMB_FK_BULK_STORE
+#define PMB_FK_BULK_STORE 1
+#endif
 #ifndef PMB_FK_FAST_NORM
 #define PMB_FK_FAST_NORM 1
 #endif
@@ -90,11 +93,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
         : "memory");
 }
 
+// 1-D bulk copy shared -> global (TMA engine, no register traffic); completion tracked per thread by bulk groups
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __host__ __device__ constexpr int ce_gcd(int a, int b) { return b == 0 ? a : ce_gcd(b, a % b); }
 __host__ __device__ constexpr int ce_lcm(int a, int b) { return a / ce_gcd(a, b) * b; }
 
 constexpr int kFkChunk = 8;                              // joints per TMA box (128-byte rows, SWIZZLE_128B)
 constexpr int kFkInBytes = kWarp * kFkChunk * 16;        // one box: dense (swizzled) [32][8] float4
+constexpr int kFkStages = 2;                             // boxes in flight per warp (prefetch depth in chunks)
 
 // Shared-memory geometry, shared by host (sizing) and device.  group = 0: dense rows of n_joints joints.
 struct FkGeom {
@@ -109,8 +122,8 @@ __host__ __device__ inline FkGeom fk_geom(int group, int vec, int rw, int warps,
     g.sp = group ? fk_pad(3 * group, vec) : 3 * n_joints;
     g.warp_bytes = ((kWarp * (g.sr + g.sp) * 4 + 15) & ~15) + n_slots * 3 * kWarp * 16;
     // 1 KB slack to align the TMA boxes to 1024 | boxes | joint table | per-warp stage + slots | mbarriers | fence words
-    g.block_bytes = 1024 + warps * kFkInBytes + ((n_joints * 16 + 127) & ~127) + warps * g.warp_bytes + warps * 8 +
-                    warps * kWarp * 4;
+    g.block_bytes = 1024 + warps * kFkStages * kFkInBytes + ((n_joints * 16 + 127) & ~127) + warps * g.warp_bytes +
+                    warps * kFkStages * 8 + warps * kWarp * 4;
     return g;
 }
 
@@ -205,28 +218,41 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     const FkGeom geo = fk_geom(G, VEC, RW, WARPS, n_joints, n_slots);
     const int SR = DENSE ? geo.sr : fk_pad(RW * G, VEC), SP = DENSE ? geo.sp : fk_pad(3 * G, VEC);
 
-    float4 *in_stage = reinterpret_cast<float4 *>(smem_raw + warp * kFkInBytes);
-    float4 *tab = reinterpret_cast<float4 *>(smem_raw + WARPS * kFkInBytes);
+    float4 *in_stage = reinterpret_cast<float4 *>(smem_raw + warp * kFkStages * kFkInBytes);  // kFkStages boxes
+    float4 *tab = reinterpret_cast<float4 *>(smem_raw + WARPS * kFkStages * kFkInBytes);
     unsigned char *after_tab = reinterpret_cast<unsigned char *>(tab) + ((n_joints * 16 + 127) & ~127);
     float *Rst = reinterpret_cast<float *>(after_tab + warp * geo.warp_bytes);
     float *Pst = Rst + kWarp * SR;
     float4 *slots = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Rst) + ((kWarp * (SR + SP) * 4 + 15) & ~15));
     uint64_t *bars = reinterpret_cast<uint64_t *>(after_tab + WARPS * geo.warp_bytes);
-    const uint32_t bar = smem_u32(bars + warp);
-    const uint32_t fence_word = smem_u32(reinterpret_cast<uint32_t *>(bars + WARPS) + threadIdx.x);  // see the chunk loop
+    const uint32_t bar0 = smem_u32(bars + warp * kFkStages);
+    const uint32_t in0 = smem_u32(in_stage);
+    const uint32_t fence_word = smem_u32(reinterpret_cast<uint32_t *>(bars + WARPS * kFkStages) + threadIdx.x);  // see the chunk loop
 
     // Persistent warps: all tiles cost the same, so a static round robin balances.
     const long long n_tiles = (n_frames + kWarp - 1) / kWarp;
     const long long tile_stride = static_cast<long long>(gridDim.x) * WARPS;
     long long tile = static_cast<long long>(blockIdx.x) * WARPS + warp;
     if (lane == 0) {
-        mbar_init(bar, 1);
+#pragma unroll
+        for (int b = 0; b < kFkStages; ++b) mbar_init(bar0 + 8 * b, 1);
         fence_barrier_init();
     }
     __syncwarp();
-    if (tile < n_tiles && lane == 0) {  // first chunk's quaternions: in flight while the block loads its joint table
-        mbar_arrive_expect_tx(bar, kFkInBytes);
-        tma_load_2d(smem_u32(in_stage), &tm_rot, 0, static_cast<int>(tile * kWarp), bar);
+    // Look-ahead cursor of the TMA producer (lane 0): the warp's chunks in processing order, across its tiles.
+    long long la_tile = tile;
+    int la_c0 = 0;
+    auto issue_next = [&](int buf) {  // lane 0 only
+        if (la_tile < n_tiles) {
+            mbar_arrive_expect_tx(bar0 + 8 * buf, kFkInBytes);
+            tma_load_2d(in0 + buf * kFkInBytes, &tm_rot, 4 * la_c0, static_cast<int>(la_tile * kWarp), bar0 + 8 * buf);
+            la_c0 += C;
+            if (la_c0 >= n_joints) la_c0 = 0, la_tile += tile_stride;
+        }
+    };
+    if (lane == 0) {  // the first kFkStages chunks: in flight while the block loads its joint table
+#pragma unroll
+        for (int b = 0; b < kFkStages; ++b) issue_next(b);
     }
     for (int j = threadIdx.x; j < n_joints; j += WARPS * kWarp) {
         float4 e;
@@ -242,9 +268,8 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
 
     // TMA 128-byte swizzle: 16-byte chunk jj of row r lands at chunk jj ^ (r & 7)
     const int swz = lane & 7;
-    const float4 *in_row = in_stage + lane * C;
     const int rpitch = n_joints * RW, ppitch = n_joints * 3;
-    uint32_t phase = 0;
+    uint32_t kchunk = 0;  // chunks consumed so far: buffer = kchunk % kFkStages, parity = (kchunk / kFkStages) & 1
     // root position of the warp's NEXT tile, fetched one chunk early like its quaternions
     float gnext[3] = {0.f, 0.f, 0.f};
     if (tile < n_tiles) {
@@ -264,8 +289,10 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
         for (int c0 = 0; c0 < n_joints; c0 += C) {
             const int cnt = min(C, n_joints - c0);
             const bool last_chunk = c0 + C >= n_joints;
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            const int buf = kchunk % kFkStages;
+            mbar_wait(bar0 + 8 * buf, (kchunk / kFkStages) & 1);
+            ++kchunk;
+            const float4 *in_row = in_stage + buf * (kFkInBytes / 16) + lane * C;
             float4 q[C];
 #pragma unroll
             for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
@@ -281,12 +308,7 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             }
             __syncwarp();  // every lane has its quaternions in registers: the buffer can be refilled
             const long long next_tile = tile + tile_stride;
-            if (lane == 0 && (!last_chunk || next_tile < n_tiles)) {
-                // next chunk of this tile, or the first chunk of the warp's next tile (hides the tile-start latency)
-                mbar_arrive_expect_tx(bar, kFkInBytes);
-                tma_load_2d(smem_u32(in_stage), &tm_rot, last_chunk ? 0 : 4 * (c0 + C),
-                            static_cast<int>(last_chunk ? next_tile * kWarp : f0), bar);
-            }
+            if (lane == 0) issue_next(buf);  // refill with the chunk kFkStages ahead (this tile's or the next tile's)
             if (last_chunk && next_tile < n_tiles) {
                 const float *g = gpos + min(next_tile * kWarp + lane, n_frames - 1) * gstride;
                 gnext[0] = __ldg(g), gnext[1] = __ldg(g + 1), gnext[2] = __ldg(g + 2);
@@ -371,8 +393,20 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             if (DENSE ? last_chunk : (gj == G || last_chunk)) {
                 __syncwarp();
                 if (DENSE) {
-                    copy_out_flat(Rst, rout + f0 * rpitch, nrows * rpitch, lane);
-                    copy_out_flat(Pst, pos + f0 * ppitch, nrows * ppitch, lane);
+                    if (PMB_FK_BULK_STORE && nrows == kWarp) {
+                        // whole tile = two contiguous, 128-byte aligned spans: hand them to the TMA engine and go on
+                        fence_proxy_async_smem();  // this lane's stage writes -> visible to the async proxy
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_store(rout + f0 * rpitch, smem_u32(Rst), static_cast<uint32_t>(kWarp * rpitch * 4));
+                            bulk_store(pos + f0 * ppitch, smem_u32(Pst), static_cast<uint32_t>(kWarp * ppitch * 4));
+                            bulk_commit();
+                            bulk_wait_read0();  // the stage may be overwritten once the engine has read it
+                        }
+                    } else {
+                        copy_out_flat(Rst, rout + f0 * rpitch, nrows * rpitch, lane);
+                        copy_out_flat(Pst, pos + f0 * ppitch, nrows * ppitch, lane);
+                    }
                 } else {
                     const int g0 = c0 + cnt - gj;  // first joint of the group
                     float *rg = rout + (f0 * n_joints + g0) * RW;
@@ -391,6 +425,7 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             }
         }
     }
+    if (DENSE && PMB_FK_BULK_STORE && lane == 0) bulk_wait0();  // global writes of the last tile are complete at exit
 }
 
 }  // namespace pmb

@@ -40,10 +40,17 @@ WORKLOADS = {
     "fk_4m_x_65": ("deep65", 4_000_000),
     "fk_4m_x_52": ("smplh52", 4_000_000),
 }
+# --kernel-only development workloads for the other ops of the path (BASELINE.json configs[2])
+DEV_OPS = ("fk", "to_dq", "from_dq", "round_trip", "fk_quat")
 
 
 def fk_bytes_per_pose(n_joints: int) -> int:
     return 64 * n_joints + 12  # read 16J + 12, write 12J + 36J
+
+
+def op_bytes_per_pose(op: str, n_joints: int) -> int:
+    return {"fk": 64 * n_joints + 12, "to_dq": 48 * n_joints + 12, "from_dq": 60 * n_joints,
+            "round_trip": 108 * n_joints + 12, "fk_quat": 44 * n_joints + 12}[op]
 
 
 def measured_peak():
@@ -236,6 +243,29 @@ def run_ours(args):
         _lib.check(lib.pmb_fk_f32(rot.data_ptr(), gpos.data_ptr(), 3, off.data_ptr(), 0, par.ctypes.data, frames,
                                   n_joints, pos.data_ptr(), rotm.data_ptr(), stream.cuda_stream))
 
+    if args.kernel_only and args.op != "fk":
+        del rotm
+        dq = torch.empty((frames, n_joints, 8), device=dev, dtype=torch.float32)
+        rots = torch.empty((frames, n_joints, 4), device=dev, dtype=torch.float32)
+        off0 = np.zeros(3, dtype=np.float32)
+        st = stream.cuda_stream
+
+        def to_dq():
+            _lib.check(lib.pmb_to_root_dual_quat_f32(rot.data_ptr(), gpos.data_ptr(), 3, par.ctypes.data, off.data_ptr(),
+                                                     off0.ctypes.data, frames, n_joints, dq.data_ptr(), st))
+
+        def from_dq():
+            _lib.check(lib.pmb_from_root_dual_quat_f32(dq.data_ptr(), par.ctypes.data, frames, n_joints, pos.data_ptr(),
+                                                       rots.data_ptr(), st))
+
+        def fk_quat():
+            _lib.check(lib.pmb_fk_quat_f32(rot.data_ptr(), gpos.data_ptr(), 3, off.data_ptr(), 0, par.ctypes.data, frames,
+                                           n_joints, pos.data_ptr(), rots.data_ptr(), st))
+
+        to_dq()
+        step = {"to_dq": to_dq, "from_dq": from_dq, "fk_quat": fk_quat,
+                "round_trip": lambda: (to_dq(), from_dq())}[args.op]
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -265,9 +295,9 @@ def run_ours(args):
 
     if args.kernel_only:
         if rank == 0:
-            bytes_per_launch = fk_bytes_per_pose(n_joints) * frames
+            bytes_per_launch = op_bytes_per_pose(args.op, n_joints) * frames
             kernel_ms = ms_max / args.steps
-            print(json.dumps({"workload": args.workload, "ms_per_step": kernel_ms, "value": value,
+            print(json.dumps({"workload": args.workload, "op": args.op, "ms_per_step": kernel_ms, "value": value,
                               "GBps": bytes_per_launch / (kernel_ms * 1e-3) / 1e9,
                               "env_chunk": os.environ.get("PMB_FK_CHUNK")}), flush=True)
         sampler.stop_flag.set()
@@ -383,6 +413,7 @@ def main():
     ap.add_argument("--workload", default="fk_1m_x_22", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="development: skip the e2e and CPU legs")
+    ap.add_argument("--op", default="fk", choices=DEV_OPS, help="with --kernel-only: which op of the path to time")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

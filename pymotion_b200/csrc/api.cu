@@ -149,7 +149,7 @@ int launch_fk_cfg(const FkArgs &a, const DeviceProps &dp) {
     int rc = set_smem(kernel, smem);
     if (rc) return rc;
     CUtensorMap tm;
-    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kFkChunk))) return rc;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk))) return rc;
     // persistent grid: as many blocks as are resident at once; warps walk the tiles round robin
     const long long tiles = (a.n_frames + 31) / 32;
     int per_sm = 0;
@@ -181,13 +181,13 @@ int launch_fk_group(const FkArgs &a, const DeviceProps &dp) {
         if (force_warps >= 0 && force_warps != warps) return false;
         return fk_fits(group, VEC, RW, warps, a, dp);
     };
-    if constexpr (FULL) {
-        if (want(0, 8)) return launch_fk_cfg<0, 8, VEC, PF, QO>(a, dp);
-        if (want(0, 6)) return launch_fk_cfg<0, 6, VEC, PF, QO>(a, dp);
-        if (want(0, 5)) return launch_fk_cfg<0, 5, VEC, PF, QO>(a, dp);
-    }
+    // Measured on B200: whole-row staging with 4 warps per SM is the fastest layout whenever it
+    // fits (1M x 22: 0.242 ms; 5 warps 0.262, 3 warps 0.298); otherwise the largest flush group that keeps
+    // 4 warps per block wins (4M x 52: G = 16 4.77 TB/s vs dense with 2 warps 3.2 TB/s).
     if (want(0, 4)) return launch_fk_cfg<0, 4, VEC, PF, QO>(a, dp);
     if constexpr (FULL) {
+        if (force_warps == 5 && want(0, 5)) return launch_fk_cfg<0, 5, VEC, PF, QO>(a, dp);
+        if (force_warps == 2 && want(0, 2)) return launch_fk_cfg<0, 2, VEC, PF, QO>(a, dp);
         if (want(32, 4)) return launch_fk_cfg<32, 4, VEC, PF, QO>(a, dp);
         if (want(16, 4)) return launch_fk_cfg<16, 4, VEC, PF, QO>(a, dp);
     }
@@ -342,25 +342,42 @@ int pmb_to_root_dual_quat_f32(const float *rotations, const float *global_pos, i
     if (n_frames == 0) return PMB_OK;
     DeviceProps dp;
     if ((rc = device_props(dp))) return rc;
-    constexpr int C = 8;
-    using Tile = pmb::DqTile<C>;
-    const int tab = (n_joints * 16 + 127) & ~127;
+    if (n_frames > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames must be below 2^31 per call");
+    // Joints per flush.  Dual quaternions are whole 32-byte sectors, so partial flushes cost DRAM little and
+    // occupancy matters more than for fk (measured, 1M x 22: whole rows / 4 warps per SM 0.239 ms, 8 joints /
+    // 12 warps 0.214 ms, 16 joints / 8 warps 0.186 ms): take the largest group that still lets TWO 4-warp
+    // blocks share an SM.
+    constexpr int WARPS = 4;
+    const int budget = (dp.smem_optin - 2048) / 2;
+    int group = n_joints;
+    if (pmb::dq_geom(group, WARPS, n_joints, n_slots).block_bytes > budget) {
+        group = ((n_joints + 7) / 8) * 8;
+        while (group > 8 && pmb::dq_geom(group, WARPS, n_joints, n_slots).block_bytes > budget) group -= 8;
+    }
+    if (const char *env = getenv("PMB_DQ_GROUP")) {
+        const int v = atoi(env);
+        if (v >= 8 && v % 8 == 0 && v < n_joints) group = v;
+    }
+    const int smem = pmb::dq_geom(group, WARPS, n_joints, n_slots).block_bytes;
+    if (smem > dp.smem_optin)
+        return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", n_slots);
+    auto kernel = pmb::to_root_dq_kernel<WARPS>;
+    if ((rc = set_smem(kernel, smem))) return rc;
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, rotations, n_frames, n_joints, pmb::kChunk))) return rc;
+    int per_sm = 0;
+    PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "to_root_dual_quat kernel does not fit on an SM");
+    per_sm = std::max(1, std::min(per_sm, env_int("PMB_DQ_BLOCKS_PER_SM", per_sm)));
     const long long tiles = (n_frames + 31) / 32;
-    auto launch = [&](auto kernel, int warps) -> int {
-        const int smem = tab + warps * Tile::warp_bytes(n_slots);
-        int r = set_smem(kernel, smem);
-        if (r) return r;
-        const long long blocks = (tiles + warps - 1) / warps;
-        if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
-        kernel<<<static_cast<unsigned>(blocks), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-            reinterpret_cast<const float4 *>(rotations), global_pos, gpos_frame_stride, offsets,
-            reinterpret_cast<float4 *>(dq), n_frames, n_joints, n_slots, prog);
-        PMB_CUDA(cudaGetLastError());
-        return PMB_OK;
-    };
-    if (tab + 4 * Tile::warp_bytes(n_slots) <= dp.smem_optin) return launch(pmb::to_root_dq_kernel<C, 4>, 4);
-    if (tab + Tile::warp_bytes(n_slots) <= dp.smem_optin) return launch(pmb::to_root_dq_kernel<C, 1>, 1);
-    return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", n_slots);
+    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
+    auto magic_of = [](int d) { return static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(d)) + 1u; };
+    const int tail = n_joints % group ? n_joints % group : group;
+    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+        tm, global_pos, gpos_frame_stride, offsets, reinterpret_cast<float4 *>(dq), n_frames, n_joints, n_slots, group,
+        magic_of(2 * group), magic_of(2 * tail), prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
 }
 
 int pmb_from_root_dual_quat_f32(const float *dq, const int64_t *parents_host, int64_t n_frames, int32_t n_joints,

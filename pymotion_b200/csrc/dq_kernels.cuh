@@ -4,112 +4,176 @@
 //   from_global_rotations ops/skeleton.py:64-93    no chain: thread per (frame, joint)
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace pmb {
 
 // ---------------------------------------------------------------------------
-// to_root_dual_quat.  Same thread-per-frame / warp-per-32-frames scheme as fk,
-// but the chain state is (quaternion, translation) = 7 registers and a dual
-// quaternion is exactly one 32-byte sector, so both staging and copy-out are
-// 16-byte vector accesses: stage row stride 8C+4 words -> (2C+1) float4, odd,
-// conflict-free for the per-thread STS.128.
+// to_root_dual_quat.  Same machinery as fk (fk_kernel.cuh): thread per frame, persistent warp per tile of
+// 32 frames, quaternions through double-buffered TMA boxes, joint program with registers / slots.  The chain
+// state is (quaternion, translation) = 7 registers and a dual quaternion is exactly one 32-byte sector, so
+// the stage holds `group` joints per row as 2*group float4 plus one float4 of padding (odd stride ->
+// conflict-free STS.128) and is copied out with 16-byte accesses.  group = n_joints (whole rows) makes the
+// tile's output one contiguous span; smaller groups are used when that does not fit in shared memory.
 // ---------------------------------------------------------------------------
-template <int C>
-struct DqTile {
-    static constexpr int SQ = 2 * C + 1;                       // row stride in float4
-    static constexpr int kStageBytesPerWarp = kWarp * SQ * 16;
-    static constexpr int kSlotBytesPerWarp = 2 * kWarp * 16;   // (R, t) = 2 float4 per lane
-    __host__ __device__ static constexpr int warp_bytes(int n_slots) {
-        return kStageBytesPerWarp + n_slots * kSlotBytesPerWarp;
-    }
+struct DqGeom {
+    int stride4;      // stage row stride in float4
+    int warp_bytes;   // stage + slots of one warp
+    int block_bytes;
 };
+__host__ __device__ inline DqGeom dq_geom(int group, int warps, int n_joints, int n_slots) {
+    DqGeom g;
+    g.stride4 = 2 * group + 1;
+    g.warp_bytes = kWarp * g.stride4 * 16 + n_slots * 2 * kWarp * 16;
+    g.block_bytes = 1024 + warps * kBoxStages * kBoxBytes + ((n_joints * 16 + 127) & ~127) + warps * g.warp_bytes +
+                    warps * kBoxStages * 8 + warps * kWarp * 4;
+    return g;
+}
 
-template <int C, int WARPS>
+template <int WARPS>
 __global__ void __launch_bounds__(WARPS *kWarp)
-to_root_dq_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, long long gstride,
+to_root_dq_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                   const float *__restrict__ offsets, float4 *__restrict__ dq, long long n_frames, int n_joints,
-                  int n_slots, const __grid_constant__ JointProgram prog) {
-    using Tile = DqTile<C>;
-    constexpr int SQ = Tile::SQ;
-    static_assert((C & (C - 1)) == 0 && 2 * C <= 32, "C must be a power of two <= 16");
-    constexpr int QW = 2 * C;          // float4 per full stage row
-    constexpr int RPI = 32 / QW;       // rows copied per warp iteration
+                  int n_slots, int group, uint32_t magic_full, uint32_t magic_tail,
+                  const __grid_constant__ JointProgram prog) {
+    constexpr int C = kChunk;
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const DqGeom geo = dq_geom(group, WARPS, n_joints, n_slots);
+    const int S4 = geo.stride4;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *tab = reinterpret_cast<float4 *>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 *in_stage = reinterpret_cast<float4 *>(smem_raw + warp * kBoxStages * kBoxBytes);
+    float4 *tab = reinterpret_cast<float4 *>(smem_raw + WARPS * kBoxStages * kBoxBytes);
+    unsigned char *after_tab = reinterpret_cast<unsigned char *>(tab) + ((n_joints * 16 + 127) & ~127);
+    float4 *stage = reinterpret_cast<float4 *>(after_tab + warp * geo.warp_bytes);
+    float4 *slots = stage + kWarp * S4;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(after_tab + WARPS * geo.warp_bytes);
+    const uint32_t bar0 = smem_u32(bars + warp * kBoxStages);
+    const uint32_t in0 = smem_u32(in_stage);
+    const uint32_t fence_word = smem_u32(reinterpret_cast<uint32_t *>(bars + WARPS * kBoxStages) + threadIdx.x);
+
+    const long long n_tiles = (n_frames + kWarp - 1) / kWarp;
+    const long long tile_stride = static_cast<long long>(gridDim.x) * WARPS;
+    long long tile = static_cast<long long>(blockIdx.x) * WARPS + warp;
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < kBoxStages; ++b) mbar_init(bar0 + 8 * b, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    long long la_tile = tile;
+    int la_c0 = 0;
+    auto issue_next = [&](int buf) {  // lane 0 only: the warp's chunks in processing order, across its tiles
+        if (la_tile < n_tiles) {
+            mbar_arrive_expect_tx(bar0 + 8 * buf, kBoxBytes);
+            tma_load_2d(in0 + buf * kBoxBytes, &tm_rot, 4 * la_c0, static_cast<int>(la_tile * kWarp), bar0 + 8 * buf);
+            la_c0 += C;
+            if (la_c0 >= n_joints) la_c0 = 0, la_tile += tile_stride;
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < kBoxStages; ++b) issue_next(b);
+    }
     for (int j = threadIdx.x; j < n_joints; j += WARPS * kWarp)
-        tab[j] = make_float4(offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2], __uint_as_float(prog.code[j]));
+        tab[j] = make_float4(offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2], 0.f);
     __syncthreads();
 
-    const long long f0 = (static_cast<long long>(blockIdx.x) * WARPS + warp) * kWarp;
-    if (f0 >= n_frames) return;
-    const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
-    const long long f = f0 + min(lane, nrows - 1);
+    const int swz = lane & 7;
+    uint32_t kchunk = 0;
+    float gnext[3] = {0.f, 0.f, 0.f};
+    if (tile < n_tiles) {
+        const float *g = gpos + min(tile * kWarp + lane, n_frames - 1) * gstride;
+        gnext[0] = __ldg(g), gnext[1] = __ldg(g + 1), gnext[2] = __ldg(g + 2);
+    }
 
-    unsigned char *wbase = smem_raw + ((n_joints * 16 + 127) & ~127) + warp * Tile::warp_bytes(n_slots);
-    float4 *stage = reinterpret_cast<float4 *>(wbase);
-    float4 *slots = stage + kWarp * SQ;
-    const float4 *qrow = rot + f * n_joints;
+    for (; tile < n_tiles; tile += tile_stride) {
+        const long long f0 = tile * kWarp;
+        const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
+        Quat<float> cr{1.f, 0.f, 0.f, 0.f};
+        Vec3<float> ct{gnext[0], gnext[1], gnext[2]};
+        int gj = 0;
 
-    Quat<float> cr{1.f, 0.f, 0.f, 0.f};
-    Vec3<float> ct{0.f, 0.f, 0.f};
-
-    for (int c0 = 0; c0 < n_joints; c0 += C) {
-        const int cnt = min(C, n_joints - c0);
-        float4 q[C];
+        for (int c0 = 0; c0 < n_joints; c0 += C) {
+            const int cnt = min(C, n_joints - c0);
+            const bool last_chunk = c0 + C >= n_joints;
+            const int buf = kchunk % kBoxStages;
+            mbar_wait(bar0 + 8 * buf, (kchunk / kBoxStages) & 1);
+            ++kchunk;
+            const float4 *in_row = in_stage + buf * (kBoxBytes / 16) + lane * C;
+            float4 q[C];
 #pragma unroll
-        for (int jj = 0; jj < C; ++jj)
-            if (jj < cnt) q[jj] = __ldg(qrow + c0 + jj);
+            for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
+            {   // loads must have LANDED before the box is refilled through the async proxy (see fk_kernel.cuh)
+                uint32_t acc = 0;
 #pragma unroll
-        for (int jj = 0; jj < C; ++jj) {
-            if (jj < cnt) {
-                const int j = c0 + jj;
-                const float4 e = tab[j];
-                const uint32_t code = __float_as_uint(e.w);
-                const Quat<float> r{q[jj].x, q[jj].y, q[jj].z, q[jj].w};
-                if (jj == 0 && c0 == 0) {  // joint 0 carries the root's global rotation and position (:232)
-                    const float *g = gpos + f * gstride;
-                    cr = r;
-                    ct = {__ldg(g), __ldg(g + 1), __ldg(g + 2)};
-                } else if (prog_parent(code) == 0) {  // children of the root stay as they are (:236-237)
-                    cr = r;
-                    ct = {e.x, e.y, e.z};
-                } else {
-                    const uint32_t src = prog_src(code);
-                    if (src != kSrcReg) {
-                        const float4 a = slots[src * 2 * kWarp + lane], b = slots[(src * 2 + 1) * kWarp + lane];
-                        cr = {a.x, a.y, a.z, a.w};
-                        ct = {b.x, b.y, b.z};
+                for (int jj = 0; jj < C; ++jj) acc |= __float_as_uint(q[jj].x) | __float_as_uint(q[jj].w);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
+            }
+            __syncwarp();
+            const long long next_tile = tile + tile_stride;
+            if (lane == 0) issue_next(buf);
+            if (last_chunk && next_tile < n_tiles) {
+                const float *g = gpos + min(next_tile * kWarp + lane, n_frames - 1) * gstride;
+                gnext[0] = __ldg(g), gnext[1] = __ldg(g + 1), gnext[2] = __ldg(g + 2);
+            }
+
+            float4 *st = stage + lane * S4 + 2 * gj;
+#pragma unroll
+            for (int jj = 0; jj < C; ++jj) {
+                if (jj < cnt) {
+                    const int j = c0 + jj;
+                    const uint32_t code = prog.code[j];  // constant bank, warp-uniform
+                    const float4 e = tab[j];
+                    const Quat<float> r{q[jj].x, q[jj].y, q[jj].z, q[jj].w};
+                    if (jj == 0 && c0 == 0) {  // joint 0 carries the root's global rotation and position (:232)
+                        cr = r;
+                    } else if (prog_parent(code) == 0) {  // children of the root stay as they are (:236-237)
+                        cr = r;
+                        ct = {e.x, e.y, e.z};
+                    } else {
+                        const uint32_t src = prog_src(code);
+                        if (src != kSrcReg) {
+                            const float4 a = slots[src * 2 * kWarp + lane], b = slots[(src * 2 + 1) * kWarp + lane];
+                            cr = {a.x, a.y, a.z, a.w};
+                            ct = {b.x, b.y, b.z};
+                        }
+                        const Vec3<float> v = q_rotate(cr, Vec3<float>{e.x, e.y, e.z});  // :238-240
+                        ct = {v.x + ct.x, v.y + ct.y, v.z + ct.z};
+                        cr = q_mul(cr, r);                                                  // :241
                     }
-                    const Vec3<float> v = q_rotate(cr, Vec3<float>{e.x, e.y, e.z});  // :238-240
-                    ct = {v.x + ct.x, v.y + ct.y, v.z + ct.z};
-                    cr = q_mul(cr, r);                                                  // :241
+                    const uint32_t sv = prog_save(code);
+                    if (sv != kNoSave) {
+                        slots[sv * 2 * kWarp + lane] = make_float4(cr.w, cr.x, cr.y, cr.z);
+                        slots[(sv * 2 + 1) * kWarp + lane] = make_float4(ct.x, ct.y, ct.z, 0.f);
+                    }
+                    // dual_quat.py:28-35: q_d = 0.5 * ((0, t) (x) q_r)
+                    const Quat<float> d = q_mul(Quat<float>{0.f, ct.x, ct.y, ct.z}, cr);
+                    st[2 * jj] = make_float4(cr.w, cr.x, cr.y, cr.z);
+                    st[2 * jj + 1] = make_float4(0.5f * d.w, 0.5f * d.x, 0.5f * d.y, 0.5f * d.z);
                 }
-                const uint32_t sv = prog_save(code);
-                if (sv != kNoSave) {
-                    slots[sv * 2 * kWarp + lane] = make_float4(cr.w, cr.x, cr.y, cr.z);
-                    slots[(sv * 2 + 1) * kWarp + lane] = make_float4(ct.x, ct.y, ct.z, 0.f);
-                }
-                // dual_quat.py:28-35: q_d = 0.5 * ((0, t) (x) q_r)
-                const Quat<float> d = q_mul(Quat<float>{0.f, ct.x, ct.y, ct.z}, cr);
-                stage[lane * SQ + 2 * jj] = make_float4(cr.w, cr.x, cr.y, cr.z);
-                stage[lane * SQ + 2 * jj + 1] = make_float4(0.5f * d.w, 0.5f * d.x, 0.5f * d.y, 0.5f * d.z);
             }
-        }
-        __syncwarp();
-        const int col = lane & (QW - 1), sub = lane / QW;
-        float4 *g = dq + ((f0 + sub) * n_joints + c0) * 2 + col;
-        const float4 *s = stage + sub * SQ + col;
-        const long long gstep = static_cast<long long>(RPI) * n_joints * 2;
-        if (col < 2 * cnt) {
+            gj += cnt;
+
+            if (gj == group || last_chunk) {
+                __syncwarp();
+                // rows of 2*gj float4 -> global rows of pitch 2*n_joints float4; flat unit i = row * (2*gj) + col
+                const int w4 = 2 * gj;
+                const uint32_t magic = (gj == group) ? magic_full : magic_tail;
+                const int n4 = nrows * w4;
+                float4 *g = dq + (f0 * n_joints + (c0 + cnt - gj)) * 2;
+                const int pitch4 = 2 * n_joints;
 #pragma unroll 4
-            for (int r = sub; r < nrows; r += RPI) {
-                __stcs(g, *s);
-                g += gstep, s += RPI * SQ;
+                for (int i = lane; i < n4; i += kWarp) {
+                    const int r = static_cast<int>(__umulhi(static_cast<uint32_t>(i), magic));
+                    const int c = i - r * w4;
+                    g[static_cast<long long>(r) * pitch4 + c] = stage[r * S4 + c];
+                }
+                __syncwarp();
+                gj = 0;
             }
         }
-        __syncwarp();
     }
 }
 

@@ -34,6 +34,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 #ifndef PMB_ST_POLICY
 #define PMB_ST_POLICY 0
@@ -66,48 +67,9 @@ __device__ __forceinline__ void out_store(V *p, const V &v) {
 #endif
 }
 
-// ---- mbarrier / TMA (PTX) -------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-        "l"(tm), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-
-// 1-D bulk copy shared -> global (TMA engine, no register traffic); completion tracked per thread by bulk groups
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 __host__ __device__ constexpr int ce_gcd(int a, int b) { return b == 0 ? a : ce_gcd(b, a % b); }
 __host__ __device__ constexpr int ce_lcm(int a, int b) { return a / ce_gcd(a, b) * b; }
 
-constexpr int kFkChunk = 8;                              // joints per TMA box (128-byte rows, SWIZZLE_128B)
-constexpr int kFkInBytes = kWarp * kFkChunk * 16;        // one box: dense (swizzled) [32][8] float4
-constexpr int kFkStages = 2;                             // boxes in flight per warp (prefetch depth in chunks)
 
 // Shared-memory geometry, shared by host (sizing) and device.  group = 0: dense rows of n_joints joints.
 struct FkGeom {
@@ -122,8 +84,8 @@ __host__ __device__ inline FkGeom fk_geom(int group, int vec, int rw, int warps,
     g.sp = group ? fk_pad(3 * group, vec) : 3 * n_joints;
     g.warp_bytes = ((kWarp * (g.sr + g.sp) * 4 + 15) & ~15) + n_slots * 3 * kWarp * 16;
     // 1 KB slack to align the TMA boxes to 1024 | boxes | joint table | per-warp stage + slots | mbarriers | fence words
-    g.block_bytes = 1024 + warps * kFkStages * kFkInBytes + ((n_joints * 16 + 127) & ~127) + warps * g.warp_bytes +
-                    warps * kFkStages * 8 + warps * kWarp * 4;
+    g.block_bytes = 1024 + warps * kBoxStages * kBoxBytes + ((n_joints * 16 + 127) & ~127) + warps * g.warp_bytes +
+                    warps * kBoxStages * 8 + warps * kWarp * 4;
     return g;
 }
 
@@ -206,7 +168,7 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
                 float *__restrict__ rout, long long n_frames, int n_joints, int n_slots,
                 const __grid_constant__ JointProgram prog) {
     constexpr int RW = QO ? 4 : 9;
-    constexpr int C = kFkChunk;
+    constexpr int C = kChunk;
     constexpr bool DENSE = (G == 0);
     static_assert(G % C == 0, "a flush group is a whole number of TMA chunks");
 
@@ -218,16 +180,16 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     const FkGeom geo = fk_geom(G, VEC, RW, WARPS, n_joints, n_slots);
     const int SR = DENSE ? geo.sr : fk_pad(RW * G, VEC), SP = DENSE ? geo.sp : fk_pad(3 * G, VEC);
 
-    float4 *in_stage = reinterpret_cast<float4 *>(smem_raw + warp * kFkStages * kFkInBytes);  // kFkStages boxes
-    float4 *tab = reinterpret_cast<float4 *>(smem_raw + WARPS * kFkStages * kFkInBytes);
+    float4 *in_stage = reinterpret_cast<float4 *>(smem_raw + warp * kBoxStages * kBoxBytes);  // kBoxStages boxes
+    float4 *tab = reinterpret_cast<float4 *>(smem_raw + WARPS * kBoxStages * kBoxBytes);
     unsigned char *after_tab = reinterpret_cast<unsigned char *>(tab) + ((n_joints * 16 + 127) & ~127);
     float *Rst = reinterpret_cast<float *>(after_tab + warp * geo.warp_bytes);
     float *Pst = Rst + kWarp * SR;
     float4 *slots = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(Rst) + ((kWarp * (SR + SP) * 4 + 15) & ~15));
     uint64_t *bars = reinterpret_cast<uint64_t *>(after_tab + WARPS * geo.warp_bytes);
-    const uint32_t bar0 = smem_u32(bars + warp * kFkStages);
+    const uint32_t bar0 = smem_u32(bars + warp * kBoxStages);
     const uint32_t in0 = smem_u32(in_stage);
-    const uint32_t fence_word = smem_u32(reinterpret_cast<uint32_t *>(bars + WARPS * kFkStages) + threadIdx.x);  // see the chunk loop
+    const uint32_t fence_word = smem_u32(reinterpret_cast<uint32_t *>(bars + WARPS * kBoxStages) + threadIdx.x);  // see the chunk loop
 
     // Persistent warps: all tiles cost the same, so a static round robin balances.
     const long long n_tiles = (n_frames + kWarp - 1) / kWarp;
@@ -235,7 +197,7 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     long long tile = static_cast<long long>(blockIdx.x) * WARPS + warp;
     if (lane == 0) {
 #pragma unroll
-        for (int b = 0; b < kFkStages; ++b) mbar_init(bar0 + 8 * b, 1);
+        for (int b = 0; b < kBoxStages; ++b) mbar_init(bar0 + 8 * b, 1);
         fence_barrier_init();
     }
     __syncwarp();
@@ -244,15 +206,15 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     int la_c0 = 0;
     auto issue_next = [&](int buf) {  // lane 0 only
         if (la_tile < n_tiles) {
-            mbar_arrive_expect_tx(bar0 + 8 * buf, kFkInBytes);
-            tma_load_2d(in0 + buf * kFkInBytes, &tm_rot, 4 * la_c0, static_cast<int>(la_tile * kWarp), bar0 + 8 * buf);
+            mbar_arrive_expect_tx(bar0 + 8 * buf, kBoxBytes);
+            tma_load_2d(in0 + buf * kBoxBytes, &tm_rot, 4 * la_c0, static_cast<int>(la_tile * kWarp), bar0 + 8 * buf);
             la_c0 += C;
             if (la_c0 >= n_joints) la_c0 = 0, la_tile += tile_stride;
         }
     };
-    if (lane == 0) {  // the first kFkStages chunks: in flight while the block loads its joint table
+    if (lane == 0) {  // the first kBoxStages chunks: in flight while the block loads its joint table
 #pragma unroll
-        for (int b = 0; b < kFkStages; ++b) issue_next(b);
+        for (int b = 0; b < kBoxStages; ++b) issue_next(b);
     }
     for (int j = threadIdx.x; j < n_joints; j += WARPS * kWarp) {
         float4 e;
@@ -269,7 +231,7 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     // TMA 128-byte swizzle: 16-byte chunk jj of row r lands at chunk jj ^ (r & 7)
     const int swz = lane & 7;
     const int rpitch = n_joints * RW, ppitch = n_joints * 3;
-    uint32_t kchunk = 0;  // chunks consumed so far: buffer = kchunk % kFkStages, parity = (kchunk / kFkStages) & 1
+    uint32_t kchunk = 0;  // chunks consumed so far: buffer = kchunk % kBoxStages, parity = (kchunk / kBoxStages) & 1
     // root position of the warp's NEXT tile, fetched one chunk early like its quaternions
     float gnext[3] = {0.f, 0.f, 0.f};
     if (tile < n_tiles) {
@@ -289,10 +251,10 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
         for (int c0 = 0; c0 < n_joints; c0 += C) {
             const int cnt = min(C, n_joints - c0);
             const bool last_chunk = c0 + C >= n_joints;
-            const int buf = kchunk % kFkStages;
-            mbar_wait(bar0 + 8 * buf, (kchunk / kFkStages) & 1);
+            const int buf = kchunk % kBoxStages;
+            mbar_wait(bar0 + 8 * buf, (kchunk / kBoxStages) & 1);
             ++kchunk;
-            const float4 *in_row = in_stage + buf * (kFkInBytes / 16) + lane * C;
+            const float4 *in_row = in_stage + buf * (kBoxBytes / 16) + lane * C;
             float4 q[C];
 #pragma unroll
             for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
@@ -308,7 +270,7 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             }
             __syncwarp();  // every lane has its quaternions in registers: the buffer can be refilled
             const long long next_tile = tile + tile_stride;
-            if (lane == 0) issue_next(buf);  // refill with the chunk kFkStages ahead (this tile's or the next tile's)
+            if (lane == 0) issue_next(buf);  // refill with the chunk kBoxStages ahead (this tile's or the next tile's)
             if (last_chunk && next_tile < n_tiles) {
                 const float *g = gpos + min(next_tile * kWarp + lane, n_frames - 1) * gstride;
                 gnext[0] = __ldg(g), gnext[1] = __ldg(g + 1), gnext[2] = __ldg(g + 2);

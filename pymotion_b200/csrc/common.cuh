@@ -131,6 +131,20 @@ __device__ __forceinline__ Quat<T> q_from_matrix(const T m[9]) {
     return q_normalize(q, T(1e-8));
 }
 
+// Same branch selection, normalisation through q_normalize_fast (used inside the fused fk_quat kernel).
+__device__ __forceinline__ Quat<float> q_from_matrix_fast(const float m[9]) {
+    const float m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5], m20 = m[6], m21 = m[7],
+                m22 = m[8];
+    const bool neg = m22 < 0.f;
+    const bool alt = neg ? (m00 > m11) : (m00 < -m11);
+    // the four candidates of quat.py:115-153 selected without divergent control flow
+    const Quat<float> a = neg ? Quat<float>{m21 - m12, 1.f + m00 - m11 - m22, m10 + m01, m02 + m20}
+                              : Quat<float>{m10 - m01, m02 + m20, m21 + m12, 1.f - m00 - m11 + m22};
+    const Quat<float> b = neg ? Quat<float>{m02 - m20, m10 + m01, 1.f - m00 + m11 - m22, m21 + m12}
+                              : Quat<float>{1.f + m00 + m11 + m22, m21 - m12, m02 - m20, m10 - m01};
+    return q_normalize_fast(alt ? a : b, 1e-8f);
+}
+
 // Rigid transform [R | p], R row-major.  12 registers.
 template <typename T>
 struct Xform {

@@ -316,7 +316,7 @@ fk_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
                     }
                     float o[RW];
                     if (QO) {
-                        const Quat<float> gq = q_from_matrix(cur.r);
+                        const Quat<float> gq = q_from_matrix_fast(cur.r);
                         o[0] = gq.w, o[1] = gq.x, o[2] = gq.y, o[3] = gq.z;
                     } else {
 #pragma unroll

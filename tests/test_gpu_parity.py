@@ -392,3 +392,57 @@ def test_host_buffer_entry_point(sk, golden_fk):
     assert_allclose(pos.numpy(), want_pos, **TOL)
     assert_allclose(rotm.numpy(), want_rotm, **TOL)
     lib.pmb_release_workspace()
+
+
+# ---------------------------------------------------------------- every kernel variant the host can select
+@pytest.mark.parametrize("knobs", [
+    {"PMB_FK_GROUP": "0", "PMB_FK_WARPS": "4"},   # whole-row stage + TMA bulk store (default for small skeletons)
+    {"PMB_FK_GROUP": "0", "PMB_FK_WARPS": "5"},
+    {"PMB_FK_GROUP": "0", "PMB_FK_WARPS": "2"},
+    {"PMB_FK_GROUP": "32", "PMB_FK_WARPS": "4"},  # padded stage, periodic copy-out
+    {"PMB_FK_GROUP": "16", "PMB_FK_WARPS": "4"},
+    {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "4"},
+    {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "1"},
+    {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "4", "PMB_FK_BLOCKS_PER_SM": "1"},
+])
+@pytest.mark.parametrize("name,n_frames", [("body22", 4099), ("smplh52", 2050), ("deep65", 1031), ("chain3", 777)])
+def test_fk_every_variant(sk, monkeypatch, knobs, name, n_frames):
+    """The launch heuristic picks one variant per shape; force each of them (ragged frame counts so the
+    remainder tile and remainder group paths run) and compare with the oracle.  A variant that does not
+    fit the shape (e.g. whole rows of a 65-joint skeleton with 5 warps) must refuse, not fall back."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=len(par) + n_frames)
+    want_pos, want_rotm = orc.fk(rot, gp, off, par)
+    try:
+        pos, rotm = sk.fk(rot, gp, off, par)
+    except ValueError as e:
+        assert "select no available variant" in str(e)
+        return
+    assert_allclose(pos, want_pos, **TOL)
+    assert_allclose(rotm, want_rotm, **TOL)
+    # per-frame offsets and quaternion output share the kernel: the two extremes of the group range
+    if knobs["PMB_FK_GROUP"] in ("0", "8") and knobs["PMB_FK_WARPS"] == "4":
+        off_pf = np.tile(off, (n_frames, 1, 1)) * np.linspace(0.5, 1.5, n_frames, dtype=np.float32)[:, None, None]
+        want_pos, want_rotm = orc.fk(rot, gp, off_pf, par)
+        try:
+            pos, rotm = sk.fk(rot, gp, off_pf, par)
+            assert_allclose(pos, want_pos, **TOL)
+            assert_allclose(rotm, want_rotm, **TOL)
+            pos, grot = sk.fk_quat(rot, gp, off, par)
+            want_q = orc.quat_from_matrix(orc.fk(rot, gp, off, par)[1])
+            assert_allclose(np.abs(np.sum(grot * want_q, axis=-1)), 1.0, atol=1e-5)
+        except ValueError as e:
+            assert "select no available variant" in str(e)
+
+
+@pytest.mark.parametrize("group", [None, "8", "16", "24"])
+@pytest.mark.parametrize("name,n_frames", [("body22", 4099), ("smplh52", 2050), ("deep65", 1031), ("chain3", 777)])
+def test_to_root_dual_quat_every_group(sk, monkeypatch, group, name, n_frames):
+    if group is not None:
+        monkeypatch.setenv("PMB_DQ_GROUP", group)
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=7 * len(par) + n_frames)
+    dq = sk.to_root_dual_quat(rot, gp, par, off)
+    assert_allclose(dq, orc.to_root_dual_quat(rot, gp, par, off), **TOL)

@@ -1,5 +1,6 @@
 #!/bin/bash
-# One GPU-box visit: environment facts, GPU parity tests, bench, ncu launch list, ncu full capture of fk.
+# One GPU-box visit: environment facts, smoke, GPU parity tests, bench (both arms), ncu launch list,
+# ncu full capture of the fk kernel.
 set -u
 mkdir -p gpurun_out
 {
@@ -8,12 +9,13 @@ mkdir -p gpurun_out
 } > gpurun_out/box.txt 2>&1
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_ref.json 2> gpurun_out/bench.err
+timeout 600 python bench.py > gpurun_out/bench.json 2>> gpurun_out/bench.err; echo "bench rc=$?"
 cat gpurun_out/bench.json
-timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fk_chain -s 3 -c 1 -f -o gpurun_out/prof_fk \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out
+    python bench.py --kernel-only --steps 3 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+bash tools/gpu_ops.sh > /dev/null 2>&1
+ls -la gpurun_out | head -30

@@ -59,6 +59,9 @@ typedef enum pmb_status {
 int pmb_version(void);
 const char *pmb_last_error(void);
 const char *pmb_status_string(int status);
+/* Diagnostics: which kernel variant (template arguments, grid, shared memory) the last fk /
+ * to_root_dual_quat launch on this thread picked.  Used by bench.py and the variant tests. */
+const char *pmb_last_variant(void);
 
 /* Number of SMs / name of the current device (diagnostics, used by bench.py). */
 int pmb_device_info(int *sm_count, int *cc_major, int *cc_minor, char *name, int name_len);

@@ -22,6 +22,7 @@ _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.
 SIGNATURES = {
     "pmb_version": [],
     "pmb_last_error": [],
+    "pmb_last_variant": [],
     "pmb_status_string": [ctypes.c_int],
     "pmb_device_info": [_vp, _vp, _vp, ctypes.c_char_p, ctypes.c_int],
     "pmb_build_joint_program": [_vp, _i32, _vp],
@@ -43,7 +44,7 @@ SIGNATURES = {
     "pmb_dq_from_translation_f32": [_vp, _vp, _i64, _vp],
     "pmb_dq_to_rotation_translation_f32": [_vp, _vp, _vp, _i64, _vp],
 }
-_RESTYPES = {"pmb_last_error": ctypes.c_char_p, "pmb_status_string": ctypes.c_char_p, "pmb_release_workspace": None}
+_RESTYPES = {"pmb_last_error": ctypes.c_char_p, "pmb_last_variant": ctypes.c_char_p, "pmb_status_string": ctypes.c_char_p, "pmb_release_workspace": None}
 
 _lib = None
 

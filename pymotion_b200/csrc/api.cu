@@ -15,11 +15,20 @@
 #include "dq_kernels.cuh"
 #include "elementwise.cuh"
 #include "fk_kernel.cuh"
+#include "fk_rows_kernel.cuh"
 #include "joint_program.h"
 
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local char g_variant[128] = "";  // which kernel variant the last launch on this thread picked
+
+void note_variant(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_variant, sizeof(g_variant), fmt, ap);
+    va_end(ap);
+}
 
 int fail(int status, const char *fmt, ...) {
     va_list ap;
@@ -157,11 +166,63 @@ int launch_fk_cfg(const FkArgs &a, const DeviceProps &dp) {
     if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk kernel does not fit on an SM (%d bytes of shared memory)", smem);
     per_sm = std::max(1, std::min(per_sm, env_int("PMB_FK_BLOCKS_PER_SM", per_sm)));
     const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
+    note_variant("fk_chain_kernel<G=%d,WARPS=%d,VEC=%d,PF=%d,QO=%d> grid=%lld smem=%d", G, WARPS, VEC, int(PF), int(QO), blocks, smem);
     kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.ostride,
                                                                         a.pos, a.rout, a.n_frames, a.n_joints,
                                                                         a.n_slots, *a.prog);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
+}
+
+// ---- fk, row-team kernel (fk_rows_kernel.cuh) ------------------------------------
+template <int S>
+int launch_fk_rows_cfg(const FkArgs &a, const DeviceProps &dp) {
+    auto kernel = pmb::fk_rows_kernel<S>;
+    const int smem = pmb::fk_rows_geom(S, a.n_joints).block_bytes;
+    int rc = set_smem(kernel, smem);
+    if (rc) return rc;
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk))) return rc;
+    const long long tiles = (a.n_frames + 31) / 32;
+    int per_sm = 0;
+    PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, pmb::kRowThreads, smem));
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk row kernel does not fit on an SM (%d bytes of shared memory)", smem);
+    per_sm = std::max(1, std::min(per_sm, env_int("PMB_FK_BLOCKS_PER_SM", per_sm)));
+    const long long blocks = std::min<long long>(tiles, static_cast<long long>(per_sm) * dp.sm_count);
+    note_variant("fk_rows_kernel<S=%d> grid=%lld (%d teams/SM) smem=%d", S, blocks, per_sm, smem);
+    kernel<<<static_cast<unsigned>(blocks), pmb::kRowThreads, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos,
+                                                                                a.rout, a.n_frames, a.n_joints, *a.prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// Teams (blocks) of the row kernel that fit on an SM with S box stages: every block also costs 1 KB of
+// system shared memory.
+inline int fk_rows_teams(int stages, const FkArgs &a, const DeviceProps &dp) {
+    const int bytes = pmb::fk_rows_geom(stages, a.n_joints).block_bytes;
+    if (bytes > dp.smem_optin) return 0;
+    return std::min(12, (dp.smem_optin + 1024) / (bytes + 1024));
+}
+
+// Returns true and launches if the row-team kernel is the better choice (PMB_FK_ROWS = 0 / 1 forces).
+bool try_fk_rows(const FkArgs &a, const DeviceProps &dp, int &rc) {
+    const int force = env_int("PMB_FK_ROWS", -1);
+    if (force == 0) return false;
+    if (force != 1 && (getenv("PMB_FK_GROUP") || getenv("PMB_FK_WARPS"))) return false;  // a chain-kernel variant is being forced
+    int stages = env_int("PMB_FK_STAGES", -1);
+    if (stages < 0) {
+        // the deepest ring that does not cost a team
+        stages = 2;
+        for (int s = 3; s <= 4; ++s)
+            if (fk_rows_teams(s, a, dp) == fk_rows_teams(2, a, dp)) stages = s;
+    }
+    if (stages < 2 || stages > 4 || fk_rows_teams(stages, a, dp) < 1) {
+        if (force == 1) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_ROWS=1: the row kernel does not fit (stages %d)", stages); return true; }
+        return false;
+    }
+    if (force != 1 && fk_rows_teams(stages, a, dp) < 2) return false;  // one team per SM cannot hide its own drain
+    rc = stages == 2 ? launch_fk_rows_cfg<2>(a, dp) : stages == 3 ? launch_fk_rows_cfg<3>(a, dp) : launch_fk_rows_cfg<4>(a, dp);
+    return true;
 }
 
 inline bool fk_fits(int group, int vec, int rw, int warps, const FkArgs &a, const DeviceProps &dp) {
@@ -224,6 +285,10 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
     if ((rc = device_props(dp))) return rc;
     FkArgs a{rot, gpos, offsets, gstride, ostride, pos, rout, n_frames, n_joints, n_slots, &prog,
              static_cast<cudaStream_t>(stream)};
+    if (ostride == 0 && !quat_out) {
+        int rrc = PMB_OK;
+        if (try_fk_rows(a, dp, rrc)) return rrc;
+    }
     if (ostride == 0) return quat_out ? launch_fk<false, true>(a, dp) : launch_fk<false, false>(a, dp);
     return quat_out ? launch_fk<true, true>(a, dp) : launch_fk<true, false>(a, dp);
 }
@@ -271,6 +336,7 @@ extern "C" {
 
 int pmb_version(void) { return PMB_VERSION; }
 const char *pmb_last_error(void) { return g_err; }
+const char *pmb_last_variant(void) { return g_variant; }
 
 const char *pmb_status_string(int status) {
     switch (status) {
@@ -373,6 +439,7 @@ int pmb_to_root_dual_quat_f32(const float *rotations, const float *global_pos, i
     const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
     auto magic_of = [](int d) { return static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(d)) + 1u; };
     const int tail = n_joints % group ? n_joints % group : group;
+    note_variant("to_root_dq_kernel<WARPS=%d> group=%d grid=%lld smem=%d", WARPS, group, blocks, smem);
     kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
         tm, global_pos, gpos_frame_stride, offsets, reinterpret_cast<float4 *>(dq), n_frames, n_joints, n_slots, group,
         magic_of(2 * group), magic_of(2 * tail), prog);

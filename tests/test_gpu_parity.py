@@ -437,6 +437,31 @@ def test_fk_every_variant(sk, monkeypatch, knobs, name, n_frames):
             assert "select no available variant" in str(e)
 
 
+@pytest.mark.parametrize("knobs", [
+    {"PMB_FK_ROWS": "1"},                                             # ring depth picked by the host
+    {"PMB_FK_ROWS": "1", "PMB_FK_STAGES": "2"},
+    {"PMB_FK_ROWS": "1", "PMB_FK_STAGES": "3"},
+    {"PMB_FK_ROWS": "1", "PMB_FK_STAGES": "4"},
+    {"PMB_FK_ROWS": "1", "PMB_FK_STAGES": "2", "PMB_FK_BLOCKS_PER_SM": "1"},   # many tiles per team
+    {"PMB_FK_ROWS": "0"},                                             # the thread-per-frame chain kernel
+])
+@pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_050), ("deep65", 10_031), ("chain3", 777),
+                                           ("body22", 31)])
+def test_fk_row_team_kernel(sk, monkeypatch, knobs, name, n_frames):
+    """The row-team kernel (three warps per tile, loader and drainer threads): forced for every ring depth,
+    with ragged frame counts (remainder tile through the drainer's 16-byte tail path) and with one block per
+    SM so that every team walks several tiles (stage reuse, ring wrap-around)."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=3 * len(par) + n_frames)
+    want_pos, want_rotm = orc.fk(rot, gp, off, par)
+    for _ in range(2):  # twice: the second launch overwrites the same outputs
+        pos, rotm = sk.fk(rot, gp, off, par)
+        assert_allclose(pos, want_pos, **TOL)
+        assert_allclose(rotm, want_rotm, **TOL)
+
+
 @pytest.mark.parametrize("group", [None, "8", "16", "24"])
 @pytest.mark.parametrize("name,n_frames", [("body22", 4099), ("smplh52", 2050), ("deep65", 1031), ("chain3", 777)])
 def test_to_root_dual_quat_every_group(sk, monkeypatch, group, name, n_frames):

@@ -28,6 +28,10 @@ __all__ = [
     "dq_from_rotation_translation", "dq_to_rotation_translation",
     "dq_from_translation", "fk", "to_root_dual_quat", "from_root_dual_quat",
     "from_global_rotations",
+    # the rest of the quat / dual_quat surface
+    "vec_normalize", "quat_from_angle_axis", "quat_from_scaled_angle_axis", "quat_from_euler", "quat_to_euler",
+    "quat_to_angle_axis", "quat_to_scaled_angle_axis", "quat_unroll", "quat_slerp", "quat_from_to",
+    "quat_from_to_axis", "dq_is_unit", "dq_normalize", "dq_unroll",
 ]
 
 
@@ -237,3 +241,193 @@ def from_global_rotations(global_quats, parents):
     up = quat_inverse(global_quats[..., parents[1:], :])
     local[..., 1:, :] = quat_mul(up, global_quats[..., 1:, :])
     return local
+
+
+# ----------------------------------------------------------------------------
+# the rest of the quaternion surface      (rotations/quat.py)
+# dtype promotions of the reference are reproduced on purpose (noted per function)
+# ----------------------------------------------------------------------------
+_AXIS_INDEX = {"x": 0, "y": 1, "z": 2}
+
+
+def vec_normalize(v, eps: float = 1e-8):
+    """ops/vector.py:4-19: v / (|v| + eps)."""
+    return v / (np.linalg.norm(v, axis=-1, keepdims=True) + eps)
+
+
+def quat_from_angle_axis(angle, axis):
+    """quat.py:24-40: (cos(a/2), sin(a/2) * axis); angle is [..., 1], axis [..., 3] unit."""
+    half = angle / 2.0
+    return np.concatenate((np.cos(half), np.sin(half) * axis), axis=-1)
+
+
+def quat_from_scaled_angle_axis(scaledaxis):
+    """quat.py:6-21: angle = |v|, axis = v / angle (0/0 = nan for the null vector, as in the reference)."""
+    angle = np.linalg.norm(scaledaxis, axis=-1)[..., np.newaxis]
+    return quat_from_angle_axis(angle, scaledaxis / angle)
+
+
+def _order_indices(order):
+    """'x'|'y'|'z' -> 0|1|2 per element (the reference does this with np.apply_along_axis, quat.py:72-81, :191-193)."""
+    order = np.asarray(order)
+    idx = np.full(order.shape, -1, dtype=np.int64)
+    for ch, k in _AXIS_INDEX.items():
+        idx[order == ch] = k
+    if (idx < 0).any():
+        raise KeyError("order entries must be 'x', 'y' or 'z'")
+    return idx
+
+
+def quat_from_euler(euler, order):
+    """quat.py:43-82: q = q(e0 about order0) (x) q(e1 about order1) (x) q(e2 about order2).  The unit axes are
+    INTEGER arrays in the reference (quat.py:65-69), so sin * axis -- and everything after it -- is float64
+    even for float32 angles (cos / sin themselves are taken in the input dtype)."""
+    assert euler.shape[:-1] == np.asarray(order).shape[:-1], "euler and order must have the same shape except for the last dimension"
+    idx = _order_indices(order)
+    eye = np.eye(3, dtype=np.int64)
+    qs = [quat_from_angle_axis(euler[..., k:k + 1], eye[idx[..., k]]) for k in range(3)]
+    return quat_mul(qs[0], quat_mul(qs[1], qs[2]))
+
+
+def quat_to_euler(quaternions, order):
+    """quat.py:159-227: intrinsic Euler angles through the half-angle sum / difference construction, every
+    angle reduced with np.mod(., 2 pi).  `sign` is an int64 array, so the two terms multiplied by it are
+    float64; the output buffer is float64 (np.empty default, quat.py:200)."""
+    assert quaternions.shape[:-1] == np.asarray(order).shape[:-1], "quaternions and order must have the same shape except for the last dimension"
+    idx = _order_indices(order)
+    i, j, k = idx[..., 2:3], idx[..., 1:2], idx[..., 0:1]
+    sign = (i - j) * (j - k) * (k - i) // 2  # +1 even permutation, -1 odd
+    w = quaternions[..., 0:1]
+    qi = np.take_along_axis(quaternions, i + 1, axis=-1)
+    qj = np.take_along_axis(quaternions, j + 1, axis=-1)
+    qk = np.take_along_axis(quaternions, k + 1, axis=-1)
+    a = w - qj
+    b = qi + qk * sign
+    c = qj + w
+    d = qk * sign - qi
+    euler = np.empty(quaternions.shape[:-1] + (3,))
+    euler[..., 1:2] = (2 * np.arctan2(np.hypot(c, d), np.hypot(a, b))) - (np.pi / 2)
+    half_sum, half_diff = np.arctan2(b, a), np.arctan2(d, c)
+    euler[..., 2:3] = half_sum - half_diff
+    euler[..., 0:1] = (half_sum + half_diff) * sign
+    return np.mod(euler, 2 * np.pi)
+
+
+def quat_to_angle_axis(quaternions):
+    """quat.py:247-273: angle = 2 acos(clip(w)); axis = xyz / sqrt(clip(1 - w^2)) where that root exceeds 1e-8,
+    zero elsewhere.  Returns (angle [..., 1], axis [..., 3])."""
+    w, xyz = quaternions[..., 0], quaternions[..., 1:]
+    angle = 2 * np.arccos(np.clip(w, -1.0, 1.0))
+    s = np.sqrt(np.clip(1.0 - w * w, 0.0, 1.0))
+    axis = np.zeros_like(xyz)
+    ok = s > 1e-8
+    if ok.any():
+        axis[ok] = xyz[ok] / np.expand_dims(s[ok], axis=-1)
+    return angle[..., np.newaxis], axis
+
+
+def quat_to_scaled_angle_axis(quaternions):
+    """quat.py:230-244."""
+    angle, axis = quat_to_angle_axis(quaternions)
+    return angle * axis
+
+
+def _unroll_signs(real, axis):
+    """Sign (+1 / -1) each entry along `axis` ends up with in quat.py:450-462 / dual_quat.py:155-167: entry i is
+    negated iff its dot product with the ALREADY UNROLLED entry i-1 is < 0 (strictly)."""
+    r = np.moveaxis(real, axis, 0)
+    sign = np.ones(r.shape[:-1], dtype=real.dtype)
+    for t in range(1, r.shape[0]):
+        d0 = np.sum(r[t] * (sign[t - 1][..., np.newaxis] * r[t - 1]), axis=-1)
+        sign[t] = np.where(d0 < -d0, -1.0, 1.0)
+    return np.moveaxis(sign, 0, axis)
+
+
+def quat_unroll(quaternions, axis):
+    """quat.py:426-462.  The reference flips IN PLACE through a swapaxes view (its input is modified); the
+    restatement returns a new array with the same values."""
+    return quaternions * _unroll_signs(quaternions, axis)[..., np.newaxis]
+
+
+def quat_slerp(q0, q1, t, shortest: bool = True):
+    """quat.py:465-501: note the 1e-6 added to every COMPONENT of q2 before its norm is taken (:499)."""
+    dot = np.sum(q0 * q1, axis=-1, keepdims=True)
+    flip = np.logical_and(shortest, dot < 0)
+    q1 = np.where(flip, -q1, q1)
+    dot = np.clip(np.where(flip, -dot, dot), -1, 1)
+    theta = np.arccos(dot) * t
+    q2 = q1 - q0 * dot
+    q2 = q2 / np.linalg.norm(q2 + 0.000001, axis=-1, keepdims=True)
+    return np.cos(theta) * q0 + np.sin(theta) * q2
+
+
+def _from_to_setup(v1, v2, normalize_input):
+    assert v1.shape[-1] == 3 and v2.shape[-1] == 3, "Input vectors must have shape [..., 3]"
+    assert v1.shape == v2.shape, "Input vectors must have the same shape"
+    a, b = (vec_normalize(v1), vec_normalize(v2)) if normalize_input else (v1, v2)
+    if v1.ndim == 1:
+        a, b = a[np.newaxis, :], b[np.newaxis, :]
+    return a, b, np.cross(a, b), np.sum(a * b, axis=-1, keepdims=True)
+
+
+def quat_from_to(v1, v2, normalize_input: bool = True):
+    """quat.py:504-576: half-angle quaternion about normalize(v1 x v2); identity where np.isclose(dot, 1);
+    where np.isclose(dot, -1) a half turn about normalize(v1 x e), e = y if |v1.x| is close to 1 else x."""
+    a, b, cross, dot = _from_to_setup(v1, v2, normalize_input)
+    rot = np.concatenate([np.sqrt((1 + dot) * 0.5), quat_normalize(cross) * np.sqrt((1 - dot) * 0.5)], axis=-1)
+    rot[np.isclose(dot, 1.0)[..., 0]] = [1.0, 0.0, 0.0, 0.0]
+    anti = np.isclose(dot, -1.0)[..., 0]
+    if np.any(anti):
+        va = a[anti]
+        ortho = np.empty_like(va)
+        along_x = np.isclose(np.abs(va[..., 0]), 1.0)
+        ortho[along_x] = np.array([0.0, 1.0, 0.0])
+        ortho[~along_x] = np.array([1.0, 0.0, 0.0])
+        ax = quat_normalize(np.cross(va, ortho))
+        rot[anti] = np.concatenate([np.zeros_like(ax[..., :1]), ax], axis=-1)
+    return rot[0] if v1.ndim == 1 else rot
+
+
+def quat_from_to_axis(v1, v2, rot_axis, normalize_input: bool = True):
+    """quat.py:579-650: same half angle about the GIVEN axis, signed by sign((v1 x v2) . axis); identity where
+    np.isclose(dot, 1); (0, axis) where np.isclose(dot, -1)."""
+    assert v1.shape == rot_axis.shape, "Input vectors and rotation axis must have the same shape"
+    if rot_axis.ndim == 1:
+        rot_axis = rot_axis[np.newaxis, :]
+    a, b, cross, dot = _from_to_setup(v1, v2, normalize_input)
+    s = np.sqrt((1 - dot) * 0.5) * np.sign(np.sum(cross * rot_axis, axis=-1, keepdims=True))
+    rot = np.concatenate([np.sqrt((1 + dot) * 0.5), rot_axis * s], axis=-1)
+    rot[np.isclose(dot, 1.0)[..., 0]] = [1.0, 0.0, 0.0, 0.0]
+    anti = np.isclose(dot, -1.0)[..., 0]
+    if np.any(anti):
+        rot[anti] = np.concatenate([np.zeros_like(rot_axis[anti][..., :1]), rot_axis[anti]], axis=-1)
+    return rot[0] if v1.ndim == 1 else rot
+
+
+# ----------------------------------------------------------------------------
+# the rest of the dual-quaternion surface               (rotations/dual_quat.py)
+# ----------------------------------------------------------------------------
+def dq_is_unit(dq, atol: float = 1e-03) -> bool:
+    """dual_quat.py:118-136: ONE bool for the whole array -- every real part has unit norm (np.isclose
+    defaults) and is orthogonal to its dual part (|dot| <= atol); all-zero real parts count as unit."""
+    real, dual = dq[..., :4], dq[..., 4:]
+    n2 = np.sum(real * real, axis=-1)
+    if np.isclose(n2, 0).all():
+        return True
+    return bool(np.isclose(n2, 1).all() and np.isclose(np.sum(real * dual, axis=-1), 0, atol=atol).all())
+
+
+def dq_normalize(dq):
+    """dual_quat.py:86-115: both parts divided by |real|; if the WHOLE array is then not unit (dq_is_unit) the
+    component of the dual part along the real part is removed from every element."""
+    real, dual = dq[..., :4], dq[..., 4:]
+    norm = np.linalg.norm(real, axis=-1)
+    rn, dn = real / norm[..., np.newaxis], dual / norm[..., np.newaxis]
+    if not dq_is_unit(np.concatenate((rn, dn), axis=-1)):
+        dn = dn - rn * (np.sum(real * dual, axis=-1) / (norm * norm))[..., np.newaxis]
+    return np.concatenate((rn, dn), axis=-1)
+
+
+def dq_unroll(dq, axis):
+    """dual_quat.py:139-167: quat unroll decided on the REAL part, the flip applied to all eight numbers."""
+    return dq * _unroll_signs(dq[..., :4], axis)[..., np.newaxis]

@@ -175,9 +175,9 @@ int launch_fk_cfg(const FkArgs &a, const DeviceProps &dp) {
 }
 
 // ---- fk, row-team kernel (fk_rows_kernel.cuh) ------------------------------------
-template <int S>
+template <int S, int VEC>
 int launch_fk_rows_cfg(const FkArgs &a, const DeviceProps &dp) {
-    auto kernel = pmb::fk_rows_kernel<S>;
+    auto kernel = pmb::fk_rows_kernel<S, VEC>;
     const int smem = pmb::fk_rows_geom(S, a.n_joints).block_bytes;
     int rc = set_smem(kernel, smem);
     if (rc) return rc;
@@ -189,7 +189,7 @@ int launch_fk_rows_cfg(const FkArgs &a, const DeviceProps &dp) {
     if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk row kernel does not fit on an SM (%d bytes of shared memory)", smem);
     per_sm = std::max(1, std::min(per_sm, env_int("PMB_FK_BLOCKS_PER_SM", per_sm)));
     const long long blocks = std::min<long long>(tiles, static_cast<long long>(per_sm) * dp.sm_count);
-    note_variant("fk_rows_kernel<S=%d> grid=%lld (%d teams/SM) smem=%d", S, blocks, per_sm, smem);
+    note_variant("fk_rows_kernel<S=%d,VEC=%d> grid=%lld (%d teams/SM) smem=%d", S, VEC, blocks, per_sm, smem);
     kernel<<<static_cast<unsigned>(blocks), pmb::kRowThreads, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos,
                                                                                 a.rout, a.n_frames, a.n_joints, *a.prog);
     PMB_CUDA(cudaGetLastError());
@@ -221,7 +221,10 @@ bool try_fk_rows(const FkArgs &a, const DeviceProps &dp, int &rc) {
         return false;
     }
     if (force != 1 && fk_rows_teams(stages, a, dp) < 2) return false;  // one team per SM cannot hide its own drain
-    rc = stages == 2 ? launch_fk_rows_cfg<2>(a, dp) : stages == 3 ? launch_fk_rows_cfg<3>(a, dp) : launch_fk_rows_cfg<4>(a, dp);
+    if (a.n_joints % 2 == 0)
+        rc = stages == 2 ? launch_fk_rows_cfg<2, 2>(a, dp) : stages == 3 ? launch_fk_rows_cfg<3, 2>(a, dp) : launch_fk_rows_cfg<4, 2>(a, dp);
+    else
+        rc = stages == 2 ? launch_fk_rows_cfg<2, 1>(a, dp) : stages == 3 ? launch_fk_rows_cfg<3, 1>(a, dp) : launch_fk_rows_cfg<4, 1>(a, dp);
     return true;
 }
 

@@ -6,8 +6,10 @@
 // tile of 32 consecutive frames; warp a walks the tree for row a, lane = frame.  Compared with one thread
 // per frame (fk_kernel.cuh) the dependent chain per thread is a third as long, the same shared memory
 // carries three times as many warps (what limits 52- and 65-joint skeletons: the stage is 1536 J bytes per
-// tile whatever the mapping), and the chain state is 4 registers.  The price is that every row warp
-// normalises the quaternion and forms the local matrix itself (~+20 % instructions in total).
+// tile whatever the mapping), and the chain state is 4 registers.  No local matrix is formed: a row times
+// R(q^) is the row rotated by the conjugate quaternion (two cross products), and the normalisation of q
+// collapses into one scale 2 / (|q| + eps)^2 per joint, computed for a whole chunk ahead of the branchy
+// tree walk.
 //
 //   in    a loader thread streams the tile's quaternions as TMA boxes of 8 joints x 32 frames (128-byte
 //         swizzle) through an S-deep ring; full / empty mbarriers, the three row warps release a box as soon
@@ -47,8 +49,30 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int S>
-__global__ void __launch_bounds__(kRowThreads)
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float a) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
+
+// 2 / (|q| + eps)^2 with three bare MUFU-class ops: the scale that turns the products of the RAW quaternion
+// into those of q / (|q| + eps) (quat.py:411-423; eps joins the NORM).  sqrt.approx(0) = 0, so the zero
+// quaternion needs no guard: its products are all zero and the local rotation is the identity, as in the
+// reference.
+__device__ __forceinline__ float rot_scale(const float4 &q, float eps) {
+    const float n2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    float n, inv;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(n) : "f"(n2));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(n + eps));
+    return (inv + inv) * inv;
+}
+
+// VEC = 2 (even joint count: every stage row is 8-byte aligned): a row's three numbers go out as one 64-bit
+// and one 32-bit store -- the minimum number of shared-memory wavefronts for this layout; VEC = 1: 32-bit
+// stores (odd row stride, conflict free as they are).
+template <int S, int VEC>
+__global__ void __launch_bounds__(kRowThreads, 5)
 fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                const float *__restrict__ offsets, float *__restrict__ pos, float *__restrict__ rout,
                long long n_frames, int n_joints, const __grid_constant__ JointProgram prog) {
@@ -78,8 +102,10 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
         mbar_init(stage_free, 1);
         fence_barrier_init();
     }
+    // offsets[0] is ignored by the reference (the root translation is global_pos, skeleton.py:49): with a zero
+    // entry the root is an ordinary joint whose parent is the identity placed at global_pos
     for (int j = threadIdx.x; j < n_joints; j += kRowThreads)
-        tab[j] = make_float4(offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2], 0.f);
+        tab[j] = j == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2], 0.f);
     __syncthreads();  // the only block-wide barrier: the roles below never meet again
 
     if (warp == 3) {
@@ -128,6 +154,8 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
     const int swz = lane & 7;
     float *Rrow = Rst + lane * rpitch + 3 * a;
     float *Prow = Pst + lane * ppitch + a;
+    const int pa = a & 1;
+    const float id0 = a == 0 ? 1.f : 0.f, id1 = a == 1 ? 1.f : 0.f, id2 = a == 2 ? 1.f : 0.f;
 
     long long tile = blockIdx.x;
     float gnext = 0.f;  // root position component of the NEXT tile, fetched a tile early
@@ -135,7 +163,8 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
     uint32_t k = 0, it = 0;
 
     for (; tile < n_tiles; tile += tile_stride, ++it) {
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, pp = gnext;  // row a of the current joint's [R | p]
+        // row a of the "parent" of the root: the identity placed at global_pos
+        float r0 = id0, r1 = id1, r2 = id2, pp = gnext;
 
         for (int c0 = 0; c0 < n_joints; c0 += C) {
             const int cnt = min(C, n_joints - c0);
@@ -146,14 +175,20 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
             float4 q[C];
 #pragma unroll
             for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
-            {   // the loads must have LANDED before the box is released to the async proxy (see fk_kernel.cuh)
+            {   // the loads must have LANDED before the box is released to the async proxy (see fk_kernel.cuh);
+                // one component per 16-byte load is enough, the four arrive together
                 uint32_t acc = 0;
 #pragma unroll
-                for (int jj = 0; jj < C; ++jj) acc |= __float_as_uint(q[jj].x) | __float_as_uint(q[jj].w);
+                for (int jj = 0; jj < C; ++jj) acc |= __float_as_uint(q[jj].x);
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * buf);
+            // branch-free part of the chunk: the eight normalisation scales, eight independent MUFU chains
+            // (joints past the end of the skeleton are zero-filled by the TMA unit: finite, unused)
+            float sc[C];
+#pragma unroll
+            for (int jj = 0; jj < C; ++jj) sc[jj] = rot_scale(q[jj], 1e-8f);
             if (c0 == 0) {
                 const long long next_tile = tile + tile_stride;
                 if (next_tile < n_tiles) gnext = __ldg(gpos + min(next_tile * kWarp + lane, n_frames - 1) * gstride + a);
@@ -166,25 +201,36 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
                     const int j = c0 + jj;
                     const uint32_t code = prog.code[j];  // constant bank, warp-uniform
                     const float4 e = tab[j];
-                    float l[9];
-                    q_to_matrix(q_normalize_fast(Quat<float>{q[jj].x, q[jj].y, q[jj].z, q[jj].w}, 1e-8f), l);
-                    if (jj == 0 && c0 == 0) {  // root: [R | global_pos] (skeleton.py:49)
-                        r0 = a == 0 ? l[0] : (a == 1 ? l[3] : l[6]);
-                        r1 = a == 0 ? l[1] : (a == 1 ? l[4] : l[7]);
-                        r2 = a == 0 ? l[2] : (a == 1 ? l[5] : l[8]);
-                    } else {
-                        if (prog_src(code) != kSrcReg) {  // parent is not the previous joint: its row is in the stage
-                            const int p = static_cast<int>(prog_parent(code));
-                            r0 = Rrow[9 * p], r1 = Rrow[9 * p + 1], r2 = Rrow[9 * p + 2];
-                            pp = Prow[3 * p];
-                        }
-                        const float n0 = r0 * l[0] + r1 * l[3] + r2 * l[6];
-                        const float n1 = r0 * l[1] + r1 * l[4] + r2 * l[7];
-                        const float n2 = r0 * l[2] + r1 * l[5] + r2 * l[8];
-                        pp = r0 * e.x + r1 * e.y + r2 * e.z + pp;
-                        r0 = n0, r1 = n1, r2 = n2;
+                    if (prog_src(code) != kSrcReg) {  // parent is not the previous joint: its row is in the stage
+                        const int p = static_cast<int>(prog_parent(code));
+                        r0 = Rrow[9 * p], r1 = Rrow[9 * p + 1], r2 = Rrow[9 * p + 2];
+                        pp = Prow[3 * p];
                     }
-                    Rrow[9 * j] = r0, Rrow[9 * j + 1] = r1, Rrow[9 * j + 2] = r2;
+                    // row' = row * R(q^) = the row rotated by the conjugate of q^:
+                    //   c = row x v,  row' = row + s (w c + c x v),  s = 2 / (|q| + eps)^2, q = (w, v) as loaded
+                    const float w = q[jj].x, x = q[jj].y, y = q[jj].z, z = q[jj].w;
+                    const float cx = r1 * z - r2 * y, cy = r2 * x - r0 * z, cz = r0 * y - r1 * x;
+                    const float ex = w * cx + (cy * z - cz * y);
+                    const float ey = w * cy + (cz * x - cx * z);
+                    const float ez = w * cz + (cx * y - cy * x);
+                    pp = r0 * e.x + r1 * e.y + r2 * e.z + pp;  // p[a] = parent row . offset + parent p[a]
+                    r0 = sc[jj] * ex + r0, r1 = sc[jj] * ey + r1, r2 = sc[jj] * ez + r2;
+                    float *rs = Rrow + 9 * j;
+                    if (VEC == 2) {
+                        // word 9j + 3a of an even-stride row: 8-byte aligned iff j + a is even (j and jj have the
+                        // same parity: chunks start at multiples of 8)
+                        // (PTX stores: the compiler otherwise merges the two arms back into three 32-bit stores)
+                        const uint32_t ra = smem_u32(rs);
+                        if (((jj & 1) ^ pa) == 0) {
+                            sts64(ra, r0, r1);
+                            sts32(ra + 8, r2);
+                        } else {
+                            sts32(ra, r0);
+                            sts64(ra + 4, r1, r2);
+                        }
+                    } else {
+                        rs[0] = r0, rs[1] = r1, rs[2] = r2;
+                    }
                     Prow[3 * j] = pp;
                 }
             }

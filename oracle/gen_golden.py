@@ -243,9 +243,110 @@ def gen_quat():
     return d
 
 
+def gen_quat_ext():
+    """the rest of quat.py / dual_quat.py.  Seeded inputs -> outputs of the real reference,
+    plus the hand-written samples of rotations/tests/test_quat.py (cited)."""
+    d = {}
+    rng = np.random.default_rng(77)
+    orders6 = np.array([list(p) for p in ("xyz", "xzy", "yxz", "yzx", "zxy", "zyx")])
+    # hand-written samples
+    d["hand/aa_axis"] = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float64)  # test_quat.py:55
+    d["hand/aa_angle"] = np.array([0, np.pi / 2, np.pi / 4, np.pi])[..., np.newaxis]               # :57
+    d["hand/aa_quat"] = np.array([[1, 0, 0, 0], [0.70710678, 0.70710678, 0, 0], [0.92387953, 0, 0.38268343, 0], [0, 0, 0, 1]])  # :61-68
+    d["hand/saa"] = np.array([[np.pi / 2, 0, 0], [0, np.pi / 4, 0], [0, 0, np.pi]])                 # :101
+    d["hand/saa_quat"] = np.array([[0.70710678, 0.70710678, 0, 0], [0.92387953, 0, 0.38268343, 0], [0, 0, 0, 1]])  # :105-111
+    d["hand/euler"] = np.array([[np.pi / 2, 0, 0], [0, np.pi / 4, 0], [0, 0, np.pi]])               # :150
+    d["hand/euler_order"] = np.array([["x", "y", "z"], ["x", "z", "y"], ["y", "x", "z"]])           # :152
+    d["hand/euler_quat"] = np.array([[0.70710678, 0.70710678, 0, 0], [0.92387953, 0, 0, 0.38268343], [0, 0, 0, 1]])  # :155-161
+    # slerp samples, test_quat.py:393-452
+    q1 = ref_q.from_angle_axis(np.array([[0], [np.pi / 2], [np.pi]]), np.array([[0, 0, 1], [0, 0, 1], [0, 0, 1]]))
+    q2 = ref_q.from_angle_axis(np.array([[np.pi / 2], [0], [np.pi]]), np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0]]))
+    d["hand/slerp_q1"], d["hand/slerp_q2"] = q1, q2
+    d["hand/slerp_t"] = np.array([[0], [0.5], [1]])
+    d["hand/slerp_t2"] = np.array([[-1], [2], [0.25]])
+    d["hand/slerp_gt"] = np.array([[1, 0, 0, 0], [0.92387953, 0, 0, 0.38268343], [0, 0, 1, 0]])
+    d["hand/slerp_gt2"] = np.array([[0.70710678, 0, 0, -0.70710678], [0.70710678, 0, 0, -0.70710678], [0, 0, 0.38268343, 0.92387953]])
+    d["hand/slerp_gt3"] = np.array([[0.83146961, 0, 0, 0.5555702], [0.98078528, 0, 0, 0.1950903], [0, 0, 0.9238795, 0.3826834]])  # t = 0.75
+    for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+        n = (3, 29)
+        axis = rng.standard_normal(n + (3,))
+        axis = (axis / np.linalg.norm(axis, axis=-1, keepdims=True)).astype(dt)
+        angle = rng.uniform(0, 2 * np.pi, n + (1,)).astype(dt)
+        d[f"{tag}/axis"], d[f"{tag}/angle"] = axis, angle
+        q = ref_q.from_angle_axis(angle, axis)
+        d[f"{tag}/from_angle_axis"] = q
+        sa = (axis * angle).astype(dt)
+        d[f"{tag}/scaled"] = sa
+        d[f"{tag}/from_scaled_angle_axis"] = ref_q.from_scaled_angle_axis(sa)
+        ta, tx = ref_q.to_angle_axis(q)
+        d[f"{tag}/to_angle_axis_angle"], d[f"{tag}/to_angle_axis_axis"] = ta, tx
+        d[f"{tag}/to_scaled_angle_axis"] = ref_q.to_scaled_angle_axis(q)
+        qid = np.array([[1, 0, 0, 0], [-1, 0, 0, 0], [1, 1e-9, 0, 0]], dtype=dt)  # s <= 1e-8: zero axis (quat.py:268-271)
+        ia, ix = ref_q.to_angle_axis(qid)
+        d[f"{tag}/qid"], d[f"{tag}/qid_angle"], d[f"{tag}/qid_axis"] = qid, ia, ix
+        euler = rng.uniform(0, 2 * np.pi, n + (3,)).astype(dt)
+        order = orders6[rng.integers(0, 6, n)]
+        d[f"{tag}/euler"], d[f"{tag}/order"] = euler, order
+        qe = ref_q.from_euler(euler, order)
+        d[f"{tag}/from_euler"] = qe
+        d[f"{tag}/to_euler"] = ref_q.to_euler(qe.astype(dt), order)
+        one = np.broadcast_to(np.array(["z", "x", "y"]), n + (3,))  # the BVH channel order, one order for the array
+        d[f"{tag}/from_euler_zxy"] = ref_q.from_euler(euler, one)
+        d[f"{tag}/to_euler_zxy"] = ref_q.to_euler(qe.astype(dt), one)
+        # unroll: random signs over 96 frames x 7 joints, one exact-zero entry (dot == 0 keeps the sign)
+        base = ref_q.normalize(rng.standard_normal((1, 7, 4)) + 0.15 * np.cumsum(rng.standard_normal((96, 7, 4)), axis=0))
+        flips = rng.choice([-1.0, 1.0], size=(96, 7, 1))
+        uq = (base * flips).astype(dt)
+        uq[50, 3] = 0
+        d[f"{tag}/unroll_in"] = uq
+        d[f"{tag}/unroll_axis0"] = ref_q.unroll(uq.copy(), 0)
+        uq1 = np.ascontiguousarray(uq.swapaxes(0, 1))
+        d[f"{tag}/unroll_axis1"] = ref_q.unroll(uq1.copy(), 1)
+        # slerp
+        qa = ref_q.normalize(rng.standard_normal(n + (4,))).astype(dt)
+        qb = ref_q.normalize(rng.standard_normal(n + (4,))).astype(dt)
+        qb[0, :3] = qa[0, :3]       # identical ends: theta = 0
+        qb[0, 3:6] = -qa[0, 3:6]    # opposite ends
+        t = rng.uniform(-0.2, 1.2, n + (1,)).astype(dt)
+        d[f"{tag}/slerp_q0"], d[f"{tag}/slerp_q1"], d[f"{tag}/slerp_t"] = qa, qb, t
+        d[f"{tag}/slerp"] = ref_q.slerp(qa, qb, t)
+        d[f"{tag}/slerp_long"] = ref_q.slerp(qa, qb, t, shortest=False)
+        d[f"{tag}/slerp_scalar"] = ref_q.slerp(qa, qb, 0.3)
+        # from_to / from_to_axis: random, parallel, anti-parallel (along x and not), one-dimensional
+        v1 = rng.standard_normal((64, 3)).astype(dt)
+        v2 = rng.standard_normal((64, 3)).astype(dt)
+        v2[:4] = v1[:4] * 2.5
+        v2[4:8] = -v1[4:8] * 0.5
+        v1[8], v2[8] = [1, 0, 0], [-3, 0, 0]
+        v1[9], v2[9] = [-2, 0, 0], [1, 0, 0]
+        d[f"{tag}/v1"], d[f"{tag}/v2"] = v1, v2
+        with np.errstate(invalid="ignore"):
+            d[f"{tag}/from_to"] = ref_q.from_to(v1, v2)
+            d[f"{tag}/from_to_raw"] = ref_q.from_to(ref_q.normalize(v1).astype(dt), ref_q.normalize(v2).astype(dt), normalize_input=False)
+            d[f"{tag}/from_to_1d"] = ref_q.from_to(v1[20], v2[20])
+            ax = ref_q.normalize(rng.standard_normal((64, 3))).astype(dt)
+            d[f"{tag}/ft_axis"] = ax
+            d[f"{tag}/from_to_axis"] = ref_q.from_to_axis(v1, v2, ax)
+            d[f"{tag}/from_to_axis_1d"] = ref_q.from_to_axis(v1[20], v2[20], ax[20])
+        # dual quaternions
+        dq = rng.standard_normal(n + (8,)).astype(dt)
+        d[f"{tag}/dq_raw"] = dq
+        d[f"{tag}/dq_normalize_raw"] = ref_dq.normalize(dq)          # not unit after scaling: ortho branch (dual_quat.py:105-111)
+        unit = ref_dq.from_rotation_translation(qa, rng.standard_normal(n + (3,)).astype(dt)) * dt(3.0)
+        d[f"{tag}/dq_scaled_unit"] = unit.astype(dt)
+        d[f"{tag}/dq_normalize_unit"] = ref_dq.normalize(unit.astype(dt))  # unit after scaling: no projection
+        d[f"{tag}/dq_is_unit"] = np.array([ref_dq.is_unit(dq), ref_dq.is_unit(ref_dq.normalize(unit.astype(dt))),
+                                           ref_dq.is_unit(np.zeros((4, 8), dtype=dt))])
+        udq = np.concatenate([uq, rng.standard_normal((96, 7, 4)).astype(dt)], axis=-1)
+        d[f"{tag}/dq_unroll_in"] = udq
+        d[f"{tag}/dq_unroll_axis0"] = ref_dq.unroll(udq.copy(), 0)
+    np.savez_compressed(os.path.join(OUT, "quat_ext.npz"), **d)
+    return d
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    for fn in (gen_fk, gen_dq, gen_quat):
+    for fn in (gen_fk, gen_dq, gen_quat, gen_quat_ext):
         out = fn()
         print(fn.__name__, len(out), "arrays")
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)}

@@ -37,7 +37,7 @@ struct FkRowsGeom {
 };
 __host__ __device__ inline FkRowsGeom fk_rows_geom(int stages, int n_joints, bool quat_out = false) {
     FkRowsGeom g;
-    g.tab_bytes = (n_joints * 16 + 127) & ~127;
+    g.tab_bytes = ((n_joints + kChunk) * 16 + 127) & ~127;  // padded: the tail chunk and the one-ahead prefetch read past J
     g.stage_bytes = kWarp * (quat_out ? 7 : 12) * n_joints * 4;
     // 1 KB slack to align the boxes | boxes | joint table | stage | barriers (full[S], empty[S], stage_full, stage_free) | fence words
     g.block_bytes = 1024 + stages * kBoxBytes + g.tab_bytes + g.stage_bytes + (2 * stages + 2) * 8 + 96 * 4;
@@ -49,11 +49,58 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
-    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+// The tree walk below has NO branches: the parent fetch and the tail-chunk guard are predicated PTX, so
+// the compiler is free to overlap the independent parts of consecutive joints (measured: with a uniform
+// branch per joint every joint paid the constant-load -> compare -> branch latency, ~280 cycles per joint).
+// Deliberately no "memory" clobber: the stage is touched only through these two helpers (volatile asm keeps
+// their mutual order) and the joint table is read-only, so its loads may float.
+__device__ __forceinline__ void load_parent_row_if(int parent /* taken iff >= 0 */, uint32_t raddr, uint32_t paddr, float &r0, float &r1,
+                                                   float &r2, float &pp) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ge.s32 p, %4, 0;\n"
+        "@p ld.shared.f32 %0, [%5];\n"
+        "@p ld.shared.f32 %1, [%5+4];\n"
+        "@p ld.shared.f32 %2, [%5+8];\n"
+        "@p ld.shared.f32 %3, [%6];\n"
+        "}"
+        : "+f"(r0), "+f"(r1), "+f"(r2), "+f"(pp)
+        : "r"(parent), "r"(raddr), "r"(paddr));
 }
-__device__ __forceinline__ void sts32(uint32_t addr, float a) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+// ALIGNED: raddr is 8-byte aligned -> (r0, r1) as one 64-bit store; otherwise (r1, r2) is the aligned pair.
+template <int VEC, bool ALIGNED>
+__device__ __forceinline__ void store_row_if(int keep /* stored iff > 0 */, uint32_t raddr, uint32_t paddr, float r0, float r1, float r2,
+                                             float pp) {
+    if (VEC == 2 && ALIGNED) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.gt.s32 p, %0, 0;\n"
+            "@p st.shared.v2.f32 [%1], {%3, %4};\n"
+            "@p st.shared.f32 [%1+8], %5;\n"
+            "@p st.shared.f32 [%2], %6;\n"
+            "}" ::"r"(keep), "r"(raddr), "r"(paddr), "f"(r0), "f"(r1), "f"(r2), "f"(pp));
+    } else if (VEC == 2) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.gt.s32 p, %0, 0;\n"
+            "@p st.shared.f32 [%1], %3;\n"
+            "@p st.shared.v2.f32 [%1+4], {%4, %5};\n"
+            "@p st.shared.f32 [%2], %6;\n"
+            "}" ::"r"(keep), "r"(raddr), "r"(paddr), "f"(r0), "f"(r1), "f"(r2), "f"(pp));
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.gt.s32 p, %0, 0;\n"
+            "@p st.shared.f32 [%1], %3;\n"
+            "@p st.shared.f32 [%1+4], %4;\n"
+            "@p st.shared.f32 [%1+8], %5;\n"
+            "@p st.shared.f32 [%2], %6;\n"
+            "}" ::"r"(keep), "r"(raddr), "r"(paddr), "f"(r0), "f"(r1), "f"(r2), "f"(pp));
+    }
 }
 
 // 2 / (|q| + eps)^2 with three bare MUFU-class ops: the scale that turns the products of the RAW quaternion
@@ -68,9 +115,95 @@ __device__ __forceinline__ float rot_scale(const float4 &q, float eps) {
     return (inv + inv) * inv;
 }
 
+// Everything a row warp needs from the kernel prologue.
+struct RowCtx {
+    const float4 *boxes, *tab;
+    uint32_t rst, pst;            // shared addresses of the stage (rotation rows, positions)
+    uint32_t full0, empty0, stage_full, stage_free, fence_word;
+    const float *gpos;
+    long long gstride, n_frames, n_tiles, tile_stride, first_tile;
+    int n_joints, lane;
+};
+
+// One row warp: row A of every joint of the tile, lane = frame.
 // VEC = 2 (even joint count: every stage row is 8-byte aligned): a row's three numbers go out as one 64-bit
 // and one 32-bit store -- the minimum number of shared-memory wavefronts for this layout; VEC = 1: 32-bit
 // stores (odd row stride, conflict free as they are).
+template <int S, int VEC, int A>
+__device__ __forceinline__ void fk_row_walk(const RowCtx &cx) {
+    constexpr int C = kChunk;
+    const int lane = cx.lane, n_joints = cx.n_joints;
+    const int swz = lane & 7;
+    const uint32_t rrow = cx.rst + (lane * 9 * n_joints + 3 * A) * 4;  // this lane's row A of joint 0
+    const uint32_t prow = cx.pst + (lane * 3 * n_joints + A) * 4;
+
+    long long tile = cx.first_tile;
+    float gnext = 0.f;  // root position component of the NEXT tile, fetched a tile early
+    if (tile < cx.n_tiles) gnext = __ldg(cx.gpos + min(tile * kWarp + lane, cx.n_frames - 1) * cx.gstride + A);
+    uint32_t k = 0, it = 0;
+
+    for (; tile < cx.n_tiles; tile += cx.tile_stride, ++it) {
+        // row A of the "parent" of the root: the identity placed at global_pos
+        float r0 = A == 0 ? 1.f : 0.f, r1 = A == 1 ? 1.f : 0.f, r2 = A == 2 ? 1.f : 0.f, pp = gnext;
+
+        for (int c0 = 0; c0 < n_joints; c0 += C) {
+            const int cnt = n_joints - c0;  // >= 8 for every chunk but a partial last one
+            const uint32_t buf = k % S;
+            mbar_wait(cx.full0 + 8 * buf, (k / S) & 1);
+            ++k;
+            const float4 *in_row = cx.boxes + buf * (kBoxBytes / 16) + lane * C;
+            float4 q[C];
+#pragma unroll
+            for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
+            {   // the loads must have LANDED before the box is released to the async proxy (see fk_kernel.cuh);
+                // one component per 16-byte load is enough, the four arrive together
+                uint32_t acc = 0;
+#pragma unroll
+                for (int jj = 0; jj < C; ++jj) acc |= __float_as_uint(q[jj].x);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(cx.fence_word), "r"(acc) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cx.empty0 + 8 * buf);
+            if (c0 == 0) {
+                const long long next_tile = tile + cx.tile_stride;
+                if (next_tile < cx.n_tiles)
+                    gnext = __ldg(cx.gpos + min(next_tile * kWarp + lane, cx.n_frames - 1) * cx.gstride + A);
+                if (it > 0) mbar_wait(cx.stage_free, (it - 1) & 1);  // the previous tile has left the stage
+            }
+
+            // Branch-free walk over the chunk.  Joints past the end of the skeleton (partial last chunk) are
+            // zero quaternions (TMA fill) with padded table entries: identity steps whose stores are predicated off.
+            float4 e = cx.tab[c0];
+#pragma unroll
+            for (int jj = 0; jj < C; ++jj) {
+                const int j = c0 + jj;
+                const float4 e_next = cx.tab[j + 1];  // one joint ahead (the table is padded by a chunk)
+                const int p = __float_as_int(e.w);    // parent whose row must come from the stage, or -1
+                load_parent_row_if(p, rrow + 36 * p, prow + 12 * p, r0, r1, r2, pp);
+                // row' = row * R(q^) = the row rotated by the conjugate of q^:
+                //   c = row x v,  row' = row + s (w c + c x v),  s = 2 / (|q| + eps)^2, q = (w, v) as loaded
+                const float sc = rot_scale(q[jj], 1e-8f);
+                const float w = q[jj].x, x = q[jj].y, y = q[jj].z, z = q[jj].w;
+                const float cx_ = r1 * z - r2 * y, cy_ = r2 * x - r0 * z, cz_ = r0 * y - r1 * x;
+                const float ex = w * cx_ + (cy_ * z - cz_ * y);
+                const float ey = w * cy_ + (cz_ * x - cx_ * z);
+                const float ez = w * cz_ + (cx_ * y - cy_ * x);
+                pp = r0 * e.x + r1 * e.y + r2 * e.z + pp;  // p[A] = parent row . offset + parent p[A]
+                r0 = sc * ex + r0, r1 = sc * ey + r1, r2 = sc * ez + r2;
+                // word 9j + 3A of an even-stride row is 8-byte aligned iff j + A is even (j and jj have the same
+                // parity: chunks start at multiples of 8)
+                // (constant after unrolling)
+                if (((jj + A) & 1) == 0) store_row_if<VEC, true>(cnt - jj, rrow + 36 * j, prow + 12 * j, r0, r1, r2, pp);
+                else store_row_if<VEC, false>(cnt - jj, rrow + 36 * j, prow + 12 * j, r0, r1, r2, pp);
+                e = e_next;
+            }
+        }
+        fence_proxy_async_smem();  // this lane's stage writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cx.stage_full);
+    }
+}
+
 template <int S, int VEC>
 __global__ void __launch_bounds__(kRowThreads, 5)
 fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
@@ -102,10 +235,19 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
         mbar_init(stage_free, 1);
         fence_barrier_init();
     }
-    // offsets[0] is ignored by the reference (the root translation is global_pos, skeleton.py:49): with a zero
-    // entry the root is an ordinary joint whose parent is the identity placed at global_pos
-    for (int j = threadIdx.x; j < n_joints; j += kRowThreads)
-        tab[j] = j == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2], 0.f);
+    // Joint table: offset (x, y, z) | parent index if the parent's row has to be fetched from the stage, -1 if it
+    // is the previous joint (still in registers).  offsets[0] is ignored by the reference (the root translation
+    // is global_pos, skeleton.py:49): with a zero entry the root is an ordinary joint whose parent is the
+    // identity placed at global_pos.  Padding entries are identity steps.
+    for (int j = threadIdx.x; j < n_joints + kChunk; j += kRowThreads) {
+        float4 e = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (j > 0 && j < n_joints) {
+            e.x = offsets[3 * j], e.y = offsets[3 * j + 1], e.z = offsets[3 * j + 2];
+            const uint32_t code = prog.code[j];
+            if (prog_src(code) != kSrcReg) e.w = __int_as_float(static_cast<int>(prog_parent(code)));
+        }
+        tab[j] = e;
+    }
     __syncthreads();  // the only block-wide barrier: the roles below never meet again
 
     if (warp == 3) {
@@ -115,7 +257,7 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
             for (long long t = blockIdx.x; t < n_tiles; t += tile_stride) {
                 for (int c0 = 0; c0 < n_joints; c0 += C, ++k) {
                     const uint32_t buf = k % S;
-                    if (k >= S) mbar_wait(empty0 + 8 * buf, ((k / S) - 1) & 1);  // all three row warps have read it
+                    if (k >= S) mbar_wait_long(empty0 + 8 * buf, ((k / S) - 1) & 1);  // all three row warps have read it
                     mbar_arrive_expect_tx(full0 + 8 * buf, kBoxBytes);
                     tma_load_2d(box0 + buf * kBoxBytes, &tm_rot, 4 * c0, static_cast<int>(t * kWarp), full0 + 8 * buf);
                 }
@@ -130,7 +272,7 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
             for (long long t = blockIdx.x; t < n_tiles; t += tile_stride, ++it) {
                 const long long f0 = t * kWarp;
                 const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
-                mbar_wait(stage_full, it & 1);
+                mbar_wait_long(stage_full, it & 1);
                 float *rg = rout + f0 * rpitch, *pg = pos + f0 * ppitch;
                 const uint32_t rbytes = static_cast<uint32_t>(nrows * rpitch * 4), pbytes = static_cast<uint32_t>(nrows * ppitch * 4);
                 // a full tile is two multiples of 128 bytes; a remainder tile can leave up to 3 words past the
@@ -148,97 +290,17 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
         return;
     }
 
-    // ---- row warps ----------------------------------------------------------------------------------
-    const int a = warp;  // the row of the transform this warp computes
-    const uint32_t fence_word = stage_free + 8 + 4 * threadIdx.x;
-    const int swz = lane & 7;
-    float *Rrow = Rst + lane * rpitch + 3 * a;
-    float *Prow = Pst + lane * ppitch + a;
-    const int pa = a & 1;
-    const float id0 = a == 0 ? 1.f : 0.f, id1 = a == 1 ? 1.f : 0.f, id2 = a == 2 ? 1.f : 0.f;
-
-    long long tile = blockIdx.x;
-    float gnext = 0.f;  // root position component of the NEXT tile, fetched a tile early
-    if (tile < n_tiles) gnext = __ldg(gpos + min(tile * kWarp + lane, n_frames - 1) * gstride + a);
-    uint32_t k = 0, it = 0;
-
-    for (; tile < n_tiles; tile += tile_stride, ++it) {
-        // row a of the "parent" of the root: the identity placed at global_pos
-        float r0 = id0, r1 = id1, r2 = id2, pp = gnext;
-
-        for (int c0 = 0; c0 < n_joints; c0 += C) {
-            const int cnt = min(C, n_joints - c0);
-            const uint32_t buf = k % S;
-            mbar_wait(full0 + 8 * buf, (k / S) & 1);
-            ++k;
-            const float4 *in_row = boxes + buf * (kBoxBytes / 16) + lane * C;
-            float4 q[C];
-#pragma unroll
-            for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
-            {   // the loads must have LANDED before the box is released to the async proxy (see fk_kernel.cuh);
-                // one component per 16-byte load is enough, the four arrive together
-                uint32_t acc = 0;
-#pragma unroll
-                for (int jj = 0; jj < C; ++jj) acc |= __float_as_uint(q[jj].x);
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * buf);
-            // branch-free part of the chunk: the eight normalisation scales, eight independent MUFU chains
-            // (joints past the end of the skeleton are zero-filled by the TMA unit: finite, unused)
-            float sc[C];
-#pragma unroll
-            for (int jj = 0; jj < C; ++jj) sc[jj] = rot_scale(q[jj], 1e-8f);
-            if (c0 == 0) {
-                const long long next_tile = tile + tile_stride;
-                if (next_tile < n_tiles) gnext = __ldg(gpos + min(next_tile * kWarp + lane, n_frames - 1) * gstride + a);
-                if (it > 0) mbar_wait(stage_free, (it - 1) & 1);  // the previous tile has left the stage
-            }
-
-#pragma unroll
-            for (int jj = 0; jj < C; ++jj) {
-                if (jj < cnt) {
-                    const int j = c0 + jj;
-                    const uint32_t code = prog.code[j];  // constant bank, warp-uniform
-                    const float4 e = tab[j];
-                    if (prog_src(code) != kSrcReg) {  // parent is not the previous joint: its row is in the stage
-                        const int p = static_cast<int>(prog_parent(code));
-                        r0 = Rrow[9 * p], r1 = Rrow[9 * p + 1], r2 = Rrow[9 * p + 2];
-                        pp = Prow[3 * p];
-                    }
-                    // row' = row * R(q^) = the row rotated by the conjugate of q^:
-                    //   c = row x v,  row' = row + s (w c + c x v),  s = 2 / (|q| + eps)^2, q = (w, v) as loaded
-                    const float w = q[jj].x, x = q[jj].y, y = q[jj].z, z = q[jj].w;
-                    const float cx = r1 * z - r2 * y, cy = r2 * x - r0 * z, cz = r0 * y - r1 * x;
-                    const float ex = w * cx + (cy * z - cz * y);
-                    const float ey = w * cy + (cz * x - cx * z);
-                    const float ez = w * cz + (cx * y - cy * x);
-                    pp = r0 * e.x + r1 * e.y + r2 * e.z + pp;  // p[a] = parent row . offset + parent p[a]
-                    r0 = sc[jj] * ex + r0, r1 = sc[jj] * ey + r1, r2 = sc[jj] * ez + r2;
-                    float *rs = Rrow + 9 * j;
-                    if (VEC == 2) {
-                        // word 9j + 3a of an even-stride row: 8-byte aligned iff j + a is even (j and jj have the
-                        // same parity: chunks start at multiples of 8)
-                        // (PTX stores: the compiler otherwise merges the two arms back into three 32-bit stores)
-                        const uint32_t ra = smem_u32(rs);
-                        if (((jj & 1) ^ pa) == 0) {
-                            sts64(ra, r0, r1);
-                            sts32(ra + 8, r2);
-                        } else {
-                            sts32(ra, r0);
-                            sts64(ra + 4, r1, r2);
-                        }
-                    } else {
-                        rs[0] = r0, rs[1] = r1, rs[2] = r2;
-                    }
-                    Prow[3 * j] = pp;
-                }
-            }
-        }
-        fence_proxy_async_smem();  // this lane's stage writes -> visible to the async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(stage_full);
-    }
+    // ---- row warps: warp a computes row a of every transform ------------------------------------------
+    RowCtx cx;
+    cx.boxes = boxes, cx.tab = tab;
+    cx.rst = smem_u32(Rst), cx.pst = smem_u32(Pst);
+    cx.full0 = full0, cx.empty0 = empty0, cx.stage_full = stage_full, cx.stage_free = stage_free;
+    cx.fence_word = stage_free + 8 + 4 * threadIdx.x;
+    cx.gpos = gpos, cx.gstride = gstride, cx.n_frames = n_frames, cx.n_tiles = n_tiles, cx.tile_stride = tile_stride;
+    cx.first_tile = blockIdx.x, cx.n_joints = n_joints, cx.lane = lane;
+    if (warp == 0) fk_row_walk<S, VEC, 0>(cx);
+    else if (warp == 1) fk_row_walk<S, VEC, 1>(cx);
+    else fk_row_walk<S, VEC, 2>(cx);
 }
 
 }  // namespace pmb

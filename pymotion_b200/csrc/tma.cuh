@@ -25,6 +25,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// Same wait with a suspend-time hint (ns): the loader / drainer threads of fk_rows_kernel wait for whole tiles;
+// without the hint they were measured spinning (4e8 warp instructions per launch at 4M x 65) in the issue slots
+// the row warps need.
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity), "r"(200000u) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),

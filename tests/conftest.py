@@ -28,3 +28,8 @@ def golden_dq():
 @pytest.fixture(scope="session")
 def golden_quat():
     return dict(np.load(os.path.join(GOLDEN, "quat.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_quat_ext():
+    return dict(np.load(os.path.join(GOLDEN, "quat_ext.npz")))

@@ -1,0 +1,279 @@
+// The rest of the quaternion / dual-quaternion surface of the reference:
+//   pymotion/rotations/quat.py       from_scaled_angle_axis :6, from_angle_axis :24, from_euler :43,
+//                                    to_euler :159, to_scaled_angle_axis :230, to_angle_axis :247,
+//                                    unroll :426, slerp :465, from_to :504, from_to_axis :579
+//   pymotion/rotations/dual_quat.py  normalize :86, is_unit :118, unroll :139
+// Element-wise kernels: one thread per element, grid-stride, 16-byte accesses for quaternions.  `unroll` is
+// the one op with a dependency ALONG the frame axis: a segmented prefix product of signs, done as a
+// three-kernel chunked scan over a 2-bit state.  All arithmetic is fp32 with correctly rounded sqrt /
+// division and the accurate libdevice sin / cos / acos / atan2 (no fast-math): these feed tolerance tests at
+// 1e-5 against the NumPy reference.
+#pragma once
+#include "common.cuh"
+#include "elementwise.cuh"
+
+namespace pmb {
+
+// np.isclose(x, target) with the NumPy defaults rtol = 1e-5, atol = 1e-8 (evaluated in fp32 for fp32 input)
+__device__ __forceinline__ bool np_isclose(float x, float target) {
+    return fabsf(x - target) <= 1e-8f + 1e-5f * fabsf(target);
+}
+// products and sums rounded separately, like NumPy's element-wise multiply followed by np.sum
+__device__ __forceinline__ float dot3_np(const Vec3<float> &a, const Vec3<float> &b) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ float dot4_np(const Quat<float> &a, const Quat<float> &b) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.w, b.w), __fmul_rn(a.x, b.x)), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ Vec3<float> cross3(const Vec3<float> &a, const Vec3<float> &b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// ops/vector.py:4-19 and quat.py:411-423 applied to a 3-vector: v / (|v| + eps)
+__device__ __forceinline__ Vec3<float> v_normalize(const Vec3<float> &v, float eps) {
+    const float d = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z) + eps;
+    return {v.x / d, v.y / d, v.z / d};
+}
+
+// quat.py:24-40
+__device__ __forceinline__ Quat<float> q_from_angle_axis(float angle, const Vec3<float> &axis) {
+    float s, c;
+    sincosf(angle * 0.5f, &s, &c);
+    return {c, s * axis.x, s * axis.y, s * axis.z};
+}
+__global__ void quat_from_angle_axis_kernel(const float *angle, const float *axis, float4 *o, long long n) {
+    PMB_GRID_STRIDE(i, n) stq(o, i, q_from_angle_axis(__ldcs(angle + i), ldv(axis, i)));
+}
+// quat.py:6-21: the null vector gives 0 / 0 = nan in the axis, as in the reference
+__global__ void quat_from_scaled_angle_axis_kernel(const float *sa, float4 *o, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        const Vec3<float> v = ldv(sa, i);
+        const float angle = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+        stq(o, i, q_from_angle_axis(angle, Vec3<float>{v.x / angle, v.y / angle, v.z / angle}));
+    }
+}
+
+// Euler orders travel as one byte per element: o0 + 3 * o1 + 9 * o2, o = 0 | 1 | 2 for 'x' | 'y' | 'z'.
+__device__ __forceinline__ void order_unpack(uint8_t code, int &o0, int &o1, int &o2) {
+    o0 = code % 3, o1 = (code / 3) % 3, o2 = code / 9;
+}
+__device__ __forceinline__ Quat<float> q_about_axis(float angle, int ax) {
+    float s, c;
+    sincosf(angle * 0.5f, &s, &c);
+    return {c, ax == 0 ? s : 0.f, ax == 1 ? s : 0.f, ax == 2 ? s : 0.f};
+}
+// quat.py:43-82: q(e0 about o0) (x) q(e1 about o1) (x) q(e2 about o2)
+__global__ void quat_from_euler_kernel(const float *euler, const uint8_t *order, long long order_stride, float4 *o,
+                                       long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        int o0, o1, o2;
+        order_unpack(order[i * order_stride], o0, o1, o2);
+        const Vec3<float> e = ldv(euler, i);
+        stq(o, i, q_mul(q_about_axis(e.x, o0), q_mul(q_about_axis(e.y, o1), q_about_axis(e.z, o2))));
+    }
+}
+__device__ __forceinline__ float np_mod_2pi(float x) {
+    constexpr float kTwoPi = 6.283185307179586f;
+    float r = fmodf(x, kTwoPi);
+    if (r < 0.f) r += kTwoPi;
+    return r;
+}
+__device__ __forceinline__ float q_component(const Quat<float> &q, int k) {  // k = 0 | 1 | 2 -> x | y | z
+    return k == 0 ? q.x : (k == 1 ? q.y : q.z);
+}
+// quat.py:159-227
+__global__ void quat_to_euler_kernel(const float4 *q, const uint8_t *order, long long order_stride, float *o,
+                                     long long n) {
+    PMB_GRID_STRIDE(idx, n) {
+        int o0, o1, o2;
+        order_unpack(order[idx * order_stride], o0, o1, o2);
+        const int i = o2, j = o1, k = o0;                      // :191-193
+        const float sign = static_cast<float>((i - j) * (j - k) * (k - i) / 2);  // +-1 (+-2 / 2, exact)
+        const Quat<float> a4 = ldq(q, idx);
+        const float qi = q_component(a4, i), qj = q_component(a4, j), qk = q_component(a4, k);
+        const float a = a4.w - qj, b = qi + qk * sign, c = qj + a4.w, d = qk * sign - qi;
+        const float second = 2.f * atan2f(hypotf(c, d), hypotf(a, b)) - 1.5707963267948966f;
+        const float half_sum = atan2f(b, a), half_diff = atan2f(d, c);
+        o[3 * idx] = np_mod_2pi((half_sum + half_diff) * sign);
+        o[3 * idx + 1] = np_mod_2pi(second);
+        o[3 * idx + 2] = np_mod_2pi(half_sum - half_diff);
+    }
+}
+
+// quat.py:247-273 (scaled = false: angle [n], axis [n][3]) and :230-244 (scaled = true: angle * axis into `axis`)
+__global__ void quat_to_angle_axis_kernel(const float4 *q, float *angle, float *axis, int scaled, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        const Quat<float> a = ldq(q, i);
+        const float ang = 2.f * acosf(fminf(fmaxf(a.w, -1.f), 1.f));
+        const float s = sqrtf(fminf(fmaxf(1.f - a.w * a.w, 0.f), 1.f));
+        Vec3<float> ax{0.f, 0.f, 0.f};
+        if (s > 1e-8f) ax = {a.x / s, a.y / s, a.z / s};
+        if (scaled) {
+            stv(axis, i, Vec3<float>{ang * ax.x, ang * ax.y, ang * ax.z});
+        } else {
+            angle[i] = ang;
+            stv(axis, i, ax);
+        }
+    }
+}
+
+// quat.py:465-501; t is one value per element (t_stride = 1) or one shared value (t_stride = 0)
+__global__ void quat_slerp_kernel(const float4 *q0, const float4 *q1, const float *t, long long t_stride, int shortest,
+                                  float4 *o, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        const Quat<float> a = ldq(q0, i);
+        Quat<float> b = ldq(q1, i);
+        float dot = dot4_np(a, b);
+        if (shortest && dot < 0.f) b = {-b.w, -b.x, -b.y, -b.z}, dot = -dot;
+        dot = fminf(fmaxf(dot, -1.f), 1.f);
+        const float theta = acosf(dot) * t[i * t_stride];
+        Quat<float> c{b.w - a.w * dot, b.x - a.x * dot, b.y - a.y * dot, b.z - a.z * dot};
+        // :499: 1e-6 joins every COMPONENT before the norm
+        const float w1 = c.w + 1e-6f, x1 = c.x + 1e-6f, y1 = c.y + 1e-6f, z1 = c.z + 1e-6f;
+        const float nrm = sqrtf(w1 * w1 + x1 * x1 + y1 * y1 + z1 * z1);
+        c = {c.w / nrm, c.x / nrm, c.y / nrm, c.z / nrm};
+        float sn, cs;
+        sincosf(theta, &sn, &cs);
+        stq(o, i, Quat<float>{cs * a.w + sn * c.w, cs * a.x + sn * c.x, cs * a.y + sn * c.y, cs * a.z + sn * c.z});
+    }
+}
+
+// quat.py:504-576 (axis == nullptr) and :579-650 (fixed rotation axis)
+__global__ void quat_from_to_kernel(const float *v1, const float *v2, const float *axis, int normalize_input, float4 *o,
+                                    long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        Vec3<float> a = ldv(v1, i), b = ldv(v2, i);
+        if (normalize_input) a = v_normalize(a, 1e-8f), b = v_normalize(b, 1e-8f);
+        const Vec3<float> cr = cross3(a, b);
+        const float dot = dot3_np(a, b);
+        const float w = sqrtf((1.f + dot) * 0.5f);
+        float s = sqrtf((1.f - dot) * 0.5f);
+        Quat<float> r;
+        if (axis == nullptr) {
+            const Vec3<float> u = v_normalize(cr, 1e-8f);
+            r = {w, u.x * s, u.y * s, u.z * s};
+        } else {
+            const Vec3<float> u = ldv(axis, i);
+            const float side = dot3_np(cr, u);
+            s *= side > 0.f ? 1.f : (side < 0.f ? -1.f : side);  // np.sign (keeps 0 and nan)
+            r = {w, u.x * s, u.y * s, u.z * s};
+        }
+        if (np_isclose(dot, 1.f)) r = {1.f, 0.f, 0.f, 0.f};
+        if (np_isclose(dot, -1.f)) {
+            if (axis == nullptr) {
+                // half turn about normalize(v1 x e), e = y if v1 lies along x, else x (:552-562)
+                const Vec3<float> e = np_isclose(fabsf(a.x), 1.f) ? Vec3<float>{0.f, 1.f, 0.f} : Vec3<float>{1.f, 0.f, 0.f};
+                const Vec3<float> u = v_normalize(cross3(a, e), 1e-8f);
+                r = {0.f, u.x, u.y, u.z};
+            } else {
+                const Vec3<float> u = ldv(axis, i);
+                r = {0.f, u.x, u.y, u.z};
+            }
+        }
+        stq(o, i, r);
+    }
+}
+
+// ---- dual_quat.normalize / is_unit -------------------------------------------------------------------
+// flags[0] = some real part is not ~0, flags[1] = some |real|^2 is not ~1, flags[2] = some real.dual is not ~0
+// (dual_quat.py:118-136 reduces over the WHOLE array).  flags must be zero on entry.
+__device__ __forceinline__ void unit_flags(const Quat<float> &r, const Quat<float> &d, float atol, int *flags) {
+    const float n2 = dot4_np(r, r);
+    const bool f0 = !np_isclose(n2, 0.f), f1 = !np_isclose(n2, 1.f), f2 = !(fabsf(dot4_np(r, d)) <= atol);
+    // one atomic per warp and flag
+    if (__any_sync(__activemask(), f0) && f0) atomicOr(flags + 0, 1);
+    if (__any_sync(__activemask(), f1) && f1) atomicOr(flags + 1, 1);
+    if (__any_sync(__activemask(), f2) && f2) atomicOr(flags + 2, 1);
+}
+__global__ void dq_is_unit_kernel(const float4 *dq, float atol, int *flags, long long n) {
+    PMB_GRID_STRIDE(i, n) unit_flags(ldq(dq, 2 * i), ldq(dq, 2 * i + 1), atol, flags);
+}
+// pass 1 (dual_quat.py:98-103): both parts divided by |real|, flags of the result (atol 1e-3, the default)
+__global__ void dq_normalize_scale_kernel(const float4 *dq, float4 *o, int *flags, long long n) {
+    PMB_GRID_STRIDE(i, n) {
+        const Quat<float> r = ldq(dq, 2 * i), d = ldq(dq, 2 * i + 1);
+        const float nrm = q_length(r);
+        const Quat<float> rn{r.w / nrm, r.x / nrm, r.y / nrm, r.z / nrm}, dn{d.w / nrm, d.x / nrm, d.y / nrm, d.z / nrm};
+        o[2 * i] = make_float4(rn.w, rn.x, rn.y, rn.z);
+        o[2 * i + 1] = make_float4(dn.w, dn.x, dn.y, dn.z);
+        unit_flags(rn, dn, 1e-3f, flags);
+    }
+}
+// pass 2 (:104-111): only if the scaled array as a whole is not unit, remove the real direction from every dual part
+__global__ void dq_normalize_ortho_kernel(const float4 *dq, float4 *o, const int *flags, long long n) {
+    const bool unit = flags[0] == 0 || (flags[1] == 0 && flags[2] == 0);
+    if (unit) return;
+    PMB_GRID_STRIDE(i, n) {
+        const Quat<float> r = ldq(dq, 2 * i), d = ldq(dq, 2 * i + 1);
+        const float nrm = q_length(r);
+        const float k = dot4_np(r, d) / (nrm * nrm);
+        const float4 rn = o[2 * i];
+        const Quat<float> dn{d.w / nrm, d.x / nrm, d.y / nrm, d.z / nrm};
+        stq(o, 2 * i + 1, Quat<float>{dn.w - rn.x * k, dn.x - rn.y * k, dn.y - rn.z * k, dn.z - rn.w * k});
+    }
+}
+
+// ---- unroll (quat.py:426-462, dual_quat.py:139-167) ---------------------------------------------------
+// x is [T][M][W4] float4 (W4 = 1 quaternions, 2 dual quaternions; the decision uses the first float4).
+// Entry t is negated iff its dot product with the UNROLLED entry t-1 is < 0.  With d_t the dot product of the
+// ORIGINAL entries, the sign s_t obeys s_t = s_{t-1} * sgn(d_t) when d_t != 0 and s_t = +1 when d_t is 0 or
+// nan (no flip): a prefix product with resets.  State = 2 bits {neg, reset seen}; combine(p, c) =
+// {c.reset ? c.neg : p.neg ^ c.neg, p.reset | c.reset} is associative, so the scan is chunked:
+//   unroll_local   per (chunk of kUnrollChunk steps, column): running state of every step -> local[T][M],
+//                  state of the whole chunk -> agg[chunks][M]
+//   unroll_chunks  per column: exclusive scan of agg over the chunks (in place)
+//   unroll_apply   per (step, column): combine(agg[chunk], local[t]) decides the flip
+constexpr int kUnrollChunk = 128;
+__device__ __forceinline__ uint8_t unroll_combine(uint8_t p, uint8_t c) {
+    const uint8_t neg = (c & 2) ? (c & 1) : ((p ^ c) & 1);
+    return neg | ((p | c) & 2);
+}
+__global__ void unroll_local_kernel(const float4 *x, int w4, long long n_steps, long long n_cols, uint8_t *local,
+                                    uint8_t *agg) {
+    const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (m >= n_cols) return;
+    const long long c = blockIdx.y, t0 = c * kUnrollChunk;
+    const long long t1 = min(t0 + kUnrollChunk, n_steps);
+    float4 prev = t0 > 0 ? __ldg(x + ((t0 - 1) * n_cols + m) * w4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    uint8_t state = 0;
+    for (long long t = t0; t < t1; ++t) {
+        const float4 cur = __ldg(x + (t * n_cols + m) * w4);
+        uint8_t el;
+        if (t == 0) {
+            el = 2;  // the first entry keeps its cover
+        } else {
+            // np.sum(r[i] * r[i - 1], axis=-1): separate roundings
+            const float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cur.x, prev.x), __fmul_rn(cur.y, prev.y)), __fmul_rn(cur.z, prev.z)),
+                                      __fmul_rn(cur.w, prev.w));
+            el = d < 0.f ? 1 : (d > 0.f ? 0 : 2);
+        }
+        state = unroll_combine(state, el);
+        local[t * n_cols + m] = state;
+        prev = cur;
+    }
+    agg[c * n_cols + m] = state;
+}
+__global__ void unroll_chunks_kernel(uint8_t *agg, long long n_chunks, long long n_cols) {
+    const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (m >= n_cols) return;
+    uint8_t run = 0;
+    for (long long c = 0; c < n_chunks; ++c) {
+        const uint8_t a = agg[c * n_cols + m];
+        agg[c * n_cols + m] = run;  // exclusive: the state BEFORE the chunk
+        run = unroll_combine(run, a);
+    }
+}
+__global__ void unroll_apply_kernel(const float4 *x, int w4, long long n_steps, long long n_cols, const uint8_t *local,
+                                    const uint8_t *agg, float4 *o) {
+    const long long n = n_steps * n_cols;
+    PMB_GRID_STRIDE(i, n) {
+        const long long t = i / n_cols, m = i - t * n_cols;
+        const uint8_t s = unroll_combine(agg[(t / kUnrollChunk) * n_cols + m], local[i]);
+        const float f = (s & 1) ? -1.f : 1.f;
+        for (int k = 0; k < w4; ++k) {
+            const float4 v = __ldcs(x + i * w4 + k);
+            __stcs(o + i * w4 + k, make_float4(f * v.x, f * v.y, f * v.z, f * v.w));
+        }
+    }
+}
+
+}  // namespace pmb

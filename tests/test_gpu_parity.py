@@ -59,7 +59,7 @@ def test_fk_chain3_goldens(sk, golden_fk, case):
     # per-frame offsets accepted (:267)
     pos2, rotm2 = sk.fk(rot, g["chain3/gpos"], np.tile(g["chain3/offsets"], (2, 1, 1)), g["chain3/parents"])
     assert_allclose(pos2, pos, **TOL)  # different kernels (row teams vs per-frame offsets): same answer, not the same bits
-    assert_allclose(rotm2, rotm, atol=0)
+    assert_allclose(rotm2, rotm, **TOL)
 
 
 def test_fk_nd_leading_dims(sk, golden_fk):

@@ -39,6 +39,9 @@ WORKLOADS = {
     "fk_1m_x_22": ("body22", 1_000_000),
     "fk_4m_x_65": ("deep65", 4_000_000),
     "fk_4m_x_52": ("smplh52", 4_000_000),
+    # launch-heuristic calibration sizes (not BASELINE configs)
+    "fk_2m_x_32": ("body32", 2_000_000),
+    "fk_2m_x_40": ("body40", 2_000_000),
 }
 # --kernel-only development workloads for the other ops of the path (BASELINE.json configs[2])
 DEV_OPS = ("fk", "to_dq", "from_dq", "round_trip", "fk_quat")

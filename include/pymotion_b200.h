@@ -4,11 +4,13 @@
  * UPC-ViRVIG/pymotion v0.2.3:
  *
  *   pymotion/ops/skeleton.py        fk :16, from_root_dual_quat :173, to_root_dual_quat :207,
- *                                   from_global_rotations :64
+ *                                   from_global_rotations :64, from_root_positions :96, mirror :247
  *   pymotion/rotations/quat.py      mul :337, mul_vec :320, length :364, inverse :379,
  *                                   conjugate :396, normalize :411, to_matrix :276, from_matrix :85
  *   pymotion/rotations/dual_quat.py from_rotation_translation :12, from_translation :39,
  *                                   to_rotation_translation :62
+ * and, off the hot path, the rest of those two modules: quat from/to angle-axis,
+ * scaled angle-axis, Euler; unroll, slerp, from_to, from_to_axis; dual_quat normalize, is_unit, unroll.
  *
  * The reference has no FFI layer of its own (it is pure NumPy / PyTorch); these
  * are the entry points a ctypes / cffi stub inside those modules would bind
@@ -130,6 +132,56 @@ int pmb_dq_from_rotation_translation_f32(const float *rotations, const float *tr
 int pmb_dq_from_translation_f32(const float *translations, float *dq, int64_t n, void *stream);       /* dual_quat.py:39 */
 int pmb_dq_to_rotation_translation_f32(const float *dq, float *rotations, float *translations,
                                        int64_t n, void *stream);                                      /* dual_quat.py:62 */
+
+/* ---- the rest of the quat / dual_quat surface -------- */
+/* n = number of elements; angle [n], axis / vectors [n][3], euler [n][3], quaternions [n][4]. */
+int pmb_quat_from_angle_axis_f32(const float *angle, const float *axis, float *out, int64_t n, void *stream);      /* quat.py:24 */
+int pmb_quat_from_scaled_angle_axis_f32(const float *scaled_axis, float *out, int64_t n, void *stream);           /* quat.py:6 */
+/* Euler orders ('x'|'y'|'z' per slot, quat.py:43-82, :159-227) travel as ONE byte per element,
+ * o0 + 3*o1 + 9*o2 with o = 0|1|2 for x|y|z (device array); order_stride 1 = per element, 0 = one shared order. */
+int pmb_quat_from_euler_f32(const float *euler, const uint8_t *order_codes, int64_t order_stride, float *out,
+                            int64_t n, void *stream);                                                             /* quat.py:43 */
+int pmb_quat_to_euler_f32(const float *q, const uint8_t *order_codes, int64_t order_stride, float *out,
+                          int64_t n, void *stream);                                                               /* quat.py:159 */
+int pmb_quat_to_angle_axis_f32(const float *q, float *angle, float *axis, int64_t n, void *stream);               /* quat.py:247 */
+int pmb_quat_to_scaled_angle_axis_f32(const float *q, float *out, int64_t n, void *stream);                       /* quat.py:230 */
+/* t: device array, t_stride 1 = one value per element, 0 = one shared value.  shortest != 0: flip q1 when q0.q1 < 0. */
+int pmb_quat_slerp_f32(const float *q0, const float *q1, const float *t, int64_t t_stride, int32_t shortest,
+                       float *out, int64_t n, void *stream);                                                      /* quat.py:465 */
+int pmb_quat_from_to_f32(const float *v1, const float *v2, int32_t normalize_input, float *out, int64_t n,
+                         void *stream);                                                                           /* quat.py:504 */
+int pmb_quat_from_to_axis_f32(const float *v1, const float *v2, const float *rot_axis, int32_t normalize_input,
+                              float *out, int64_t n, void *stream);                                               /* quat.py:579 */
+/* quat.unroll (quat.py:426, width 4) / dual_quat.unroll (dual_quat.py:139, width 8) along the LEADING axis of
+ * x [n_steps][n_cols][width]: entry t is negated iff its dot product (first 4 numbers) with the already
+ * unrolled entry t-1 is < 0.  Chunked scan; `workspace` is a device scratch buffer of at least
+ * pmb_unroll_workspace_bytes(n_steps, n_cols) bytes owned by the caller.  out may not alias x. */
+int64_t pmb_unroll_workspace_bytes(int64_t n_steps, int64_t n_cols);
+int pmb_unroll_f32(const float *x, int32_t width, int64_t n_steps, int64_t n_cols, float *out, void *workspace,
+                   int64_t workspace_bytes, void *stream);
+/* dual_quat.is_unit (dual_quat.py:118): ONE verdict for the whole array, returned as three device flags the
+ * caller reads after synchronising: flags3[0] = some real part is not ~0, [1] = some |real|^2 is not ~1,
+ * [2] = some |real.dual| > atol;  unit  <=>  !flags3[0] || (!flags3[1] && !flags3[2]). */
+int pmb_dq_is_unit_f32(const float *dq, float atol, int64_t n, int32_t *flags3, void *stream);
+/* dual_quat.normalize (dual_quat.py:86): divide by |real|; if the WHOLE scaled array is not unit, project the
+ * real direction out of every dual part.  flags3: device scratch (3 int32), no host synchronisation. */
+int pmb_dq_normalize_f32(const float *dq, float *out, int64_t n, int32_t *flags3, void *stream);
+
+/* ---- fk consumers ------------------------------------ */
+/* ops/skeleton.py:96-170  from_root_positions(positions, parents, offsets) -> rotations
+ *   positions [n_frames][n_joints][3] root-centred joint positions, offsets [n_joints][3] (device),
+ *   rotations [n_frames][n_joints][4] out.  One tree walk per frame instead of the reference's O(J) fk passes. */
+int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_host, const float *offsets,
+                                int64_t n_frames, int32_t n_joints, float *rotations, void *stream);
+/* Second half of mirror / _true_mirror (ops/skeleton.py:324-331, :410-416): global quaternions re-indexed by
+ * joints_mapping_host (NULL = identity; 'symmetry' mode), the two vector components for `mirror_axis`
+ * (0 = X, 1 = Y, 2 = Z) negated, then back to local space as from_global_rotations does. */
+int pmb_mirror_to_local_f32(const float *global_quats, const int64_t *parents_host, const int64_t *joints_mapping_host,
+                            int32_t mirror_axis, int64_t n_frames, int32_t n_joints, float *local_quats, void *stream);
+/* out = v with component `axis` negated, v [n][3] (translations / offsets / end sites, skeleton.py:405-408). */
+int pmb_vec_mirror_f32(const float *v, int32_t axis, float *out, int64_t n, void *stream);
+/* out[f][j] = positions[f][j] - positions[f][0] (mirror mode 'positions', skeleton.py:338). */
+int pmb_root_center_f32(const float *positions, float *out, int64_t n_frames, int32_t n_joints, void *stream);
 
 /* ---- introspection of the host-side joint program (tests) ---- */
 

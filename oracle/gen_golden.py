@@ -344,9 +344,39 @@ def gen_quat_ext():
     return d
 
 
+def gen_ik():
+    """from_root_positions and the three mirror modes (real reference outputs)."""
+    d = {}
+    mapping22 = np.array([0, 5, 6, 7, 8, 1, 2, 3, 4, 9, 10, 11, 12, 13, 18, 19, 20, 21, 14, 15, 16, 17])  # legs / arms swapped
+    d["body22/joints_mapping"] = mapping22
+    rng = np.random.default_rng(99)
+    d["end_sites"] = rng.standard_normal((5, 3)).astype(np.float32)
+    for name, frames in (("chain3", 8), ("body22", 32), ("smplh52", 12), ("deep65", 10)):
+        par = np.array(TOPOLOGIES[name])
+        rot, gpos, off = synth_numpy(frames, par, seed=17 + len(par))
+        d[f"{name}/parents"], d[f"{name}/rot"], d[f"{name}/gpos"], d[f"{name}/offsets"] = par, rot, gpos, off
+        pos, _ = ref_sk.fk(rot, gpos, off, par)
+        centred = (pos - pos[:, 0:1]).astype(np.float32)
+        d[f"{name}/centred"] = centred
+        with np.errstate(invalid="ignore"):
+            d[f"{name}/from_root_positions"] = ref_sk.from_root_positions(centred, par, off)
+            for axis in ("XYZ" if name == "body22" else "Y"):
+                out = ref_sk.mirror(rot.copy(), gpos.copy(), par, off.copy(), d["end_sites"].copy(), None, "all", axis)
+                for key, val in zip(("rot", "gpos", "offsets", "ends"), out):
+                    d[f"{name}/mirror_all_{axis}/{key}"] = val
+            out = ref_sk.mirror(rot.copy(), gpos.copy(), par, off.copy(), None, None, "positions", "X")
+            d[f"{name}/mirror_positions_X/rot"], d[f"{name}/mirror_positions_X/gpos"] = out[0], out[1]
+            if name == "body22":
+                for axis in "XZ":
+                    out = ref_sk.mirror(rot.copy(), gpos.copy(), par, off.copy(), None, mapping22, "symmetry", axis)
+                    d[f"{name}/mirror_symmetry_{axis}/rot"], d[f"{name}/mirror_symmetry_{axis}/gpos"] = out[0], out[1]
+    np.savez_compressed(os.path.join(OUT, "ik.npz"), **d)
+    return d
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    for fn in (gen_fk, gen_dq, gen_quat, gen_quat_ext):
+    for fn in (gen_fk, gen_dq, gen_quat, gen_quat_ext, gen_ik):
         out = fn()
         print(fn.__name__, len(out), "arrays")
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)}

@@ -32,6 +32,8 @@ __all__ = [
     "vec_normalize", "quat_from_angle_axis", "quat_from_scaled_angle_axis", "quat_from_euler", "quat_to_euler",
     "quat_to_angle_axis", "quat_to_scaled_angle_axis", "quat_unroll", "quat_slerp", "quat_from_to",
     "quat_from_to_axis", "dq_is_unit", "dq_normalize", "dq_unroll",
+    # the in-repo consumers of fk
+    "from_root_positions", "mirror",
 ]
 
 
@@ -431,3 +433,99 @@ def dq_normalize(dq):
 def dq_unroll(dq, axis):
     """dual_quat.py:139-167: quat unroll decided on the REAL part, the flip applied to all eight numbers."""
     return dq * _unroll_signs(dq[..., :4], axis)[..., np.newaxis]
+
+
+# ----------------------------------------------------------------------------
+# fk consumers (SURVEY 8f rank 2)                         (ops/skeleton.py)
+# ----------------------------------------------------------------------------
+def from_root_positions(positions, parents, offsets):
+    """ops/skeleton.py:96-170.  Joints are visited in index order; before EVERY alignment the current
+    rotations go through a full fk (root at the origin) and quat.from_matrix, exactly like the reference:
+      first child c of j   : rot_j = from_to(G_j^-1 (p_c - p_j), G_j^-1 (P_c - P_j))
+      further children g   : rot_j = rot_j (x) from_to_axis(G_j^-1 (p_g - p_j), G_j^-1 (P_g - P_j),
+                                                           G_j^-1 normalize(P_c - P_j))
+    with p the fk pose under the rotations chosen so far, P the target positions and G_j the global rotation
+    of j in that pose.  Result float64 (the rotations start as a float64 identity, :129)."""
+    parents = np.asarray(parents)
+    n_frames, n_joints = positions.shape[0], parents.shape[0]
+    kids = [[] for _ in range(n_joints)]
+    for i in range(1, n_joints):
+        kids[parents[i]].append(i)
+    rotations = np.tile(np.array([1.0, 0.0, 0.0, 0.0]), (n_frames, n_joints, 1))
+    origin = np.zeros((1, 3))
+
+    def pose():
+        pos, rotm = fk(rotations, origin, offsets, parents)
+        return pos, quat_from_matrix(rotm)
+
+    for j, ks in enumerate(kids):
+        if not ks:
+            continue
+        pos, grot = pose()
+        back = quat_inverse(grot[:, j])
+        c = ks[0]
+        rest = quat_mul_vec(back, pos[:, c] - pos[:, j])
+        pred = quat_mul_vec(back, positions[:, c] - positions[:, j])
+        rotations[:, j] = quat_from_to(rest, pred)
+        for g in ks[1:]:
+            pos, grot = pose()
+            back = quat_inverse(grot[:, j])
+            rest_g = quat_mul_vec(back, pos[:, g] - pos[:, j])
+            pred_g = quat_mul_vec(back, positions[:, g] - positions[:, j])
+            roll_axis = quat_mul_vec(back, vec_normalize(positions[:, c] - positions[:, j]))
+            rotations[:, j] = quat_mul(rotations[:, j], quat_from_to_axis(rest_g, pred_g, roll_axis))
+    return rotations
+
+
+_MIRROR = {"X": (0, (2, 3)), "Y": (1, (1, 3)), "Z": (2, (1, 2))}  # axis -> (vector index, quaternion indices negated)
+
+
+def _mirror_all(local_rotations, global_translation, parents, offsets, end_sites, axis):
+    """ops/skeleton.py:347-418 (_true_mirror): offsets / end sites / root translation reflected, global
+    quaternions (fk with the reflected offsets, root at the origin -> from_matrix) get two components negated
+    and go back to local space."""
+    if axis not in _MIRROR:
+        raise ValueError("Invalid axis. Choose 'X', 'Y', or 'Z'")
+    vi, (qa, qb) = _MIRROR[axis]
+    offsets = offsets.copy()
+    offsets[:, vi] = -offsets[:, vi]
+    if end_sites is not None:
+        end_sites = end_sites.copy()
+        end_sites[:, vi] = -end_sites[:, vi]
+    global_translation = global_translation.copy()
+    global_translation[..., vi] = -global_translation[..., vi]
+    _, rotm = fk(local_rotations, np.zeros_like(global_translation), offsets, parents)
+    gq = quat_from_matrix(rotm)
+    gq[..., qa] = -gq[..., qa]
+    gq[..., qb] = -gq[..., qb]
+    return from_global_rotations(gq, parents), global_translation, offsets, end_sites
+
+
+def mirror(local_rotations, global_translation, parents, offsets, end_sites=None, joints_mapping=None, mode="all",
+           axis="X"):
+    """ops/skeleton.py:247-344.  Unlike the reference ('symmetry' mode negates the caller's global_translation
+    in place, :321) the restatement never modifies its inputs; returned values are the same."""
+    parents = np.asarray(parents)
+    if mode == "all":
+        return _mirror_all(local_rotations, global_translation, parents, offsets, end_sites, axis)
+    if mode == "symmetry":
+        if joints_mapping is None:
+            raise ValueError("joints_mapping must be provided for mode 'symmetry'")
+        if len(joints_mapping) != len(parents):
+            raise ValueError("joints_mapping must have the same length as the number of joints")
+        if axis not in _MIRROR:
+            raise ValueError("Invalid axis. Choose 'X', 'Y', or 'Z'")
+        vi, (qa, qb) = _MIRROR[axis]
+        _, rotm = fk(local_rotations, np.zeros_like(global_translation), offsets, parents)
+        gq = quat_from_matrix(rotm)[..., np.asarray(joints_mapping), :]
+        gq[..., qa] = -gq[..., qa]
+        gq[..., qb] = -gq[..., qb]
+        moved = global_translation.copy()
+        moved[..., vi] = -moved[..., vi]
+        return from_global_rotations(gq, parents), moved, offsets, end_sites
+    if mode == "positions":
+        rots, moved, mirrored_offsets, _ = _mirror_all(local_rotations, global_translation, parents, offsets, end_sites, axis)
+        pos, _ = fk(rots, moved, mirrored_offsets, parents)
+        pos = pos - pos[..., 0:1, :]
+        return from_root_positions(pos, parents, offsets), moved, offsets, end_sites
+    raise ValueError("Invalid mode. Choose 'symmetry', 'all', or 'positions'")

@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpymotion_b200.so")
+LIB_PATH = os.environ.get("PMB_LIB_PATH") or os.path.join(_PKG, "libpymotion_b200.so")  # override: kernel experiments only
 
 PMB_OK = 0
 PMB_ERR_NULL, PMB_ERR_SHAPE, PMB_ERR_ALIGN, PMB_ERR_TOPOLOGY, PMB_ERR_CUDA, PMB_ERR_ROOT_OFFSET = -1, -2, -3, -4, -5, -6
@@ -43,8 +43,26 @@ SIGNATURES = {
     "pmb_dq_from_rotation_translation_f32": [_vp, _vp, _vp, _i64, _vp],
     "pmb_dq_from_translation_f32": [_vp, _vp, _i64, _vp],
     "pmb_dq_to_rotation_translation_f32": [_vp, _vp, _vp, _i64, _vp],
+    "pmb_quat_from_angle_axis_f32": [_vp, _vp, _vp, _i64, _vp],
+    "pmb_quat_from_scaled_angle_axis_f32": [_vp, _vp, _i64, _vp],
+    "pmb_quat_from_euler_f32": [_vp, _vp, _i64, _vp, _i64, _vp],
+    "pmb_quat_to_euler_f32": [_vp, _vp, _i64, _vp, _i64, _vp],
+    "pmb_quat_to_angle_axis_f32": [_vp, _vp, _vp, _i64, _vp],
+    "pmb_quat_to_scaled_angle_axis_f32": [_vp, _vp, _i64, _vp],
+    "pmb_quat_slerp_f32": [_vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp],
+    "pmb_quat_from_to_f32": [_vp, _vp, _i32, _vp, _i64, _vp],
+    "pmb_quat_from_to_axis_f32": [_vp, _vp, _vp, _i32, _vp, _i64, _vp],
+    "pmb_unroll_workspace_bytes": [_i64, _i64],
+    "pmb_unroll_f32": [_vp, _i32, _i64, _i64, _vp, _vp, _i64, _vp],
+    "pmb_dq_is_unit_f32": [_vp, _f32, _i64, _vp, _vp],
+    "pmb_dq_normalize_f32": [_vp, _vp, _i64, _vp, _vp],
+    "pmb_from_root_positions_f32": [_vp, _vp, _vp, _i64, _i32, _vp, _vp],
+    "pmb_mirror_to_local_f32": [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp],
+    "pmb_vec_mirror_f32": [_vp, _i32, _vp, _i64, _vp],
+    "pmb_root_center_f32": [_vp, _vp, _i64, _i32, _vp],
 }
-_RESTYPES = {"pmb_last_error": ctypes.c_char_p, "pmb_last_variant": ctypes.c_char_p, "pmb_status_string": ctypes.c_char_p, "pmb_release_workspace": None}
+_RESTYPES = {"pmb_last_error": ctypes.c_char_p, "pmb_last_variant": ctypes.c_char_p, "pmb_status_string": ctypes.c_char_p, "pmb_release_workspace": None,
+             "pmb_unroll_workspace_bytes": ctypes.c_int64}
 
 _lib = None
 

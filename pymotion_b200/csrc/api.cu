@@ -16,7 +16,9 @@
 #include "elementwise.cuh"
 #include "fk_kernel.cuh"
 #include "fk_rows_kernel.cuh"
+#include "ik_kernels.cuh"
 #include "joint_program.h"
+#include "rotations_ext.cuh"
 
 namespace {
 
@@ -176,7 +178,7 @@ int launch_fk_cfg(const FkArgs &a, const DeviceProps &dp) {
 
 // ---- fk, row-team kernel (fk_rows_kernel.cuh) ------------------------------------
 template <int S, int VEC>
-int launch_fk_rows_cfg(const FkArgs &a, const DeviceProps &dp) {
+int launch_fk_rows_cfg(const FkArgs &a, const DeviceProps &dp, int team_cap) {
     auto kernel = pmb::fk_rows_kernel<S, VEC>;
     const int smem = pmb::fk_rows_geom(S, a.n_joints).block_bytes;
     int rc = set_smem(kernel, smem);
@@ -187,6 +189,7 @@ int launch_fk_rows_cfg(const FkArgs &a, const DeviceProps &dp) {
     int per_sm = 0;
     PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, pmb::kRowThreads, smem));
     if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk row kernel does not fit on an SM (%d bytes of shared memory)", smem);
+    if (team_cap > 0) per_sm = std::min(per_sm, team_cap);
     per_sm = std::max(1, std::min(per_sm, env_int("PMB_FK_BLOCKS_PER_SM", per_sm)));
     const long long blocks = std::min<long long>(tiles, static_cast<long long>(per_sm) * dp.sm_count);
     note_variant("fk_rows_kernel<S=%d,VEC=%d> grid=%lld (%d teams/SM) smem=%d", S, VEC, blocks, per_sm, smem);
@@ -205,26 +208,40 @@ inline int fk_rows_teams(int stages, const FkArgs &a, const DeviceProps &dp) {
 }
 
 // Returns true and launches if the row-team kernel is the better choice (PMB_FK_ROWS = 0 / 1 forces).
+// Measured on B200: what matters is how many teams share an SM.
+//   >= 4 teams (J <= 30): rows win with the shallow ring and exactly 4 teams (1M x 22: 0.231 ms vs 0.2415 ms
+//                         for the thread-per-frame kernel; a 5th team or a deeper ring is slower);
+//   3 teams  (J <= 44):   rows, deepest ring that keeps the 3 teams;
+//   2 teams  (J <= 69):   a toss-up decided by the joint order: the thread-per-frame kernel pays for every live
+//                         branch slot (4M x 65, 10 slots: rows 4.45 TB/s vs 3.93), the row kernel does not have
+//                         slots but only two tiles in flight per SM (4M x 52, 3 slots: rows 4.54 vs 4.77);
+//   1 team:               never (nothing overlaps the drain of the stage).
 bool try_fk_rows(const FkArgs &a, const DeviceProps &dp, int &rc) {
     const int force = env_int("PMB_FK_ROWS", -1);
     if (force == 0) return false;
     if (force != 1 && (getenv("PMB_FK_GROUP") || getenv("PMB_FK_WARPS"))) return false;  // a chain-kernel variant is being forced
     int stages = env_int("PMB_FK_STAGES", -1);
+    int team_cap = 0;  // 0: as many as fit
     if (stages < 0) {
-        // the deepest ring that does not cost a team
-        stages = 2;
-        for (int s = 3; s <= 4; ++s)
-            if (fk_rows_teams(s, a, dp) == fk_rows_teams(2, a, dp)) stages = s;
+        const int t2 = fk_rows_teams(2, a, dp);
+        if (t2 >= 4) {
+            stages = 2, team_cap = 4;
+        } else {
+            stages = 2;
+            for (int s = 3; s <= 4; ++s)
+                if (fk_rows_teams(s, a, dp) == t2) stages = s;  // the deepest ring that does not cost a team
+        }
     }
-    if (stages < 2 || stages > 4 || fk_rows_teams(stages, a, dp) < 1) {
+    const int teams = (stages >= 2 && stages <= 4) ? fk_rows_teams(stages, a, dp) : 0;
+    if (teams < 1) {
         if (force == 1) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_ROWS=1: the row kernel does not fit (stages %d)", stages); return true; }
         return false;
     }
-    if (force != 1 && fk_rows_teams(stages, a, dp) < 2) return false;  // one team per SM cannot hide its own drain
+    if (force != 1 && (teams < 2 || (teams == 2 && a.n_slots <= 4))) return false;
     if (a.n_joints % 2 == 0)
-        rc = stages == 2 ? launch_fk_rows_cfg<2, 2>(a, dp) : stages == 3 ? launch_fk_rows_cfg<3, 2>(a, dp) : launch_fk_rows_cfg<4, 2>(a, dp);
+        rc = stages == 2 ? launch_fk_rows_cfg<2, 2>(a, dp, team_cap) : stages == 3 ? launch_fk_rows_cfg<3, 2>(a, dp, team_cap) : launch_fk_rows_cfg<4, 2>(a, dp, team_cap);
     else
-        rc = stages == 2 ? launch_fk_rows_cfg<2, 1>(a, dp) : stages == 3 ? launch_fk_rows_cfg<3, 1>(a, dp) : launch_fk_rows_cfg<4, 1>(a, dp);
+        rc = stages == 2 ? launch_fk_rows_cfg<2, 1>(a, dp, team_cap) : stages == 3 ? launch_fk_rows_cfg<3, 1>(a, dp, team_cap) : launch_fk_rows_cfg<4, 1>(a, dp, team_cap);
     return true;
 }
 
@@ -640,6 +657,227 @@ int pmb_dq_to_rotation_translation_f32(const float *dq, float *rotations, float 
     PMB_EW_PROLOGUE(n, dq, rotations, translations);
     PMB_NEED16(dq); PMB_NEED16(rotations);
     pmb::dq_to_rt_kernel<<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)rotations, translations, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// ---- the rest of the quaternion / dual-quaternion surface (rotations_ext.cuh) ------------------
+int pmb_quat_from_angle_axis_f32(const float *angle, const float *axis, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, angle, axis, out);
+    PMB_NEED16(out);
+    pmb::quat_from_angle_axis_kernel<<<grid_, 256, 0, st_>>>(angle, axis, (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_from_scaled_angle_axis_f32(const float *scaled_axis, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, scaled_axis, out);
+    PMB_NEED16(out);
+    pmb::quat_from_scaled_angle_axis_kernel<<<grid_, 256, 0, st_>>>(scaled_axis, (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_from_euler_f32(const float *euler, const uint8_t *order_codes, int64_t order_stride, float *out, int64_t n,
+                            void *stream) {
+    PMB_EW_PROLOGUE(n, euler, order_codes, out);
+    PMB_NEED16(out);
+    if (order_stride != 0 && order_stride != 1) return fail(PMB_ERR_SHAPE, "%s: order_stride must be 0 or 1", __func__);
+    pmb::quat_from_euler_kernel<<<grid_, 256, 0, st_>>>(euler, order_codes, order_stride, (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_to_euler_f32(const float *q, const uint8_t *order_codes, int64_t order_stride, float *out, int64_t n,
+                          void *stream) {
+    PMB_EW_PROLOGUE(n, q, order_codes, out);
+    PMB_NEED16(q);
+    if (order_stride != 0 && order_stride != 1) return fail(PMB_ERR_SHAPE, "%s: order_stride must be 0 or 1", __func__);
+    pmb::quat_to_euler_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, order_codes, order_stride, out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_to_angle_axis_f32(const float *q, float *angle, float *axis, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q, angle, axis);
+    PMB_NEED16(q);
+    pmb::quat_to_angle_axis_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, angle, axis, 0, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_to_scaled_angle_axis_f32(const float *q, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q, out);
+    PMB_NEED16(q);
+    pmb::quat_to_angle_axis_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, nullptr, out, 1, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_slerp_f32(const float *q0, const float *q1, const float *t, int64_t t_stride, int32_t shortest, float *out,
+                       int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q0, q1, t, out);
+    PMB_NEED16(q0); PMB_NEED16(q1); PMB_NEED16(out);
+    if (t_stride != 0 && t_stride != 1) return fail(PMB_ERR_SHAPE, "%s: t_stride must be 0 or 1", __func__);
+    pmb::quat_slerp_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q0, (const float4 *)q1, t, t_stride, shortest,
+                                                   (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_from_to_f32(const float *v1, const float *v2, int32_t normalize_input, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, v1, v2, out);
+    PMB_NEED16(out);
+    pmb::quat_from_to_kernel<<<grid_, 256, 0, st_>>>(v1, v2, nullptr, normalize_input, (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_quat_from_to_axis_f32(const float *v1, const float *v2, const float *rot_axis, int32_t normalize_input, float *out,
+                              int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, v1, v2, rot_axis, out);
+    PMB_NEED16(out);
+    pmb::quat_from_to_kernel<<<grid_, 256, 0, st_>>>(v1, v2, rot_axis, normalize_input, (float4 *)out, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+int64_t pmb_unroll_workspace_bytes(int64_t n_steps, int64_t n_cols) {
+    if (n_steps < 0 || n_cols < 0) return 0;
+    const int64_t chunks = (n_steps + pmb::kUnrollChunk - 1) / pmb::kUnrollChunk;
+    return n_steps * n_cols + chunks * n_cols + 16;
+}
+int pmb_unroll_f32(const float *x, int32_t width, int64_t n_steps, int64_t n_cols, float *out, void *workspace,
+                   int64_t workspace_bytes, void *stream) {
+    if (width != 4 && width != 8) return fail(PMB_ERR_SHAPE, "%s: width must be 4 (quaternions) or 8 (dual quaternions)", __func__);
+    if (n_steps < 0 || n_cols < 0) return fail(PMB_ERR_SHAPE, "%s: negative size", __func__);
+    if (n_steps == 0 || n_cols == 0) return PMB_OK;
+    if (!x || !out || !workspace) return fail(PMB_ERR_NULL, "%s: NULL array pointer", __func__);
+    PMB_NEED16(x); PMB_NEED16(out);
+    if (workspace_bytes < pmb_unroll_workspace_bytes(n_steps, n_cols))
+        return fail(PMB_ERR_SHAPE, "%s: workspace too small (%lld < %lld bytes)", __func__,
+                    static_cast<long long>(workspace_bytes), static_cast<long long>(pmb_unroll_workspace_bytes(n_steps, n_cols)));
+    DeviceProps dp;
+    int rc = device_props(dp);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t chunks = (n_steps + pmb::kUnrollChunk - 1) / pmb::kUnrollChunk;
+    if (chunks > 65535) {
+        // grid.y limit: 65535 chunks of 128 steps = 8.3 M steps per call
+        return fail(PMB_ERR_SHAPE, "%s: at most %lld steps along the unroll axis per call", __func__,
+                    static_cast<long long>(65535) * pmb::kUnrollChunk);
+    }
+    uint8_t *local = static_cast<uint8_t *>(workspace), *agg = local + n_steps * n_cols;
+    const int w4 = width / 4;
+    const int tc = 128;
+    const unsigned col_blocks = static_cast<unsigned>((n_cols + tc - 1) / tc);
+    pmb::unroll_local_kernel<<<dim3(col_blocks, static_cast<unsigned>(chunks)), tc, 0, st>>>(
+        reinterpret_cast<const float4 *>(x), w4, n_steps, n_cols, local, agg);
+    PMB_CUDA(cudaGetLastError());
+    pmb::unroll_chunks_kernel<<<col_blocks, tc, 0, st>>>(agg, chunks, n_cols);
+    PMB_CUDA(cudaGetLastError());
+    pmb::unroll_apply_kernel<<<ew_grid(n_steps * n_cols, 256, dp), 256, 0, st>>>(
+        reinterpret_cast<const float4 *>(x), w4, n_steps, n_cols, local, agg, reinterpret_cast<float4 *>(out));
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+int pmb_dq_is_unit_f32(const float *dq, float atol, int64_t n, int32_t *flags3, void *stream) {
+    if (!flags3) return fail(PMB_ERR_NULL, "%s: flags3 is NULL", __func__);
+    PMB_CUDA(cudaMemsetAsync(flags3, 0, 3 * sizeof(int32_t), static_cast<cudaStream_t>(stream)));
+    PMB_EW_PROLOGUE(n, dq);
+    PMB_NEED16(dq);
+    pmb::dq_is_unit_kernel<<<grid_, 256, 0, st_>>>((const float4 *)dq, atol, flags3, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_dq_normalize_f32(const float *dq, float *out, int64_t n, int32_t *flags3, void *stream) {
+    if (!flags3) return fail(PMB_ERR_NULL, "%s: flags3 is NULL", __func__);
+    PMB_CUDA(cudaMemsetAsync(flags3, 0, 3 * sizeof(int32_t), static_cast<cudaStream_t>(stream)));
+    PMB_EW_PROLOGUE(n, dq, out);
+    PMB_NEED16(dq); PMB_NEED16(out);
+    pmb::dq_normalize_scale_kernel<<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
+    PMB_CUDA(cudaGetLastError());
+    pmb::dq_normalize_ortho_kernel<<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// ---- fk consumers: from_root_positions, mirror (ik_kernels.cuh) ------------------------------
+int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_host, const float *offsets,
+                                int64_t n_frames, int32_t n_joints, float *rotations, void *stream) {
+    if (!positions || !offsets || !rotations) return fail(PMB_ERR_NULL, "from_root_positions: NULL array pointer");
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
+    PMB_NEED16(rotations);
+    pmb::JointProgram prog;
+    int n_slots = 0;
+    int rc = check_program(parents_host, n_joints, false, prog, n_slots);
+    if (rc) return rc;
+    if (n_frames == 0) return PMB_OK;
+    // children in index order, like the reference's `children` lists (skeleton.py:122-126)
+    pmb::ChildTable kids;
+    {
+        int count[PMB_MAX_JOINTS + 1] = {0};
+        for (int i = 1; i < n_joints; ++i) ++count[parents_host[i]];
+        kids.start[0] = 0;
+        for (int j = 0; j < n_joints; ++j) kids.start[j + 1] = static_cast<uint16_t>(kids.start[j] + count[j]);
+        int fill[PMB_MAX_JOINTS] = {0};
+        for (int i = 1; i < n_joints; ++i) {
+            const int p = static_cast<int>(parents_host[i]);
+            kids.child[kids.start[p] + fill[p]++] = static_cast<uint16_t>(i);
+        }
+    }
+    DeviceProps dp;
+    if ((rc = device_props(dp))) return rc;
+    constexpr int THREADS = 128;
+    const int smem = n_joints * 16 + n_slots * THREADS * 16;
+    if (smem > dp.smem_optin)
+        return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", n_slots);
+    auto kernel = pmb::from_root_positions_kernel<THREADS>;
+    if ((rc = set_smem(kernel, smem))) return rc;
+    const long long blocks = (n_frames + THREADS - 1) / THREADS;
+    if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
+    kernel<<<static_cast<unsigned>(blocks), THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        positions, offsets, reinterpret_cast<float4 *>(rotations), n_frames, n_joints, n_slots, prog, kids);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+int pmb_mirror_to_local_f32(const float *global_quats, const int64_t *parents_host, const int64_t *joints_mapping_host,
+                            int32_t mirror_axis, int64_t n_frames, int32_t n_joints, float *local_quats, void *stream) {
+    if (!global_quats || !local_quats) return fail(PMB_ERR_NULL, "mirror_to_local: NULL array pointer");
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
+    if (mirror_axis < 0 || mirror_axis > 2) return fail(PMB_ERR_SHAPE, "mirror_axis must be 0 (X), 1 (Y) or 2 (Z)");
+    PMB_NEED16(global_quats); PMB_NEED16(local_quats);
+    pmb::JointProgram prog;
+    int n_slots = 0;
+    int rc = check_program(parents_host, n_joints, false, prog, n_slots);
+    if (rc) return rc;
+    pmb::JointMap jm;
+    for (int j = 0; j < n_joints; ++j) {
+        const int64_t m = joints_mapping_host ? joints_mapping_host[j] : j;
+        if (m < 0 || m >= n_joints) return fail(PMB_ERR_SHAPE, "joints_mapping[%d] = %lld outside [0, %d)", j, static_cast<long long>(m), n_joints);
+        jm.map[j] = static_cast<uint16_t>(m);
+    }
+    if (n_frames == 0) return PMB_OK;
+    constexpr int THREADS = 256;
+    const int fb = tile_frames(n_joints, 4096);
+    const long long blocks = (n_frames + fb - 1) / fb;
+    if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
+    const uint32_t magic = static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(n_joints)) + 1u;
+    // the two vector components that change sign (skeleton.py:307-315): X -> (y, z), Y -> (x, z), Z -> (x, y)
+    const float fx = mirror_axis == 0 ? 1.f : -1.f, fy = mirror_axis == 1 ? 1.f : -1.f, fz = mirror_axis == 2 ? 1.f : -1.f;
+    pmb::mirror_to_local_kernel<THREADS><<<static_cast<unsigned>(blocks), THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4 *>(global_quats), reinterpret_cast<float4 *>(local_quats), n_frames, n_joints, fb,
+        magic, fx, fy, fz, prog, jm);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+int pmb_vec_mirror_f32(const float *v, int32_t axis, float *out, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, v, out);
+    if (axis < 0 || axis > 2) return fail(PMB_ERR_SHAPE, "%s: axis must be 0, 1 or 2", __func__);
+    pmb::vec_mirror_kernel<<<ew_grid(3 * n, 256, dp_), 256, 0, st_>>>(v, out, axis, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+int pmb_root_center_f32(const float *positions, float *out, int64_t n_frames, int32_t n_joints, void *stream) {
+    if (n_joints < 1) return fail(PMB_ERR_SHAPE, "%s: n_joints < 1", __func__);
+    PMB_EW_PROLOGUE(n_frames, positions, out);
+    pmb::root_center_kernel<<<ew_grid(n_frames * n_joints * 3, 256, dp_), 256, 0, st_>>>(positions, out, n_frames, n_joints);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }

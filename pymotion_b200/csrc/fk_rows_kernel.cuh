@@ -28,6 +28,18 @@
 #include "common.cuh"
 #include "tma.cuh"
 
+// Build-time variants of the walk (measured on B200): chunk-wide hoisting of the normalisation
+// scales, one-joint-early fetch of parent rows, and the algebraic form of the row rotation.
+#ifndef PMB_ROWS_HOIST
+#define PMB_ROWS_HOIST 0
+#endif
+#ifndef PMB_ROWS_PREFETCH
+#define PMB_ROWS_PREFETCH 0
+#endif
+#ifndef PMB_ROWS_FORM
+#define PMB_ROWS_FORM 0
+#endif
+
 namespace pmb {
 
 constexpr int kRowThreads = 160;
@@ -164,12 +176,13 @@ __device__ __forceinline__ void fk_row_walk(const RowCtx &cx) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(cx.empty0 + 8 * buf);
-            // The eight normalisation scales of the chunk: independent MUFU chains, issued together ahead of the
-            // dependent walk -- and ahead of the block boundary below, which keeps ptxas from sinking them back into it (joints past the end of the skeleton are zero-filled by the TMA unit: finite, unused).
+#if PMB_ROWS_HOIST
+            // The eight normalisation scales of the chunk ahead of the walk (and of the block boundary below,
+            // which keeps ptxas from sinking them back into it).
             float sc[C];
 #pragma unroll
             for (int jj = 0; jj < C; ++jj) sc[jj] = rot_scale(q[jj], 1e-8f);
-
+#endif
             if (c0 == 0) {
                 const long long next_tile = tile + cx.tile_stride;
                 if (next_tile < cx.n_tiles)
@@ -178,34 +191,59 @@ __device__ __forceinline__ void fk_row_walk(const RowCtx &cx) {
             }
 
             // Branch-free walk over the chunk.  Joints past the end of the skeleton (partial last chunk) are
-            // zero quaternions with padded table entries: identity steps whose stores are predicated off.
-            // A parent row that has to come from the stage is fetched ONE JOINT EARLY into (t0, t1, t2, tp):
-            // such a parent is at most joint j - 2, so its row is already in the stage when joint j - 1 starts,
-            // and the shared-memory latency hides behind that joint's arithmetic.
+            // zero quaternions (TMA fill) with padded table entries: identity steps whose stores are predicated off.
             float4 e = cx.tab[c0];
+#if PMB_ROWS_PREFETCH
+            // A parent row that has to come from the stage is fetched ONE JOINT EARLY into (t0, t1, t2, tp): such a
+            // parent is at most joint j - 2, so its row is already in the stage when joint j - 1 starts.
             float t0 = 0.f, t1 = 0.f, t2 = 0.f, tp = 0.f;
             {
                 const int p = __float_as_int(e.w);
                 load_parent_row_if(p, rrow + 36 * p, prow + 12 * p, t0, t1, t2, tp);
             }
+#endif
 #pragma unroll
             for (int jj = 0; jj < C; ++jj) {
                 const int j = c0 + jj;
                 const float4 e_next = cx.tab[j + 1];  // one joint ahead (the table is padded by a chunk)
+#if PMB_ROWS_PREFETCH
                 if (__float_as_int(e.w) >= 0) r0 = t0, r1 = t1, r2 = t2, pp = tp;  // selects, not a branch
                 if (jj + 1 < C) {
-                    const int pn = __float_as_int(e_next.w);  // parent of joint j + 1 if it lives in the stage, else -1
+                    const int pn = __float_as_int(e_next.w);
                     load_parent_row_if(pn, rrow + 36 * pn, prow + 12 * pn, t0, t1, t2, tp);
                 }
+#else
+                const int p = __float_as_int(e.w);    // parent whose row must come from the stage, or -1
+                load_parent_row_if(p, rrow + 36 * p, prow + 12 * p, r0, r1, r2, pp);
+#endif
+#if PMB_ROWS_HOIST
+                const float s = sc[jj];
+#else
+                const float s = rot_scale(q[jj], 1e-8f);
+#endif
+                const float w = q[jj].x, x = q[jj].y, y = q[jj].z, z = q[jj].w;
+                pp = r0 * e.x + r1 * e.y + r2 * e.z + pp;  // p[A] = parent row . offset + parent p[A]
+#if PMB_ROWS_FORM == 2
+                // experiment: no arithmetic at all (data-movement ceiling of the kernel structure)
+                r0 = x + s, r1 = y, r2 = z + w;
+#elif PMB_ROWS_FORM == 0
                 // row' = row * R(q^) = the row rotated by the conjugate of q^:
                 //   c = row x v,  row' = row + s (w c + c x v),  s = 2 / (|q| + eps)^2, q = (w, v) as loaded
-                const float w = q[jj].x, x = q[jj].y, y = q[jj].z, z = q[jj].w;
                 const float cx_ = r1 * z - r2 * y, cy_ = r2 * x - r0 * z, cz_ = r0 * y - r1 * x;
                 const float ex = w * cx_ + (cy_ * z - cz_ * y);
                 const float ey = w * cy_ + (cz_ * x - cx_ * z);
                 const float ez = w * cz_ + (cx_ * y - cy_ * x);
-                pp = r0 * e.x + r1 * e.y + r2 * e.z + pp;  // p[A] = parent row . offset + parent p[A]
-                r0 = sc[jj] * ex + r0, r1 = sc[jj] * ey + r1, r2 = sc[jj] * ez + r2;
+                r0 = s * ex + r0, r1 = s * ey + r1, r2 = s * ez + r2;
+#else
+                // the same rotation with (row x v) x v = v (row . v) - row |v|^2 expanded: the part that depends on
+                // the row is 4 operations deep instead of 7,
+                //   row' = a row + row x b + (row . v) d,   a = 1 - s |v|^2,  b = s w v,  d = s v
+                const float a_ = 1.f - s * (x * x + y * y + z * z), sw = s * w;
+                const float bx = sw * x, by = sw * y, bz = sw * z, dx = s * x, dy = s * y, dz = s * z;
+                const float kd = r0 * x + r1 * y + r2 * z;
+                const float n0 = a_ * r0 + (r1 * bz - r2 * by), n1 = a_ * r1 + (r2 * bx - r0 * bz), n2 = a_ * r2 + (r0 * by - r1 * bx);
+                r0 = kd * dx + n0, r1 = kd * dy + n1, r2 = kd * dz + n2;
+#endif
                 // word 9j + 3A of an even-stride row is 8-byte aligned iff j + A is even (j and jj have the same
                 // parity: chunks start at multiples of 8); constant after unrolling
                 if (((jj + A) & 1) == 0) store_row_if<VEC, true>(cnt - jj, rrow + 36 * j, prow + 12 * j, r0, r1, r2, pp);

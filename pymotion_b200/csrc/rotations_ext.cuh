@@ -104,7 +104,7 @@ __global__ void quat_to_angle_axis_kernel(const float4 *q, float *angle, float *
     PMB_GRID_STRIDE(i, n) {
         const Quat<float> a = ldq(q, i);
         const float ang = 2.f * acosf(fminf(fmaxf(a.w, -1.f), 1.f));
-        const float s = sqrtf(fminf(fmaxf(1.f - a.w * a.w, 0.f), 1.f));
+        const float s = sqrtf(fminf(fmaxf(__fsub_rn(1.f, __fmul_rn(a.w, a.w)), 0.f), 1.f));  // two roundings, like NumPy: 1 - w*w is ill-conditioned near |w| = 1
         Vec3<float> ax{0.f, 0.f, 0.f};
         if (s > 1e-8f) ax = {a.x / s, a.y / s, a.z / s};
         if (scaled) {
@@ -137,39 +137,45 @@ __global__ void quat_slerp_kernel(const float4 *q0, const float4 *q1, const floa
     }
 }
 
-// quat.py:504-576 (axis == nullptr) and :579-650 (fixed rotation axis)
+// quat.py:504-576: rotation taking direction v1 onto v2 (half-angle quaternion about normalize(v1 x v2));
+// identity where np.isclose(dot, 1); where np.isclose(dot, -1) a half turn about normalize(v1 x e), e = y if
+// v1 lies along x, else x (:552-562).
+__device__ __forceinline__ Quat<float> q_from_to(Vec3<float> a, Vec3<float> b, bool normalize_input) {
+    if (normalize_input) a = v_normalize(a, 1e-8f), b = v_normalize(b, 1e-8f);
+    const Vec3<float> cr = cross3(a, b);
+    const float dot = dot3_np(a, b);
+    const float w = sqrtf((1.f + dot) * 0.5f), s = sqrtf((1.f - dot) * 0.5f);
+    const Vec3<float> u = v_normalize(cr, 1e-8f);
+    Quat<float> r{w, u.x * s, u.y * s, u.z * s};
+    if (np_isclose(dot, 1.f)) r = {1.f, 0.f, 0.f, 0.f};
+    if (np_isclose(dot, -1.f)) {
+        const Vec3<float> e = np_isclose(fabsf(a.x), 1.f) ? Vec3<float>{0.f, 1.f, 0.f} : Vec3<float>{1.f, 0.f, 0.f};
+        const Vec3<float> h = v_normalize(cross3(a, e), 1e-8f);
+        r = {0.f, h.x, h.y, h.z};
+    }
+    return r;
+}
+// quat.py:579-650: the same half angle about the GIVEN axis u, signed by sign((v1 x v2) . u); identity where
+// np.isclose(dot, 1); (0, u) where np.isclose(dot, -1).
+__device__ __forceinline__ Quat<float> q_from_to_axis(Vec3<float> a, Vec3<float> b, const Vec3<float> &u, bool normalize_input) {
+    if (normalize_input) a = v_normalize(a, 1e-8f), b = v_normalize(b, 1e-8f);
+    const Vec3<float> cr = cross3(a, b);
+    const float dot = dot3_np(a, b);
+    const float w = sqrtf((1.f + dot) * 0.5f);
+    float s = sqrtf((1.f - dot) * 0.5f);
+    const float side = dot3_np(cr, u);
+    s *= side > 0.f ? 1.f : (side < 0.f ? -1.f : side);  // np.sign (keeps 0 and nan)
+    Quat<float> r{w, u.x * s, u.y * s, u.z * s};
+    if (np_isclose(dot, 1.f)) r = {1.f, 0.f, 0.f, 0.f};
+    if (np_isclose(dot, -1.f)) r = {0.f, u.x, u.y, u.z};
+    return r;
+}
 __global__ void quat_from_to_kernel(const float *v1, const float *v2, const float *axis, int normalize_input, float4 *o,
                                     long long n) {
     PMB_GRID_STRIDE(i, n) {
-        Vec3<float> a = ldv(v1, i), b = ldv(v2, i);
-        if (normalize_input) a = v_normalize(a, 1e-8f), b = v_normalize(b, 1e-8f);
-        const Vec3<float> cr = cross3(a, b);
-        const float dot = dot3_np(a, b);
-        const float w = sqrtf((1.f + dot) * 0.5f);
-        float s = sqrtf((1.f - dot) * 0.5f);
-        Quat<float> r;
-        if (axis == nullptr) {
-            const Vec3<float> u = v_normalize(cr, 1e-8f);
-            r = {w, u.x * s, u.y * s, u.z * s};
-        } else {
-            const Vec3<float> u = ldv(axis, i);
-            const float side = dot3_np(cr, u);
-            s *= side > 0.f ? 1.f : (side < 0.f ? -1.f : side);  // np.sign (keeps 0 and nan)
-            r = {w, u.x * s, u.y * s, u.z * s};
-        }
-        if (np_isclose(dot, 1.f)) r = {1.f, 0.f, 0.f, 0.f};
-        if (np_isclose(dot, -1.f)) {
-            if (axis == nullptr) {
-                // half turn about normalize(v1 x e), e = y if v1 lies along x, else x (:552-562)
-                const Vec3<float> e = np_isclose(fabsf(a.x), 1.f) ? Vec3<float>{0.f, 1.f, 0.f} : Vec3<float>{1.f, 0.f, 0.f};
-                const Vec3<float> u = v_normalize(cross3(a, e), 1e-8f);
-                r = {0.f, u.x, u.y, u.z};
-            } else {
-                const Vec3<float> u = ldv(axis, i);
-                r = {0.f, u.x, u.y, u.z};
-            }
-        }
-        stq(o, i, r);
+        const Vec3<float> a = ldv(v1, i), b = ldv(v2, i);
+        stq(o, i, axis == nullptr ? q_from_to(a, b, normalize_input != 0)
+                                  : q_from_to_axis(a, b, ldv(axis, i), normalize_input != 0));
     }
 }
 

@@ -1,7 +1,8 @@
 """Skeleton ops: drop-in for ``pymotion.ops.skeleton`` / ``skeleton_torch`` on the
 path BASELINE.json names -- ``fk``, ``to_root_dual_quat``, ``from_root_dual_quat``
 (plus ``from_global_rotations``, the step that follows ``fk`` in every in-repo
-caller of the reference).
+caller of the reference, and those callers themselves: ``from_root_positions`` and
+``mirror``).
 
 Same names, positional order and return order as the reference
 (/root/reference/pymotion/ops/skeleton.py:16, :207, :173, :64).  Each call is one
@@ -177,6 +178,132 @@ def from_global_rotations(global_quats, parents):
         rt.call("pmb_from_global_rotations_f32", m.device, rt.ptr(g), par.ctypes.data, _lead_frames(lead), n_joints,
                 rt.ptr(out), m.stream())
     return m.out(out)
+
+
+def from_root_positions(positions, parents, offsets):
+    """Root-centred joint positions -> local rotations (reference: ops/skeleton.py:96-170): every joint
+    with children is rotated so that its first child's rest direction points at the predicted child
+    (``quat.from_to``), further children fix the roll about that direction (``quat.from_to_axis``).
+    The reference re-runs ``fk`` before every alignment (O(J) passes); here one kernel walks the tree
+    once per frame.  positions [n_frames, n_joints, 3], offsets [n_joints, 3] -> [n_frames, n_joints, 4]
+    (float32; the reference returns float64)."""
+    m = rt.Marshal(positions, offsets)
+    p = m.dev(positions)
+    if p.dim() != 3 or p.shape[-1] != 3:
+        raise ValueError(f"positions must have shape [n_frames, n_joints, 3], got {tuple(p.shape)}")
+    p = p.contiguous()
+    n_frames, n_joints = int(p.shape[0]), int(p.shape[1])
+    par = rt.host_parents(parents)
+    if par.shape[0] != n_joints:
+        raise ValueError(f"parents has {par.shape[0]} entries but positions has {n_joints} joints")
+    off = m.dev(offsets)
+    if tuple(off.shape) != (n_joints, 3):
+        raise ValueError(f"offsets must have shape [{n_joints}, 3], got {tuple(off.shape)}")
+    off = off.contiguous()
+    out = m.new((n_frames, n_joints, 4))
+    if n_frames > 0:
+        rt.call("pmb_from_root_positions_f32", m.device, rt.ptr(p), par.ctypes.data, rt.ptr(off), n_frames, n_joints,
+                rt.ptr(out), m.stream())
+    return m.out(out)
+
+
+_MIRROR_AXES = {"X": 0, "Y": 1, "Z": 2}
+
+
+def _vec_mirror(m: rt.Marshal, v, axis_index: int):
+    """Copy of ``v [..., 3]`` with one component negated (device kernel; None passes through)."""
+    if v is None:
+        return None
+    t = m.dev(v).contiguous()
+    if t.shape[-1] != 3:
+        raise ValueError(f"expected [..., 3], got {tuple(t.shape)}")
+    out = m.new(t.shape)
+    n = t.numel() // 3
+    if n > 0:
+        rt.call("pmb_vec_mirror_f32", m.device, rt.ptr(t), axis_index, rt.ptr(out), n, m.stream())
+    return out
+
+
+def _mirrored_local(m: rt.Marshal, q, offsets_dev, par, mapping, axis_index: int):
+    """fk -> global quaternions -> (re-index, flip two components) -> local rotations
+    (ops/skeleton.py:322-331, :410-416)."""
+    lead, n_joints = tuple(q.shape[:-2]), int(q.shape[-2])
+    n_frames = _lead_frames(lead)
+    zero = torch.zeros(3, device=m.device, dtype=torch.float32)  # np.zeros_like(global_translation): root at the origin
+    pos = m.new(lead + (n_joints, 3))
+    grot = m.new(lead + (n_joints, 4))
+    local = m.new(lead + (n_joints, 4))
+    if n_frames > 0:
+        rt.call("pmb_fk_quat_f32", m.device, rt.ptr(q), rt.ptr(zero), 0, rt.ptr(offsets_dev), 0, par.ctypes.data,
+                n_frames, n_joints, rt.ptr(pos), rt.ptr(grot), m.stream())
+        rt.call("pmb_mirror_to_local_f32", m.device, rt.ptr(grot), par.ctypes.data,
+                None if mapping is None else mapping.ctypes.data, axis_index, n_frames, n_joints, rt.ptr(local),
+                m.stream())
+    return local
+
+
+def mirror(local_rotations, global_translation, parents, offsets, end_sites=None, joints_mapping=None,
+           mode: str = "all", axis: str = "X"):
+    """Mirror a motion along ``axis`` (reference: ops/skeleton.py:247-344, :347-418).
+
+    mode 'all'        exact mirror, offsets (and end sites) mirrored with it (``_true_mirror``);
+    mode 'symmetry'   joints swapped by ``joints_mapping``, skeleton unchanged;
+    mode 'positions'  mirrored pose re-targeted onto the ORIGINAL skeleton through ``from_root_positions``.
+
+    Returns ``(local_rotations, global_translation, offsets, end_sites)`` like the reference.  Inputs are
+    never modified (the NumPy reference negates ``global_translation`` in place in 'symmetry' mode)."""
+    if mode not in ("all", "symmetry", "positions"):
+        raise ValueError("Invalid mode. Choose 'symmetry', 'all', or 'positions'")
+    if axis not in _MIRROR_AXES:
+        raise ValueError("Invalid axis. Choose 'X', 'Y', or 'Z'")
+    ax = _MIRROR_AXES[axis]
+    m = rt.Marshal(local_rotations, global_translation, offsets)
+    q = m.dev(local_rotations)
+    if q.dim() < 2 or q.shape[-1] != 4:
+        raise ValueError(f"local_rotations must have shape [..., n_joints, 4], got {tuple(q.shape)}")
+    q = q.contiguous()
+    n_joints = int(q.shape[-2])
+    par = rt.host_parents(parents)
+    if par.shape[0] != n_joints:
+        raise ValueError(f"parents has {par.shape[0]} entries but local_rotations has {n_joints} joints")
+    off = m.dev(offsets)
+    if tuple(off.shape) != (n_joints, 3):
+        raise ValueError(f"offsets must have shape [{n_joints}, 3], got {tuple(off.shape)}")
+    off = off.contiguous()
+    gt_mirrored = _vec_mirror(m, global_translation, ax)
+
+    if mode == "symmetry":
+        if joints_mapping is None:
+            raise ValueError("joints_mapping must be provided for mode 'symmetry'")
+        mapping = rt.host_parents(joints_mapping)
+        if mapping.shape[0] != n_joints:
+            raise ValueError("joints_mapping must have the same length as the number of joints")
+        local = _mirrored_local(m, q, off, par, mapping, ax)
+        return m.out(local), m.out(gt_mirrored), offsets, end_sites
+
+    off_mirrored = _vec_mirror(m, off, ax)
+    ends_mirrored = _vec_mirror(m, end_sites, ax)
+    local = _mirrored_local(m, q, off_mirrored, par, None, ax)
+    if mode == "all":
+        return (m.out(local), m.out(gt_mirrored), m.out(off_mirrored),
+                None if ends_mirrored is None else m.out(ends_mirrored))
+
+    # 'positions' (:333-340): pose of the mirrored skeleton, root-centred, re-targeted onto the original offsets
+    if q.dim() != 3:
+        raise ValueError("mode 'positions' needs local_rotations of shape [n_frames, n_joints, 4]")
+    n_frames = int(q.shape[0])
+    gt, g_stride = _broadcast_rows(m, gt_mirrored, (n_frames,), (3,))
+    pos = m.new((n_frames, n_joints, 3))
+    rotm = m.new((n_frames, n_joints, 3, 3))
+    centred = m.new((n_frames, n_joints, 3))
+    rots = m.new((n_frames, n_joints, 4))
+    if n_frames > 0:
+        rt.call("pmb_fk_f32", m.device, rt.ptr(local), rt.ptr(gt), g_stride, rt.ptr(off_mirrored), 0, par.ctypes.data,
+                n_frames, n_joints, rt.ptr(pos), rt.ptr(rotm), m.stream())
+        rt.call("pmb_root_center_f32", m.device, rt.ptr(pos), rt.ptr(centred), n_frames, n_joints, m.stream())
+        rt.call("pmb_from_root_positions_f32", m.device, rt.ptr(centred), par.ctypes.data, rt.ptr(off), n_frames,
+                n_joints, rt.ptr(rots), m.stream())
+    return m.out(rots), m.out(gt_mirrored), offsets, end_sites
 
 
 def fk_host(rot, global_pos, offsets, parents, out=None, chunk_frames: int = 0):

@@ -37,7 +37,13 @@ DEEP65 = (
     + [27, 30, 33, 36, 39, 42, 45, 48, 51, 54]
 )
 
-TOPOLOGIES = {"body22": BODY22, "smplh52": SMPLH52, "deep65": DEEP65, "chain3": [0, 0, 1]}
+# Mid-size skeletons used to calibrate the launch heuristics between the bench sizes: the SMPL body with one
+# joint per finger (32 joints) and with three 3-joint fingers per hand (40 joints).
+BODY32 = _SMPL_BODY22 + [20] * 5 + [21] * 5
+BODY40 = _SMPL_BODY22 + _hand(20, 22)[:9] + _hand(21, 31)[:9]
+
+TOPOLOGIES = {"body22": BODY22, "smplh52": SMPLH52, "deep65": DEEP65, "chain3": [0, 0, 1], "body32": BODY32,
+              "body40": BODY40}
 
 
 def parents_of(name: str) -> np.ndarray:

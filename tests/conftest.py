@@ -33,3 +33,8 @@ def golden_quat():
 @pytest.fixture(scope="session")
 def golden_quat_ext():
     return dict(np.load(os.path.join(GOLDEN, "quat_ext.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_ik():
+    return dict(np.load(os.path.join(GOLDEN, "ik.npz")))

@@ -44,7 +44,7 @@ WORKLOADS = {
     "fk_2m_x_40": ("body40", 2_000_000),
 }
 # --kernel-only development workloads for the other ops of the path (BASELINE.json configs[2])
-DEV_OPS = ("fk", "to_dq", "from_dq", "round_trip", "fk_quat")
+DEV_OPS = ("fk", "to_dq", "from_dq", "round_trip", "fk_quat", "from_root_positions", "mirror_all")
 
 
 def fk_bytes_per_pose(n_joints: int) -> int:
@@ -53,7 +53,10 @@ def fk_bytes_per_pose(n_joints: int) -> int:
 
 def op_bytes_per_pose(op: str, n_joints: int) -> int:
     return {"fk": 64 * n_joints + 12, "to_dq": 48 * n_joints + 12, "from_dq": 60 * n_joints,
-            "round_trip": 108 * n_joints + 12, "fk_quat": 44 * n_joints + 12}[op]
+            "round_trip": 108 * n_joints + 12, "fk_quat": 44 * n_joints + 12,
+            # 8f rank 2 ops: positions in, rotations out; mirror = rotations in, rotations out (its two kernels
+            # move 76 J + 12: the fk_quat positions and the global quaternions in between are not algorithmic)
+            "from_root_positions": 28 * n_joints, "mirror_all": 32 * n_joints}[op]
 
 
 def measured_peak():
@@ -247,6 +250,9 @@ def run_ours(args):
                                   n_joints, pos.data_ptr(), rotm.data_ptr(), stream.cuda_stream))
 
     if args.kernel_only and args.op != "fk":
+        if args.op == "from_root_positions":
+            step()  # needs `rotm` alive for this one launch
+            torch.cuda.synchronize(dev)
         del rotm
         dq = torch.empty((frames, n_joints, 8), device=dev, dtype=torch.float32)
         rots = torch.empty((frames, n_joints, 4), device=dev, dtype=torch.float32)
@@ -265,9 +271,18 @@ def run_ours(args):
             _lib.check(lib.pmb_fk_quat_f32(rot.data_ptr(), gpos.data_ptr(), 3, off.data_ptr(), 0, par.ctypes.data, frames,
                                            n_joints, pos.data_ptr(), rots.data_ptr(), st))
 
+        def from_root_positions():
+            _lib.check(lib.pmb_from_root_positions_f32(pos.data_ptr(), par.ctypes.data, off.data_ptr(), frames, n_joints,
+                                                       rots.data_ptr(), st))
+
+        def mirror_all():  # device part of mirror(mode="all"): fk_quat -> flip -> local
+            fk_quat()
+            _lib.check(lib.pmb_mirror_to_local_f32(rots.data_ptr(), par.ctypes.data, None, 0, frames, n_joints,
+                                                   dq.data_ptr(), st))
+
         to_dq()
-        step = {"to_dq": to_dq, "from_dq": from_dq, "fk_quat": fk_quat,
-                "round_trip": lambda: (to_dq(), from_dq())}[args.op]
+        step = {"to_dq": to_dq, "from_dq": from_dq, "fk_quat": fk_quat, "from_root_positions": from_root_positions,
+                "mirror_all": mirror_all, "round_trip": lambda: (to_dq(), from_dq())}[args.op]
 
     def barrier():
         if world > 1:
@@ -393,7 +408,7 @@ def run_ours(args):
                 "peak_source": peak_src,
                 "frac_of_nominal_8000": achieved / 8000.0,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
-                "kernel": "pmb::fk_chain_kernel",
+                "kernel": "pmb::" + lib.pmb_last_variant().decode(),
             },
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -15,6 +15,7 @@
 #include "dq_kernels.cuh"
 #include "elementwise.cuh"
 #include "fk_kernel.cuh"
+#include "fk_quat_kernel.cuh"
 #include "fk_rows_kernel.cuh"
 #include "ik_kernels.cuh"
 #include "joint_program.h"
@@ -216,6 +217,9 @@ inline int fk_rows_teams(int stages, const FkArgs &a, const DeviceProps &dp) {
 //                         branch slot (4M x 65, 10 slots: rows 4.45 TB/s vs 3.93), the row kernel does not have
 //                         slots but only two tiles in flight per SM (4M x 52, 3 slots: rows 4.54 vs 4.77);
 //   1 team:               never (nothing overlaps the drain of the stage).
+// And the joint count must keep the dense stage free of bank conflicts: lane = frame, so the 32 lanes of a store
+// are 9J words apart.  J odd: conflict free; J = 2 (mod 4): conflict free with the 64-bit stores; J = 0 (mod 4):
+// 4-way (J = 52: 4.5 TB/s) up to 32-way (J = 32: 0.84 TB/s, measured) -> thread-per-frame kernel with its padded stage.
 bool try_fk_rows(const FkArgs &a, const DeviceProps &dp, int &rc) {
     const int force = env_int("PMB_FK_ROWS", -1);
     if (force == 0) return false;
@@ -237,12 +241,50 @@ bool try_fk_rows(const FkArgs &a, const DeviceProps &dp, int &rc) {
         if (force == 1) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_ROWS=1: the row kernel does not fit (stages %d)", stages); return true; }
         return false;
     }
-    if (force != 1 && (teams < 2 || (teams == 2 && a.n_slots <= 4))) return false;
+    if (force != 1 && (teams < 2 || (teams == 2 && a.n_slots <= 4) || a.n_joints % 4 == 0)) return false;
     if (a.n_joints % 2 == 0)
         rc = stages == 2 ? launch_fk_rows_cfg<2, 2>(a, dp, team_cap) : stages == 3 ? launch_fk_rows_cfg<3, 2>(a, dp, team_cap) : launch_fk_rows_cfg<4, 2>(a, dp, team_cap);
     else
         rc = stages == 2 ? launch_fk_rows_cfg<2, 1>(a, dp, team_cap) : stages == 3 ? launch_fk_rows_cfg<3, 1>(a, dp, team_cap) : launch_fk_rows_cfg<4, 1>(a, dp, team_cap);
     return true;
+}
+
+// ---- fk_quat, quaternion-chain kernel (fk_quat_kernel.cuh) ------------------------------
+int launch_fk_quat_chain(const FkArgs &a, const DeviceProps &dp) {
+    constexpr int WARPS = 4;
+    // like to_root_dual_quat: the largest flush group that still lets TWO 4-warp blocks share an SM
+    const int budget = (dp.smem_optin - 2048) / 2;
+    int group = a.n_joints;
+    if (pmb::fkq_geom(group, WARPS, a.n_joints, a.n_slots).block_bytes > budget) {
+        group = ((a.n_joints + 7) / 8) * 8;
+        while (group > 8 && pmb::fkq_geom(group, WARPS, a.n_joints, a.n_slots).block_bytes > budget) group -= 8;
+    }
+    if (const char *env = getenv("PMB_FKQ_GROUP")) {
+        const int v = atoi(env);
+        if (v >= 8 && v % 8 == 0 && v < a.n_joints) group = v;
+    }
+    const int smem = pmb::fkq_geom(group, WARPS, a.n_joints, a.n_slots).block_bytes;
+    if (smem > dp.smem_optin)
+        return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
+    auto kernel = pmb::fk_quat_chain_kernel<WARPS>;
+    int rc = set_smem(kernel, smem);
+    if (rc) return rc;
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk))) return rc;
+    int per_sm = 0;
+    PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk_quat kernel does not fit on an SM");
+    per_sm = std::max(1, std::min(per_sm, env_int("PMB_FKQ_BLOCKS_PER_SM", per_sm)));
+    const long long tiles = (a.n_frames + 31) / 32;
+    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
+    auto magic_of = [](int d) { return static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(d)) + 1u; };
+    const int tail = a.n_joints % group ? a.n_joints % group : group;
+    note_variant("fk_quat_chain_kernel<WARPS=%d> group=%d grid=%lld smem=%d", WARPS, group, blocks, smem);
+    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(
+        tm, a.gpos, a.gstride, a.offsets, a.pos, reinterpret_cast<float4 *>(a.rout), a.n_frames, a.n_joints, a.n_slots,
+        group, magic_of(group), magic_of(tail), magic_of(3 * group), magic_of(3 * tail), *a.prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
 }
 
 inline bool fk_fits(int group, int vec, int rw, int warps, const FkArgs &a, const DeviceProps &dp) {
@@ -309,6 +351,7 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
         int rrc = PMB_OK;
         if (try_fk_rows(a, dp, rrc)) return rrc;
     }
+    if (ostride == 0 && quat_out && env_int("PMB_FKQ_MATRIX", 0) == 0) return launch_fk_quat_chain(a, dp);
     if (ostride == 0) return quat_out ? launch_fk<false, true>(a, dp) : launch_fk<false, false>(a, dp);
     return quat_out ? launch_fk<true, true>(a, dp) : launch_fk<true, false>(a, dp);
 }

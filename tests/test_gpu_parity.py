@@ -462,6 +462,29 @@ def test_fk_row_team_kernel(sk, monkeypatch, knobs, name, n_frames):
         assert_allclose(rotm, want_rotm, **TOL)
 
 
+@pytest.mark.parametrize("knobs", [{}, {"PMB_FKQ_GROUP": "8"}, {"PMB_FKQ_GROUP": "16"}, {"PMB_FKQ_GROUP": "24"},
+                                   {"PMB_FKQ_BLOCKS_PER_SM": "1"}, {"PMB_FKQ_MATRIX": "1"}])
+@pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 6_050), ("deep65", 5_031), ("chain3", 777),
+                                           ("body40", 2_049)])
+def test_fk_quat_every_variant(sk, monkeypatch, knobs, name, n_frames):
+    """fk_quat: the quaternion-chain kernel for every flush group (ragged frame counts: remainder tile and
+    remainder group), one block per SM (several tiles per warp), and the older matrix-path kernel.  Positions
+    at the hot-path tolerance; rotations equal to quat.from_matrix(fk rotmats) with the reference's sign
+    convention except where from_matrix's branch test is within rounding of a tie."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=11 * len(par) + n_frames)
+    want_pos, want_rotm = orc.fk(rot, gp, off, par)
+    want_q = orc.quat_from_matrix(want_rotm)
+    pos, grot = sk.fk_quat(rot, gp, off, par)
+    assert_allclose(pos, want_pos, **TOL)
+    dots = np.sum(grot * want_q, axis=-1)
+    assert_allclose(np.abs(dots), 1.0, atol=1e-5)
+    assert (dots > 0).mean() > 0.999
+    assert_allclose(np.linalg.norm(grot, axis=-1), 1.0, atol=1e-5)
+
+
 @pytest.mark.parametrize("group", [None, "8", "16", "24"])
 @pytest.mark.parametrize("name,n_frames", [("body22", 4099), ("smplh52", 2050), ("deep65", 1031), ("chain3", 777)])
 def test_to_root_dual_quat_every_group(sk, monkeypatch, group, name, n_frames):

@@ -305,6 +305,7 @@ def run_ours(args):
     sampler.windows.append((w0, time.perf_counter()))
     barrier()
     ms = ev0.elapsed_time(ev1)
+    variant = lib.pmb_last_variant().decode()  # what the timed launches actually ran
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -408,7 +409,7 @@ def run_ours(args):
                 "peak_source": peak_src,
                 "frac_of_nominal_8000": achieved / 8000.0,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
-                "kernel": "pmb::" + lib.pmb_last_variant().decode(),
+                "kernel": "pmb::" + variant,
             },
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -259,9 +259,17 @@ int launch_fk_quat_chain(const FkArgs &a, const DeviceProps &dp) {
         group = ((a.n_joints + 7) / 8) * 8;
         while (group > 8 && pmb::fkq_geom(group, WARPS, a.n_joints, a.n_slots).block_bytes > budget) group -= 8;
     }
+    // ... unless that leaves flushes of 8 joints (deep orderings with many live slots): measured at 4M x 65,
+    // one block per SM flushing 24 joints at a time beats two blocks flushing 8 (3.16 ms vs 3.87 ms)
+    if (group < 16 && a.n_joints > 16) {
+        int g1 = 24;
+        while (g1 > 8 && pmb::fkq_geom(g1, WARPS, a.n_joints, a.n_slots).block_bytes > dp.smem_optin) g1 -= 8;
+        if (g1 > group) group = g1;
+    }
     if (const char *env = getenv("PMB_FKQ_GROUP")) {
         const int v = atoi(env);
-        if (v >= 8 && v % 8 == 0 && v < a.n_joints) group = v;
+        if (v >= a.n_joints) group = a.n_joints;  // whole rows
+        else if (v >= 8 && v % 8 == 0) group = v;
     }
     const int smem = pmb::fkq_geom(group, WARPS, a.n_joints, a.n_slots).block_bytes;
     if (smem > dp.smem_optin)

@@ -140,7 +140,10 @@ fk_quat_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__
                     const int j = c0 + jj;
                     const uint32_t code = prog.code[j];  // constant bank, warp-uniform
                     const float4 e = tab[j];
-                    const Quat<float> r = q_normalize_fast(Quat<float>{q[jj].x, q[jj].y, q[jj].z, q[jj].w}, 1e-8f);
+                    // the reference turns q / (|q| + eps) into a MATRIX: the zero quaternion becomes the identity
+                    // (quat.py:293-315 with all products zero), so it has to here too
+                    Quat<float> r = q_normalize_fast(Quat<float>{q[jj].x, q[jj].y, q[jj].z, q[jj].w}, 1e-8f);
+                    if (r.w == 0.f && r.x == 0.f && r.y == 0.f && r.z == 0.f) r.w = 1.f;
                     if (jj == 0 && c0 == 0) {  // root: [R(q^_0) | global_pos] (skeleton.py:49), offsets[0] ignored
                         cr = r;
                     } else {
@@ -175,7 +178,8 @@ fk_quat_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__
                     float4 *g = grot + f0 * n_joints + g0;
 #pragma unroll 4
                     for (int i = lane; i < n4; i += kWarp) {
-                        const int r = static_cast<int>(__umulhi(static_cast<uint32_t>(i), magic));
+                        // (a remainder group of ONE joint has no 32-bit magic: 2^32 / 1 + 1 wraps)
+                        const int r = gj == 1 ? i : static_cast<int>(__umulhi(static_cast<uint32_t>(i), magic));
                         const int c = i - r * gj;
                         g[static_cast<long long>(r) * n_joints + c] = qstage[r * S4 + c];
                     }

@@ -60,8 +60,8 @@ def main():
 
         ref_pos = ref_out = None
         for ks in knob_sets:
-            for k in KNOBS:
-                os.environ.pop(k, None)
+            for k in [k for k in os.environ if k.startswith("PMB_") and k != "PMB_LIB_PATH"]:
+                os.environ.pop(k)
             for kv in ks:
                 if kv != "-":
                     k, v = kv.split("=")

@@ -42,6 +42,8 @@ WORKLOADS = {
     # launch-heuristic calibration sizes (not BASELINE configs)
     "fk_2m_x_32": ("body32", 2_000_000),
     "fk_2m_x_40": ("body40", 2_000_000),
+    "fk_2m_x_16": ("body16", 2_000_000),
+    "fk_2m_x_24": ("body24", 2_000_000),
 }
 # --kernel-only development workloads for the other ops of the path (BASELINE.json configs[2])
 DEV_OPS = ("fk", "to_dq", "from_dq", "round_trip", "fk_quat", "from_root_positions", "mirror_all")

@@ -17,6 +17,7 @@
 #include "fk_kernel.cuh"
 #include "fk_quat_kernel.cuh"
 #include "fk_rows_kernel.cuh"
+#include "fk_lanes_kernel.cuh"
 #include "ik_kernels.cuh"
 #include "joint_program.h"
 #include "rotations_ext.cuh"
@@ -122,13 +123,13 @@ int encode_fn(EncodeTiledFn &out) {
 
 // rot viewed as a 2-D float tensor [n_frames][4 * n_joints]; box = 32 frames x C joints, hardware swizzle
 // matched to the box row (64 B for C = 4, 128 B for C = 8) so thread-per-frame 16-byte reads are conflict free.
-int make_rot_map(CUtensorMap &tm, const float *rot, int64_t n_frames, int32_t n_joints, int chunk) {
+int make_rot_map(CUtensorMap &tm, const float *rot, int64_t n_frames, int32_t n_joints, int chunk, int box_frames = 32) {
     EncodeTiledFn enc;
     int rc = encode_fn(enc);
     if (rc) return rc;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(4) * n_joints, static_cast<cuuint64_t>(n_frames)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(16) * n_joints};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(4 * chunk), 32};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(4 * chunk), static_cast<cuuint32_t>(box_frames)};
     cuuint32_t estr[2] = {1, 1};
     const CUtensorMapSwizzle sw = chunk == 8 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(rot), dims, strides, box, estr,
@@ -208,18 +209,96 @@ inline int fk_rows_teams(int stages, const FkArgs &a, const DeviceProps &dp) {
     return std::min(12, (dp.smem_optin + 1024) / (bytes + 1024));
 }
 
-// Returns true and launches if the row-team kernel is the better choice (PMB_FK_ROWS = 0 / 1 forces).
-// Measured on B200: what matters is how many teams share an SM.
-//   >= 4 teams (J <= 30): rows win with the shallow ring and exactly 4 teams (1M x 22: 0.231 ms vs 0.2415 ms
-//                         for the thread-per-frame kernel; a 5th team or a deeper ring is slower);
-//   3 teams  (J <= 44):   rows, deepest ring that keeps the 3 teams;
-//   2 teams  (J <= 69):   a toss-up decided by the joint order: the thread-per-frame kernel pays for every live
-//                         branch slot (4M x 65, 10 slots: rows 4.45 TB/s vs 3.93), the row kernel does not have
-//                         slots but only two tiles in flight per SM (4M x 52, 3 slots: rows 4.54 vs 4.77);
-//   1 team:               never (nothing overlaps the drain of the stage).
-// And the joint count must keep the dense stage free of bank conflicts: lane = frame, so the 32 lanes of a store
-// are 9J words apart.  J odd: conflict free; J = 2 (mod 4): conflict free with the 64-bit stores; J = 0 (mod 4):
-// 4-way (J = 52: 4.5 TB/s) up to 32-way (J = 32: 0.84 TB/s, measured) -> thread-per-frame kernel with its padded stage.
+// ---- fk, lane = (frame, row) kernel (fk_lanes_kernel.cuh) ---------------------------------
+template <int FR, int WARPS>
+int launch_fk_lanes_cfg(const FkArgs &a, const DeviceProps &dp, int block_cap) {
+    auto kernel = pmb::fk_lanes_kernel<FR, WARPS>;
+    const int smem = pmb::fk_lanes_geom(FR, WARPS, a.n_joints).block_bytes;
+    if (smem > dp.smem_optin) return fail(PMB_ERR_SHAPE, "fk lane kernel: %d joints do not fit in shared memory", a.n_joints);
+    int rc = set_smem(kernel, smem);
+    if (rc) return rc;
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk, FR))) return rc;
+    const long long tiles = (a.n_frames + FR - 1) / FR;
+    int per_sm = 0;
+    PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk lane kernel does not fit on an SM (%d bytes of shared memory)", smem);
+    per_sm = std::max(1, std::min(per_sm, block_cap));
+    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
+    note_variant("fk_lanes_kernel<FR=%d,WARPS=%d> grid=%lld (%d warps/SM) smem=%d", FR, WARPS, blocks, per_sm * WARPS, smem);
+    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos, a.rout,
+                                                                        a.n_frames, a.n_joints, *a.prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// Worst-case number of lanes of one stage store that fall into the same shared-memory bank: lane = (frame, row)
+// puts the frames of a tile 9J words apart, so only (9J mod 32) matters.  1 = conflict free.
+inline int fk_lanes_bank_degree(int fr, int n_joints) {
+    int count[32] = {0}, worst = 0;
+    for (int f = 0; f < fr; ++f) worst = std::max(worst, ++count[(f * 9 * n_joints) & 31]);
+    return worst;
+}
+
+struct FkLanesPlan {
+    int fr = 0, warps = 0, frames_in_flight = 0;
+};
+// The tile size / block shape that keeps the most frames in flight per SM (what the throughput of the large
+// skeletons follows): FR = 10 needs an even joint count, blocks of 1, 2 or 4 warps.
+inline FkLanesPlan fk_lanes_plan(const FkArgs &a, const DeviceProps &dp) {
+    FkLanesPlan best;
+    for (int fr : {10, 8}) {
+        if (fr == 10 && a.n_joints % 2) continue;
+        for (int warps : {4, 2, 1}) {
+            const int bytes = pmb::fk_lanes_geom(fr, warps, a.n_joints).block_bytes;
+            if (bytes > dp.smem_optin) continue;
+            const int blocks = std::min(32, (dp.smem_optin + 1024) / (bytes + 1024));
+            const int warps_sm = std::min(blocks * warps, 12);  // measured at 22 joints: beyond 12 walking warps per SM it gets slower
+            const int fif = warps_sm * fr;
+            if (fif > best.frames_in_flight) best = {fr, warps, fif};
+        }
+    }
+    return best;
+}
+
+// PMB_FK_LANES = 0 / 1 forces; PMB_FK_FR = 8 | 10, PMB_FK_WARPS = 1 | 2 | 4 pick the shape.
+bool try_fk_lanes(const FkArgs &a, const DeviceProps &dp, int &rc, bool rows_preferred) {
+    const int force = env_int("PMB_FK_LANES", -1);
+    if (force == 0) return false;
+    if (force != 1 && (getenv("PMB_FK_GROUP") || getenv("PMB_FK_ROWS"))) return false;  // another kernel is being forced
+    FkLanesPlan plan = fk_lanes_plan(a, dp);
+    if (plan.fr == 0) {
+        if (force == 1) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_LANES=1: the lane kernel does not fit"); return true; }
+        return false;
+    }
+    int fr = env_int("PMB_FK_FR", plan.fr);
+    if (fr != 10 || a.n_joints % 2) fr = 8;  // the spans of 10 frames are 16-byte multiples only for an even joint count
+    const int warps = env_int("PMB_FK_WARPS", plan.warps);
+    if (force != 1) {
+        if (rows_preferred) return false;
+        // a dense stage whose frames collide in 4 or more banks (J = 16, 32, 48, 64, ...: measured 2.0 TB/s at
+        // J = 32) belongs to the thread-per-frame kernel with its padded stage
+        if (fk_lanes_bank_degree(fr, a.n_joints) >= 4) return false;
+    }
+    const int cap = env_int("PMB_FK_BLOCKS_PER_SM", std::max(1, 12 / std::max(1, warps)));
+    if (fr == 10) rc = warps == 1 ? launch_fk_lanes_cfg<10, 1>(a, dp, cap) : warps == 2 ? launch_fk_lanes_cfg<10, 2>(a, dp, cap) : launch_fk_lanes_cfg<10, 4>(a, dp, cap);
+    else rc = warps == 1 ? launch_fk_lanes_cfg<8, 1>(a, dp, cap) : warps == 2 ? launch_fk_lanes_cfg<8, 2>(a, dp, cap) : launch_fk_lanes_cfg<8, 4>(a, dp, cap);
+    return true;
+}
+
+// Which fk kernel (shared offsets, matrices out) -- measured on B200, DESIGN.md section 4:
+//   row-team kernel      skeletons small enough for >= 4 teams per SM (J <= 30) with J not a multiple of 4
+//                        (1M x 22: 0.2316 ms against 0.2415 ms thread-per-frame, 0.2326 ms lanes);
+//   lane kernel          everything larger (2M x 40: 5.6 TB/s against 5.15; 4M x 52: 5.0 against 4.76; 4M x 65:
+//                        4.4, as the row kernel, against 3.9), unless
+//   thread-per-frame     the dense stage of the lane kernel would put >= 4 frames in one bank (J = 16, 32, 48,
+//                        64, ...: 2.0 TB/s at J = 32 against 5.6), per-frame offsets, or a forced variant.
+// Bank conflicts of the row-team kernel (lane = frame, 32 lanes 9J words apart): J odd: none; J = 2 (mod 4):
+// none with its 64-bit stores; J = 0 (mod 4): 4-way (J = 52: 4.5 TB/s) up to 32-way (J = 32: 0.84 TB/s).
+bool fk_rows_preferred(const FkArgs &a, const DeviceProps &dp) {
+    return fk_rows_teams(2, a, dp) >= 4 && a.n_joints % 4 != 0;
+}
+
 bool try_fk_rows(const FkArgs &a, const DeviceProps &dp, int &rc) {
     const int force = env_int("PMB_FK_ROWS", -1);
     if (force == 0) return false;
@@ -241,7 +320,7 @@ bool try_fk_rows(const FkArgs &a, const DeviceProps &dp, int &rc) {
         if (force == 1) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_ROWS=1: the row kernel does not fit (stages %d)", stages); return true; }
         return false;
     }
-    if (force != 1 && (teams < 2 || (teams == 2 && a.n_slots <= 4) || a.n_joints % 4 == 0)) return false;
+    if (force != 1 && !fk_rows_preferred(a, dp)) return false;
     if (a.n_joints % 2 == 0)
         rc = stages == 2 ? launch_fk_rows_cfg<2, 2>(a, dp, team_cap) : stages == 3 ? launch_fk_rows_cfg<3, 2>(a, dp, team_cap) : launch_fk_rows_cfg<4, 2>(a, dp, team_cap);
     else
@@ -315,7 +394,10 @@ int launch_fk_group(const FkArgs &a, const DeviceProps &dp) {
     // Measured on B200: whole-row staging with 4 warps per SM is the fastest layout whenever it
     // fits (1M x 22: 0.242 ms; 5 warps 0.262, 3 warps 0.298); otherwise the largest flush group that keeps
     // 4 warps per block wins (4M x 52: G = 16 4.77 TB/s vs dense with 2 warps 3.2 TB/s).
-    if (want(0, 4)) return launch_fk_cfg<0, 4, VEC, PF, QO>(a, dp);
+    // (whole rows are bank-conflict free only for odd J or J = 2 mod 4; unless forced, other joint counts take a
+    // padded flush group)
+    const bool dense_ok = QO || force_group == 0 || a.n_joints % 4 != 0;
+    if (dense_ok && want(0, 4)) return launch_fk_cfg<0, 4, VEC, PF, QO>(a, dp);
     if constexpr (FULL) {
         if (force_warps == 5 && want(0, 5)) return launch_fk_cfg<0, 5, VEC, PF, QO>(a, dp);
         if (force_warps == 2 && want(0, 2)) return launch_fk_cfg<0, 2, VEC, PF, QO>(a, dp);
@@ -357,6 +439,8 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
              static_cast<cudaStream_t>(stream)};
     if (ostride == 0 && !quat_out) {
         int rrc = PMB_OK;
+        const bool rows_first = fk_rows_preferred(a, dp) && env_int("PMB_FK_ROWS", -1) != 0;
+        if (try_fk_lanes(a, dp, rrc, rows_first || env_int("PMB_FK_ROWS", -1) == 1)) return rrc;
         if (try_fk_rows(a, dp, rrc)) return rrc;
     }
     if (ostride == 0 && quat_out && env_int("PMB_FKQ_MATRIX", 0) == 0) return launch_fk_quat_chain(a, dp);
@@ -677,6 +761,7 @@ int pmb_quat_conjugate_f32(const float *q, float *out, int64_t n, void *stream) 
 int pmb_quat_to_matrix_f32(const float *q, float *out, int64_t n, void *stream) {
     PMB_EW_PROLOGUE(n, q, out);
     PMB_NEED16(q);
+    PMB_NEED16(out);
     pmb::quat_to_matrix_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, out, n);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
@@ -805,19 +890,15 @@ int pmb_unroll_f32(const float *x, int32_t width, int64_t n_steps, int64_t n_col
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t chunks = (n_steps + pmb::kUnrollChunk - 1) / pmb::kUnrollChunk;
-    if (chunks > 65535) {
-        // grid.y limit: 65535 chunks of 128 steps = 8.3 M steps per call
-        return fail(PMB_ERR_SHAPE, "%s: at most %lld steps along the unroll axis per call", __func__,
-                    static_cast<long long>(65535) * pmb::kUnrollChunk);
-    }
+    if (n_cols > 0x7FFFFFFFLL || (chunks * n_cols + 127) / 128 > 0x7FFFFFFFLL)
+        return fail(PMB_ERR_SHAPE, "%s: array too large for one launch", __func__);
     uint8_t *local = static_cast<uint8_t *>(workspace), *agg = local + n_steps * n_cols;
     const int w4 = width / 4;
-    const int tc = 128;
-    const unsigned col_blocks = static_cast<unsigned>((n_cols + tc - 1) / tc);
-    pmb::unroll_local_kernel<<<dim3(col_blocks, static_cast<unsigned>(chunks)), tc, 0, st>>>(
-        reinterpret_cast<const float4 *>(x), w4, n_steps, n_cols, local, agg);
+    const long long local_threads = chunks * n_cols;
+    pmb::unroll_local_kernel<<<static_cast<unsigned>((local_threads + 127) / 128), 128, 0, st>>>(
+        reinterpret_cast<const float4 *>(x), w4, n_steps, n_cols, chunks, local, agg);
     PMB_CUDA(cudaGetLastError());
-    pmb::unroll_chunks_kernel<<<col_blocks, tc, 0, st>>>(agg, chunks, n_cols);
+    pmb::unroll_chunks_kernel<<<static_cast<unsigned>(n_cols), 256, 0, st>>>(agg, chunks, n_cols);
     PMB_CUDA(cudaGetLastError());
     pmb::unroll_apply_kernel<<<ew_grid(n_steps * n_cols, 256, dp), 256, 0, st>>>(
         reinterpret_cast<const float4 *>(x), w4, n_steps, n_cols, local, agg, reinterpret_cast<float4 *>(out));
@@ -910,7 +991,7 @@ int pmb_mirror_to_local_f32(const float *global_quats, const int64_t *parents_ho
     const uint32_t magic = static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(n_joints)) + 1u;
     // the two vector components that change sign (skeleton.py:307-315): X -> (y, z), Y -> (x, z), Z -> (x, y)
     const float fx = mirror_axis == 0 ? 1.f : -1.f, fy = mirror_axis == 1 ? 1.f : -1.f, fz = mirror_axis == 2 ? 1.f : -1.f;
-    pmb::mirror_to_local_kernel<THREADS><<<static_cast<unsigned>(blocks), THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+    pmb::mirror_to_local_kernel<THREADS><<<static_cast<unsigned>(blocks), THREADS, (4 * n_joints + 15) & ~15, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4 *>(global_quats), reinterpret_cast<float4 *>(local_quats), n_frames, n_joints, fb,
         magic, fx, fy, fz, prog, jm);
     PMB_CUDA(cudaGetLastError());

@@ -45,12 +45,21 @@ __global__ void quat_normalize_kernel(const float4 *q, float eps, float4 *o, lon
 __global__ void quat_conjugate_kernel(const float4 *q, float4 *o, long long n) {
     PMB_GRID_STRIDE(i, n) stq(o, i, q_conj(ldq(q, i)));
 }
-__global__ void quat_to_matrix_kernel(const float4 *q, float *o, long long n) {
-    PMB_GRID_STRIDE(i, n) {
-        float m[9];
-        q_to_matrix(ldq(q, i), m);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) o[9 * i + k] = m[k];
+// 36-byte records: a block stages its 256 matrices (9216 contiguous bytes, 16-byte aligned since 256 * 36 is a
+// multiple of 16) in shared memory with a conflict-free odd stride of 9 words and writes them out as float4
+// (measured: scalar 36-byte-strided stores ran at 1.3 TB/s, 22M quaternions).
+__global__ void __launch_bounds__(256) quat_to_matrix_kernel(const float4 *q, float *o, long long n) {
+    __shared__ __align__(16) float stage[256 * 9];
+    const long long n_tiles = (n + 255) / 256;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long base = tile * 256, i = base + threadIdx.x;
+        if (i < n) q_to_matrix(ldq(q, i), stage + 9 * threadIdx.x);
+        __syncthreads();
+        const int cnt = static_cast<int>(min(256LL, n - base)) * 9;  // floats in this tile
+        float *out = o + base * 9;
+        for (int k = threadIdx.x; k < cnt / 4; k += 256) __stcs(reinterpret_cast<float4 *>(out) + k, reinterpret_cast<const float4 *>(stage)[k]);
+        for (int k = (cnt & ~3) + threadIdx.x; k < cnt; k += 256) out[k] = stage[k];
+        __syncthreads();
     }
 }
 __global__ void quat_from_matrix_kernel(const float *m, float4 *o, long long n) {

@@ -233,11 +233,12 @@ __device__ __forceinline__ uint8_t unroll_combine(uint8_t p, uint8_t c) {
     const uint8_t neg = (c & 2) ? (c & 1) : ((p ^ c) & 1);
     return neg | ((p | c) & 2);
 }
-__global__ void unroll_local_kernel(const float4 *x, int w4, long long n_steps, long long n_cols, uint8_t *local,
-                                    uint8_t *agg) {
-    const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (m >= n_cols) return;
-    const long long c = blockIdx.y, t0 = c * kUnrollChunk;
+__global__ void unroll_local_kernel(const float4 *x, int w4, long long n_steps, long long n_cols, long long n_chunks,
+                                    uint8_t *local, uint8_t *agg) {
+    // one thread per (chunk, column), columns fastest: neighbouring threads read neighbouring quaternions
+    const long long id = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (id >= n_chunks * n_cols) return;
+    const long long c = id / n_cols, m = id - c * n_cols, t0 = c * kUnrollChunk;
     const long long t1 = min(t0 + kUnrollChunk, n_steps);
     float4 prev = t0 > 0 ? __ldg(x + ((t0 - 1) * n_cols + m) * w4) : make_float4(0.f, 0.f, 0.f, 0.f);
     uint8_t state = 0;
@@ -258,11 +259,25 @@ __global__ void unroll_local_kernel(const float4 *x, int w4, long long n_steps, 
     }
     agg[c * n_cols + m] = state;
 }
-__global__ void unroll_chunks_kernel(uint8_t *agg, long long n_chunks, long long n_cols) {
-    const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (m >= n_cols) return;
+// one block per column: every thread folds a contiguous run of chunks, the block scans the 256 partial
+// states in shared memory, then every thread rewrites its run with the exclusive prefixes
+__global__ void __launch_bounds__(256) unroll_chunks_kernel(uint8_t *agg, long long n_chunks, long long n_cols) {
+    __shared__ uint8_t part[256];
+    const long long m = blockIdx.x;
+    const long long per = (n_chunks + 255) / 256;
+    const long long c0 = min(threadIdx.x * per, n_chunks), c1 = min(c0 + per, n_chunks);
     uint8_t run = 0;
-    for (long long c = 0; c < n_chunks; ++c) {
+    for (long long c = c0; c < c1; ++c) run = unroll_combine(run, agg[c * n_cols + m]);
+    part[threadIdx.x] = run;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {  // inclusive Hillis-Steele scan with the (associative, non-commutative) combine
+        const uint8_t left = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        if (threadIdx.x >= d) part[threadIdx.x] = unroll_combine(left, part[threadIdx.x]);
+        __syncthreads();
+    }
+    run = threadIdx.x > 0 ? part[threadIdx.x - 1] : 0;  // state before this thread's run
+    for (long long c = c0; c < c1; ++c) {
         const uint8_t a = agg[c * n_cols + m];
         agg[c * n_cols + m] = run;  // exclusive: the state BEFORE the chunk
         run = unroll_combine(run, a);

@@ -42,8 +42,11 @@ DEEP65 = (
 BODY32 = _SMPL_BODY22 + [20] * 5 + [21] * 5
 BODY40 = _SMPL_BODY22 + _hand(20, 22)[:9] + _hand(21, 31)[:9]
 
+BODY16 = _SMPL_BODY22[:16]
+BODY24 = _SMPL_BODY22 + [20, 21]
+
 TOPOLOGIES = {"body22": BODY22, "smplh52": SMPLH52, "deep65": DEEP65, "chain3": [0, 0, 1], "body32": BODY32,
-              "body40": BODY40}
+              "body40": BODY40, "body16": BODY16, "body24": BODY24}
 
 
 def parents_of(name: str) -> np.ndarray:

@@ -15,7 +15,12 @@ timeout 600 python bench.py > gpurun_out/bench.json 2>> gpurun_out/bench.err; ec
 cat gpurun_out/bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fk_chain -s 3 -c 1 -f -o gpurun_out/prof_fk \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fk_ -s 3 -c 1 -f -o gpurun_out/prof_fk \
     python bench.py --kernel-only --steps 3 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fk_ -s 3 -c 1 -f -o gpurun_out/prof_fk_52 \
+    python bench.py --kernel-only --steps 3 --warmup 3 --workload fk_4m_x_52 > gpurun_out/ncu_full_52.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fk_quat -s 3 -c 1 -f -o gpurun_out/prof_fkq \
+    python bench.py --kernel-only --steps 3 --warmup 3 --op fk_quat > gpurun_out/ncu_full_fkq.log 2>&1
+python tools/bench_elementwise.py > gpurun_out/elementwise.jsonl 2> gpurun_out/elementwise.err
 bash tools/gpu_ops.sh > /dev/null 2>&1
 ls -la gpurun_out | head -30

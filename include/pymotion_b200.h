@@ -183,6 +183,25 @@ int pmb_vec_mirror_f32(const float *v, int32_t axis, float *out, int64_t n, void
 /* out[f][j] = positions[f][j] - positions[f][0] (mirror mode 'positions', skeleton.py:338). */
 int pmb_root_center_f32(const float *positions, float *out, int64_t n_frames, int32_t n_joints, void *stream);
 
+/* ---- the numeric modules either side of fk (SURVEY 8f rank 3 tail, rank 4) -------------------- */
+/* rotations/ortho6d.py: ortho6d [n][3][2] = the first two columns of the rotation matrix (8-byte aligned). */
+int pmb_ortho6d_from_matrix_f32(const float *rotmats, float *ortho6d, int64_t n, void *stream);   /* ortho6d.py:31 */
+int pmb_ortho6d_from_quat_f32(const float *q, float *ortho6d, int64_t n, void *stream);           /* ortho6d.py:14 */
+int pmb_ortho6d_to_matrix_f32(const float *ortho6d, float *rotmats, int64_t n, void *stream);     /* ortho6d.py:67 */
+int pmb_ortho6d_to_quat_f32(const float *ortho6d, float *q, int64_t n, void *stream);             /* ortho6d.py:50 */
+/* ops/center_of_mass.py:52  out[f][:] = sum_j joints[f][j][:] * weights[j];  weights_frame_stride 0 = one row of
+ * weights shared by every frame, n_joints = weights per frame. */
+int pmb_center_of_mass_f32(const float *joints, const float *weights, int64_t weights_frame_stride, int64_t n_frames,
+                           int32_t n_joints, float *out, void *stream);
+/* ops/time.py:4  linear interpolation along the time axis of positions [outer][n_original][inner] ->
+ * out [outer][n_samples][inner].  Times are DEVICE float64 arrays (sorted original_times); idx_workspace
+ * (n_samples int32) and weight_workspace (n_samples float) are device scratch owned by the caller. */
+int pmb_interpolate_positions_f32(const double *sample_times, const double *original_times, const float *positions,
+                                  int64_t outer, int64_t n_original, int64_t n_samples, int64_t inner, float *out,
+                                  int32_t *idx_workspace, float *weight_workspace, void *stream);
+/* ops/vector.py:4  v / (|v| + eps) over rows of length k. */
+int pmb_vec_normalize_f32(const float *v, float eps, float *out, int64_t n, int32_t k, void *stream);
+
 /* ---- introspection of the host-side joint program (tests) ---- */
 
 /* Builds the per-joint program the chain kernels execute for `parents_host`:

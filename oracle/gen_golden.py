@@ -22,7 +22,11 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 sys.path.insert(0, "/root/reference")
 
+import pymotion.ops.center_of_mass as ref_com  # noqa: E402
 import pymotion.ops.skeleton as ref_sk  # noqa: E402
+import pymotion.ops.time as ref_time  # noqa: E402
+import pymotion.ops.vector as ref_vec  # noqa: E402
+import pymotion.rotations.ortho6d as ref_o6  # noqa: E402
 import pymotion.rotations.dual_quat as ref_dq  # noqa: E402
 import pymotion.rotations.quat as ref_q  # noqa: E402
 
@@ -374,9 +378,56 @@ def gen_ik():
     return d
 
 
+def gen_misc():
+    """SURVEY 8f rank 3 (ortho6d) and rank 4 (center_of_mass, interpolate_positions, vector.normalize)."""
+    d = {}
+    rng = np.random.default_rng(2024)
+    for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+        q = ref_q.normalize(rng.standard_normal((3, 17, 4))).astype(dt)
+        m = ref_q.to_matrix(q).astype(dt)
+        d[f"{tag}/q"], d[f"{tag}/m"] = q, m
+        d[f"{tag}/o6_from_quat"] = ref_o6.from_quat(q)
+        d[f"{tag}/o6_from_matrix"] = np.ascontiguousarray(ref_o6.from_matrix(m))
+        o6 = (ref_o6.from_matrix(m) * rng.uniform(0.5, 2.0, (3, 17, 1, 2)) + 0.05 * rng.standard_normal((3, 17, 3, 2))).astype(dt)
+        d[f"{tag}/o6"] = o6                       # scaled and skewed: Gram-Schmidt has work to do
+        d[f"{tag}/o6_to_matrix"] = np.ascontiguousarray(ref_o6.to_matrix(o6))
+        d[f"{tag}/o6_to_quat"] = ref_o6.to_quat(o6)
+        joints = rng.standard_normal((4, 5, 22, 3)).astype(dt)
+        w = rng.uniform(0.1, 1.0, 22)
+        w /= w.sum()
+        d[f"{tag}/joints"], d[f"{tag}/weights"] = joints, w.astype(dt)
+        d[f"{tag}/com"] = ref_com.center_of_mass(joints, w.astype(dt))
+        wpf = rng.uniform(0.1, 1.0, (4, 5, 22)).astype(dt)
+        d[f"{tag}/weights_pf"] = wpf
+        d[f"{tag}/com_pf"] = ref_com.center_of_mass(joints, wpf)
+        parts = [joints[..., 0:6, :], joints[..., 6:10, :], joints[..., 10:14, :], joints[..., 14:18, :], joints[..., 18:22, :]]
+        d[f"{tag}/human_com"] = ref_com.human_center_of_mass(*parts)
+        t0 = np.sort(rng.uniform(0, 10, 40))
+        ts = np.concatenate([rng.uniform(-1, 11, 60), t0[[0, 7, 39]]])  # outside the range and exactly on knots
+        d[f"{tag}/t_orig"], d[f"{tag}/t_sample"] = t0, ts
+        p1 = rng.standard_normal((40, 3)).astype(dt)
+        p2 = rng.standard_normal((4, 40, 3)).astype(dt)
+        d[f"{tag}/interp_p1"], d[f"{tag}/interp_p2"] = p1, p2
+        d[f"{tag}/interp_1"] = ref_time.interpolate_positions(ts, t0, p1, 0)
+        d[f"{tag}/interp_2"] = ref_time.interpolate_positions(ts, t0, p2, 1)
+        v = rng.standard_normal((6, 11, 3)).astype(dt)
+        v[0, 0] = 0
+        d[f"{tag}/vec"] = v
+        d[f"{tag}/vec_normalize"] = ref_vec.normalize(v)
+        d[f"{tag}/vec_normalize_eps"] = ref_vec.normalize(v, eps=1e-3)
+        v5 = rng.standard_normal((9, 5)).astype(dt)
+        d[f"{tag}/vec5"], d[f"{tag}/vec5_normalize"] = v5, ref_vec.normalize(v5)
+    # hand-written sample of ops/tests/test_center_of_mass.py:15-40
+    d["hand/com_joints"] = np.array([[[0, 0, 0], [1, 1, 1], [2, 2, 2]], [[1, 0, 0], [0, 1, 0], [0, 0, 1]]], dtype=np.float64)
+    d["hand/com_weights"] = np.array([0.2, 0.3, 0.5])
+    d["hand/com"] = ref_com.center_of_mass(d["hand/com_joints"], d["hand/com_weights"])
+    np.savez_compressed(os.path.join(OUT, "misc.npz"), **d)
+    return d
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    for fn in (gen_fk, gen_dq, gen_quat, gen_quat_ext, gen_ik):
+    for fn in (gen_fk, gen_dq, gen_quat, gen_quat_ext, gen_ik, gen_misc):
         out = fn()
         print(fn.__name__, len(out), "arrays")
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)}

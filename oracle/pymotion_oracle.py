@@ -34,6 +34,9 @@ __all__ = [
     "quat_from_to_axis", "dq_is_unit", "dq_normalize", "dq_unroll",
     # the in-repo consumers of fk
     "from_root_positions", "mirror",
+    # SURVEY 8f rank 3 (ortho6d) and rank 4 (the consumers / helpers either side of fk)
+    "ortho6d_from_quat", "ortho6d_from_matrix", "ortho6d_to_matrix", "ortho6d_to_quat", "center_of_mass",
+    "human_center_of_mass", "interpolate_positions",
 ]
 
 
@@ -529,3 +532,70 @@ def mirror(local_rotations, global_translation, parents, offsets, end_sites=None
         pos = pos - pos[..., 0:1, :]
         return from_root_positions(pos, parents, offsets), moved, offsets, end_sites
     raise ValueError("Invalid mode. Choose 'symmetry', 'all', or 'positions'")
+
+
+# ----------------------------------------------------------------------------
+# 6-D rotation representation                           (rotations/ortho6d.py)
+# [..., 3, 2] = the first two COLUMNS of the rotation matrix
+# ----------------------------------------------------------------------------
+def ortho6d_from_matrix(rotmats):
+    """ortho6d.py:31-47 (a view of the input, like the reference)."""
+    return rotmats[..., :2]
+
+
+def ortho6d_from_quat(quaternions):
+    """ortho6d.py:14-28."""
+    return ortho6d_from_matrix(quat_to_matrix(quaternions))
+
+
+def ortho6d_to_matrix(ortho6d):
+    """ortho6d.py:67-90: Gram-Schmidt on the two columns (plain norms, no eps), third column = cross product."""
+    a, b = ortho6d[..., 0], ortho6d[..., 1]
+    c1 = a / np.linalg.norm(a, axis=-1, keepdims=True)
+    c2 = b - np.sum(c1 * b, axis=-1)[..., np.newaxis] * c1
+    c2 = c2 / np.linalg.norm(c2, axis=-1, keepdims=True)
+    c3 = np.cross(c1, c2, axis=-1)
+    rows = np.concatenate([c1, c2, c3], axis=-1).reshape(*ortho6d.shape[:-2], 3, 3)
+    return np.swapaxes(rows, -2, -1)
+
+
+def ortho6d_to_quat(ortho6d):
+    """ortho6d.py:50-64."""
+    return quat_from_matrix(ortho6d_to_matrix(ortho6d))
+
+
+# ----------------------------------------------------------------------------
+# consumers of fk positions                 (ops/center_of_mass.py, ops/time.py)
+# ----------------------------------------------------------------------------
+def center_of_mass(joints, weights):
+    """center_of_mass.py:52-68: sum over the joint axis of joints * weights."""
+    return np.sum(joints * weights[..., np.newaxis], axis=-2)
+
+
+def human_center_of_mass(joints_spine, joints_left_arm, joints_right_arm, joints_left_leg, joints_right_leg):
+    """center_of_mass.py:4-49: spine 60 %, each arm 5 %, each leg 15 %, spread evenly over the joints of the part."""
+    parts = (joints_spine, joints_left_arm, joints_right_arm, joints_left_leg, joints_right_leg)
+    shares = (0.6, 0.05, 0.05, 0.15, 0.15)
+    weights = np.array([w for part, share in zip(parts, shares) for w in [share / part.shape[-2]] * part.shape[-2]])
+    return center_of_mass(np.concatenate(parts, axis=-2), weights)
+
+
+def interpolate_positions(sample_times, original_times, positions, axis, method="linear"):
+    """time.py:4-66: linear interpolation along `axis`; the bracketing interval comes from np.searchsorted
+    (left) clamped to [0, T-2], so samples outside the original range extrapolate from the end intervals."""
+    assert method == "linear", "Only linear interpolation is supported yet."
+    assert positions.shape[axis] == original_times.shape[0], (
+        "Wrong shape of data. Positions along the axis dimension must be equal to the length of original_times.")
+    idx = np.minimum(np.maximum(np.searchsorted(original_times, sample_times) - 1, 0), original_times.shape[0] - 2)
+    w = (sample_times - original_times[idx]) / (original_times[idx + 1] - original_times[idx])
+    lo = np.take(positions, idx, axis=axis)
+    hi = np.take(positions, idx + 1, axis=axis)
+    shape = [1] * positions.ndim
+    shape[axis] = len(sample_times)
+    # the reference broadcasts the weights as weights[..., np.newaxis] against positions indexed on `axis`
+    # (time.py:61-64), which lines them up with `axis` only when it is the second-to-last axis or the array is
+    # [T, 3]; the restatement aligns them with `axis` explicitly (same result wherever the reference works)
+    wb = w.reshape(shape)
+    out = (1 - wb) * lo
+    out += wb * hi
+    return out

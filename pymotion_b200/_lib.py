@@ -60,6 +60,13 @@ SIGNATURES = {
     "pmb_mirror_to_local_f32": [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp],
     "pmb_vec_mirror_f32": [_vp, _i32, _vp, _i64, _vp],
     "pmb_root_center_f32": [_vp, _vp, _i64, _i32, _vp],
+    "pmb_ortho6d_from_matrix_f32": [_vp, _vp, _i64, _vp],
+    "pmb_ortho6d_from_quat_f32": [_vp, _vp, _i64, _vp],
+    "pmb_ortho6d_to_matrix_f32": [_vp, _vp, _i64, _vp],
+    "pmb_ortho6d_to_quat_f32": [_vp, _vp, _i64, _vp],
+    "pmb_center_of_mass_f32": [_vp, _vp, _i64, _i64, _i32, _vp, _vp],
+    "pmb_interpolate_positions_f32": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
+    "pmb_vec_normalize_f32": [_vp, _f32, _vp, _i64, _i32, _vp],
 }
 _RESTYPES = {"pmb_last_error": ctypes.c_char_p, "pmb_last_variant": ctypes.c_char_p, "pmb_status_string": ctypes.c_char_p, "pmb_release_workspace": None,
              "pmb_unroll_workspace_bytes": ctypes.c_int64}

@@ -20,6 +20,7 @@
 #include "fk_lanes_kernel.cuh"
 #include "ik_kernels.cuh"
 #include "joint_program.h"
+#include "misc_ops.cuh"
 #include "rotations_ext.cuh"
 
 namespace {
@@ -1014,6 +1015,72 @@ int pmb_root_center_f32(const float *positions, float *out, int64_t n_frames, in
     if (n_joints < 1) return fail(PMB_ERR_SHAPE, "%s: n_joints < 1", __func__);
     PMB_EW_PROLOGUE(n_frames, positions, out);
     pmb::root_center_kernel<<<ew_grid(n_frames * n_joints * 3, 256, dp_), 256, 0, st_>>>(positions, out, n_frames, n_joints);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// ---- ortho6d, center_of_mass, interpolate_positions, vector.normalize (misc_ops.cuh) ---------
+int pmb_ortho6d_from_matrix_f32(const float *rotmats, float *ortho6d, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, rotmats, ortho6d);
+    if (reinterpret_cast<uintptr_t>(ortho6d) & 7u) return fail(PMB_ERR_ALIGN, "%s: ortho6d must be 8-byte aligned", __func__);
+    pmb::ortho6d_from_matrix_kernel<<<grid_, 256, 0, st_>>>(rotmats, ortho6d, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_ortho6d_from_quat_f32(const float *q, float *ortho6d, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, q, ortho6d);
+    PMB_NEED16(q);
+    if (reinterpret_cast<uintptr_t>(ortho6d) & 7u) return fail(PMB_ERR_ALIGN, "%s: ortho6d must be 8-byte aligned", __func__);
+    pmb::ortho6d_from_quat_kernel<<<grid_, 256, 0, st_>>>((const float4 *)q, ortho6d, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_ortho6d_to_matrix_f32(const float *ortho6d, float *rotmats, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, ortho6d, rotmats);
+    if (reinterpret_cast<uintptr_t>(ortho6d) & 7u) return fail(PMB_ERR_ALIGN, "%s: ortho6d must be 8-byte aligned", __func__);
+    pmb::ortho6d_to_matrix_kernel<<<grid_, 256, 0, st_>>>(ortho6d, rotmats, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_ortho6d_to_quat_f32(const float *ortho6d, float *q, int64_t n, void *stream) {
+    PMB_EW_PROLOGUE(n, ortho6d, q);
+    PMB_NEED16(q);
+    if (reinterpret_cast<uintptr_t>(ortho6d) & 7u) return fail(PMB_ERR_ALIGN, "%s: ortho6d must be 8-byte aligned", __func__);
+    pmb::ortho6d_to_quat_kernel<<<grid_, 256, 0, st_>>>(ortho6d, (float4 *)q, n);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_center_of_mass_f32(const float *joints, const float *weights, int64_t weights_frame_stride, int64_t n_frames,
+                           int32_t n_joints, float *out, void *stream) {
+    if (n_joints < 1) return fail(PMB_ERR_SHAPE, "%s: n_joints < 1", __func__);
+    if (weights_frame_stride != 0 && weights_frame_stride != n_joints)
+        return fail(PMB_ERR_SHAPE, "%s: weights_frame_stride must be 0 or n_joints", __func__);
+    PMB_EW_PROLOGUE(n_frames, joints, weights, out);
+    pmb::center_of_mass_kernel<<<ew_grid(3 * n_frames, 256, dp_), 256, 0, st_>>>(joints, weights, weights_frame_stride, out,
+                                                                              n_frames, n_joints);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_interpolate_positions_f32(const double *sample_times, const double *original_times, const float *positions,
+                                  int64_t outer, int64_t n_original, int64_t n_samples, int64_t inner, float *out,
+                                  int32_t *idx_workspace, float *weight_workspace, void *stream) {
+    if (n_original < 2) return fail(PMB_ERR_SHAPE, "%s: at least two original times are needed", __func__);
+    if (outer < 0 || inner < 0 || n_samples < 0) return fail(PMB_ERR_SHAPE, "%s: negative size", __func__);
+    if (n_original > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "%s: n_original must be below 2^31", __func__);
+    if (outer == 0 || inner == 0 || n_samples == 0) return PMB_OK;
+    PMB_EW_PROLOGUE(n_samples, sample_times, original_times, positions, out, idx_workspace, weight_workspace);
+    pmb::interp_coeff_kernel<<<grid_, 256, 0, st_>>>(sample_times, original_times, n_samples, n_original, idx_workspace,
+                                                     weight_workspace);
+    PMB_CUDA(cudaGetLastError());
+    pmb::interp_apply_kernel<<<ew_grid(outer * n_samples * inner, 256, dp_), 256, 0, st_>>>(
+        positions, idx_workspace, weight_workspace, out, outer, n_original, n_samples, inner);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+int pmb_vec_normalize_f32(const float *v, float eps, float *out, int64_t n, int32_t k, void *stream) {
+    if (k < 1) return fail(PMB_ERR_SHAPE, "%s: k < 1", __func__);
+    PMB_EW_PROLOGUE(n, v, out);
+    pmb::vec_normalize_kernel<<<grid_, 256, 0, st_>>>(v, eps, out, n, k);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }

@@ -38,3 +38,8 @@ def golden_quat_ext():
 @pytest.fixture(scope="session")
 def golden_ik():
     return dict(np.load(os.path.join(GOLDEN, "ik.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_misc():
+    return dict(np.load(os.path.join(GOLDEN, "misc.npz")))

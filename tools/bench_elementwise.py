@@ -69,6 +69,11 @@ def main():
         "quat.from_to": (lambda: lib.pmb_quat_from_to_f32(p(v), p(v2), 1, p(o4), n, st), 40),
         "quat.unroll [F x 22]": (lambda: lib.pmb_unroll_f32(p(q0), 4, F, J, p(o4), p(work), work.numel(), st), 32),
         "dual_quat.normalize": (lambda: lib.pmb_dq_normalize_f32(p(dq), p(m), n, p(flags), st) if False else lib.pmb_dq_normalize_f32(p(dq), p(dq), n, p(flags), st), 64),
+        "ortho6d.from_quat": (lambda: lib.pmb_ortho6d_from_quat_f32(p(q0), p(dq), n, st), 40),
+        "ortho6d.to_matrix": (lambda: lib.pmb_ortho6d_to_matrix_f32(p(dq), p(m), n, st), 60),
+        "ortho6d.to_quat": (lambda: lib.pmb_ortho6d_to_quat_f32(p(dq), p(o4), n, st), 40),
+        "vector.normalize [n x 3]": (lambda: lib.pmb_vec_normalize_f32(p(v), 1e-8, p(o3), n, 3, st), 24),
+        "center_of_mass [F x 22]": (lambda: lib.pmb_center_of_mass_f32(p(v), p(tt), 0, F, J, p(o3), st), 12 + 12.0 / J),
         "from_global_rotations [F x 22]": (lambda: lib.pmb_from_global_rotations_f32(p(q0), par.ctypes.data, F, J, p(o4), st), 32),
         "mirror_to_local [F x 22]": (lambda: lib.pmb_mirror_to_local_f32(p(q0), par.ctypes.data, None, 0, F, J, p(o4), st), 32),
     }

@@ -54,6 +54,7 @@ int cuda_fail(cudaError_t e, const char *what) {
     } while (0)
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned32(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 struct DeviceProps {
     int sm_count = 0;
@@ -782,14 +783,16 @@ int pmb_dq_from_rotation_translation_f32(const float *rotations, const float *tr
                                          void *stream) {
     PMB_EW_PROLOGUE(n, rotations, translations, dq);
     PMB_NEED16(rotations); PMB_NEED16(dq);
-    pmb::dq_from_rt_kernel<<<grid_, 256, 0, st_>>>((const float4 *)rotations, translations, (float4 *)dq, n);
+    if (aligned32(dq)) pmb::dq_from_rt_kernel<true><<<grid_, 256, 0, st_>>>((const float4 *)rotations, translations, (float4 *)dq, n);
+    else pmb::dq_from_rt_kernel<false><<<grid_, 256, 0, st_>>>((const float4 *)rotations, translations, (float4 *)dq, n);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
 int pmb_dq_from_translation_f32(const float *translations, float *dq, int64_t n, void *stream) {
     PMB_EW_PROLOGUE(n, translations, dq);
     PMB_NEED16(dq);
-    pmb::dq_from_t_kernel<<<grid_, 256, 0, st_>>>(translations, (float4 *)dq, n);
+    if (aligned32(dq)) pmb::dq_from_t_kernel<true><<<grid_, 256, 0, st_>>>(translations, (float4 *)dq, n);
+    else pmb::dq_from_t_kernel<false><<<grid_, 256, 0, st_>>>(translations, (float4 *)dq, n);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
@@ -797,7 +800,8 @@ int pmb_dq_to_rotation_translation_f32(const float *dq, float *rotations, float 
                                        void *stream) {
     PMB_EW_PROLOGUE(n, dq, rotations, translations);
     PMB_NEED16(dq); PMB_NEED16(rotations);
-    pmb::dq_to_rt_kernel<<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)rotations, translations, n);
+    if (aligned32(dq)) pmb::dq_to_rt_kernel<true><<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)rotations, translations, n);
+    else pmb::dq_to_rt_kernel<false><<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)rotations, translations, n);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
@@ -925,9 +929,17 @@ int pmb_dq_normalize_f32(const float *dq, float *out, int64_t n, int32_t *flags3
     PMB_CUDA(cudaMemsetAsync(flags3, 0, 3 * sizeof(int32_t), static_cast<cudaStream_t>(stream)));
     PMB_EW_PROLOGUE(n, dq, out);
     PMB_NEED16(dq); PMB_NEED16(out);
-    pmb::dq_normalize_scale_kernel<<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
-    PMB_CUDA(cudaGetLastError());
-    pmb::dq_normalize_ortho_kernel<<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
+    // pass 1 reads the array and reduces the reference's whole-array is_unit verdict into flags3; pass 2 reads it
+    // again and writes every result once (96 bytes of traffic per element instead of the 128 of scale-then-fix)
+    if (aligned32(dq) && aligned32(out)) {
+        pmb::dq_normalize_flags_kernel<true><<<grid_, 256, 0, st_>>>((const float4 *)dq, flags3, n);
+        PMB_CUDA(cudaGetLastError());
+        pmb::dq_normalize_write_kernel<true><<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
+    } else {
+        pmb::dq_normalize_flags_kernel<false><<<grid_, 256, 0, st_>>>((const float4 *)dq, flags3, n);
+        PMB_CUDA(cudaGetLastError());
+        pmb::dq_normalize_write_kernel<false><<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
+    }
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
@@ -958,15 +970,15 @@ int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_h
     }
     DeviceProps dp;
     if ((rc = device_props(dp))) return rc;
-    constexpr int THREADS = 128;
-    const int smem = n_joints * 16 + n_slots * THREADS * 16;
+    const int smem = pmb::frp_geom(n_joints, n_slots).block_bytes;
     if (smem > dp.smem_optin)
-        return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", n_slots);
-    auto kernel = pmb::from_root_positions_kernel<THREADS>;
+        return fail(PMB_ERR_TOPOLOGY, "from_root_positions: %d joints with %d live branch slots do not fit in shared memory", n_joints, n_slots);
+    auto kernel = pmb::from_root_positions_kernel;
     if ((rc = set_smem(kernel, smem))) return rc;
-    const long long blocks = (n_frames + THREADS - 1) / THREADS;
+    if (!aligned16(positions)) return fail(PMB_ERR_ALIGN, "from_root_positions: positions must be 16-byte aligned");
+    const long long blocks = (n_frames + 31) / 32;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
-    kernel<<<static_cast<unsigned>(blocks), THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+    kernel<<<static_cast<unsigned>(blocks), 32, smem, static_cast<cudaStream_t>(stream)>>>(
         positions, offsets, reinterpret_cast<float4 *>(rotations), n_frames, n_joints, n_slots, prog, kids);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
@@ -1038,6 +1050,7 @@ int pmb_ortho6d_from_quat_f32(const float *q, float *ortho6d, int64_t n, void *s
 int pmb_ortho6d_to_matrix_f32(const float *ortho6d, float *rotmats, int64_t n, void *stream) {
     PMB_EW_PROLOGUE(n, ortho6d, rotmats);
     if (reinterpret_cast<uintptr_t>(ortho6d) & 7u) return fail(PMB_ERR_ALIGN, "%s: ortho6d must be 8-byte aligned", __func__);
+    PMB_NEED16(rotmats);
     pmb::ortho6d_to_matrix_kernel<<<grid_, 256, 0, st_>>>(ortho6d, rotmats, n);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;

@@ -34,6 +34,42 @@ __device__ __forceinline__ void stg_stream(V *p, const V &v) {
     __stcs(p, v);
 }
 
+// ---- 256-bit global accesses (Blackwell: LDG.E.ENL2.256 / STG.E.ENL2.256) ----------------------------
+// A dual quaternion is 32 bytes = one DRAM sector.  Written as two 16-byte stores by the same thread every
+// sector arrives at L2 in two halves from two different instructions (measured: the dual-quaternion writers ran
+// at 2.6 .. 2.9 TB/s of write traffic against 4.6 TB/s for the bulk-stored fk output); one 32-byte access moves
+// the sector whole.  The address must be 32-byte aligned.
+struct F8 {
+    float4 lo, hi;
+};
+__device__ __forceinline__ F8 ldg256(const void *p) {
+    F8 v;
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v.lo.x), "=f"(v.lo.y), "=f"(v.lo.z), "=f"(v.lo.w), "=f"(v.hi.x), "=f"(v.hi.y), "=f"(v.hi.z), "=f"(v.hi.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg256(void *p, const float4 &lo, const float4 &hi) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z),
+                 "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w)
+                 : "memory");
+}
+// dual quaternion i of a [n][8] array: one 32-byte access when the array is 32-byte aligned (A32), else two float4
+template <bool A32>
+__device__ __forceinline__ F8 ld_dq(const float4 *dq, long long i) {
+    if (A32) return ldg256(dq + 2 * i);
+    return F8{__ldcs(dq + 2 * i), __ldcs(dq + 2 * i + 1)};
+}
+template <bool A32>
+__device__ __forceinline__ void st_dq(float4 *dq, long long i, const float4 &lo, const float4 &hi) {
+    if (A32) {
+        stg256(dq + 2 * i, lo, hi);
+    } else {
+        __stcs(dq + 2 * i, lo);
+        __stcs(dq + 2 * i + 1, hi);
+    }
+}
+
 // ---- quaternion algebra, (w,x,y,z) ------------------------------------------
 template <typename T>
 struct Quat {

@@ -71,27 +71,29 @@ __global__ void quat_from_matrix_kernel(const float *m, float4 *o, long long n) 
     }
 }
 // dual_quat.py:12-36
+template <bool A32>
 __global__ void dq_from_rt_kernel(const float4 *r, const float *t, float4 *dq, long long n) {
     PMB_GRID_STRIDE(i, n) {
         const Quat<float> qr = ldq(r, i);
         const Vec3<float> v = ldv(t, i);
         const Quat<float> d = q_mul(Quat<float>{0.f, v.x, v.y, v.z}, qr);
-        stq(dq, 2 * i, qr);
-        stq(dq, 2 * i + 1, Quat<float>{0.5f * d.w, 0.5f * d.x, 0.5f * d.y, 0.5f * d.z});
+        st_dq<A32>(dq, i, make_float4(qr.w, qr.x, qr.y, qr.z), make_float4(0.5f * d.w, 0.5f * d.x, 0.5f * d.y, 0.5f * d.z));
     }
 }
 // dual_quat.py:39-59
+template <bool A32>
 __global__ void dq_from_t_kernel(const float *t, float4 *dq, long long n) {
     PMB_GRID_STRIDE(i, n) {
         const Vec3<float> v = ldv(t, i);
-        stq(dq, 2 * i, Quat<float>{1.f, 0.f, 0.f, 0.f});
-        stq(dq, 2 * i + 1, Quat<float>{0.f, v.x * 0.5f, v.y * 0.5f, v.z * 0.5f});
+        st_dq<A32>(dq, i, make_float4(1.f, 0.f, 0.f, 0.f), make_float4(0.f, v.x * 0.5f, v.y * 0.5f, v.z * 0.5f));
     }
 }
 // dual_quat.py:62-83
+template <bool A32>
 __global__ void dq_to_rt_kernel(const float4 *dq, float4 *r, float *t, long long n) {
     PMB_GRID_STRIDE(i, n) {
-        const Quat<float> qr = ldq(dq, 2 * i), qd = ldq(dq, 2 * i + 1);
+        const F8 x = ld_dq<A32>(dq, i);
+        const Quat<float> qr{x.lo.x, x.lo.y, x.lo.z, x.lo.w}, qd{x.hi.x, x.hi.y, x.hi.z, x.hi.w};
         const Quat<float> m = q_mul(qd, q_conj(qr));
         stq(r, i, qr);
         stv(t, i, Vec3<float>{2.f * m.x, 2.f * m.y, 2.f * m.z});

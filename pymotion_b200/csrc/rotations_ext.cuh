@@ -193,28 +193,39 @@ __device__ __forceinline__ void unit_flags(const Quat<float> &r, const Quat<floa
 __global__ void dq_is_unit_kernel(const float4 *dq, float atol, int *flags, long long n) {
     PMB_GRID_STRIDE(i, n) unit_flags(ldq(dq, 2 * i), ldq(dq, 2 * i + 1), atol, flags);
 }
-// pass 1 (dual_quat.py:98-103): both parts divided by |real|, flags of the result (atol 1e-3, the default)
-__global__ void dq_normalize_scale_kernel(const float4 *dq, float4 *o, int *flags, long long n) {
+// dual_quat.py:98-103: both parts divided by |real|
+template <bool A32>
+__device__ __forceinline__ void dq_scaled(const float4 *dq, long long i, Quat<float> &r, Quat<float> &d, Quat<float> &rn,
+                                          Quat<float> &dn, float &nrm) {
+    const F8 x = ld_dq<A32>(dq, i);
+    r = {x.lo.x, x.lo.y, x.lo.z, x.lo.w}, d = {x.hi.x, x.hi.y, x.hi.z, x.hi.w};
+    nrm = q_length(r);
+    rn = {r.w / nrm, r.x / nrm, r.y / nrm, r.z / nrm}, dn = {d.w / nrm, d.x / nrm, d.y / nrm, d.z / nrm};
+}
+// pass 1: is the scaled array, as a whole, unit (atol 1e-3, the reference's default)?
+template <bool A32>
+__global__ void dq_normalize_flags_kernel(const float4 *dq, int *flags, long long n) {
     PMB_GRID_STRIDE(i, n) {
-        const Quat<float> r = ldq(dq, 2 * i), d = ldq(dq, 2 * i + 1);
-        const float nrm = q_length(r);
-        const Quat<float> rn{r.w / nrm, r.x / nrm, r.y / nrm, r.z / nrm}, dn{d.w / nrm, d.x / nrm, d.y / nrm, d.z / nrm};
-        o[2 * i] = make_float4(rn.w, rn.x, rn.y, rn.z);
-        o[2 * i + 1] = make_float4(dn.w, dn.x, dn.y, dn.z);
+        Quat<float> r, d, rn, dn;
+        float nrm;
+        dq_scaled<A32>(dq, i, r, d, rn, dn, nrm);
         unit_flags(rn, dn, 1e-3f, flags);
     }
 }
-// pass 2 (:104-111): only if the scaled array as a whole is not unit, remove the real direction from every dual part
-__global__ void dq_normalize_ortho_kernel(const float4 *dq, float4 *o, const int *flags, long long n) {
+// pass 2 (:104-113): write the scaled parts; only if the whole scaled array is not unit, the real direction is
+// removed from every dual part
+template <bool A32>
+__global__ void dq_normalize_write_kernel(const float4 *dq, float4 *o, const int *flags, long long n) {
     const bool unit = flags[0] == 0 || (flags[1] == 0 && flags[2] == 0);
-    if (unit) return;
     PMB_GRID_STRIDE(i, n) {
-        const Quat<float> r = ldq(dq, 2 * i), d = ldq(dq, 2 * i + 1);
-        const float nrm = q_length(r);
-        const float k = dot4_np(r, d) / (nrm * nrm);
-        const float4 rn = o[2 * i];
-        const Quat<float> dn{d.w / nrm, d.x / nrm, d.y / nrm, d.z / nrm};
-        stq(o, 2 * i + 1, Quat<float>{dn.w - rn.x * k, dn.x - rn.y * k, dn.y - rn.z * k, dn.z - rn.w * k});
+        Quat<float> r, d, rn, dn;
+        float nrm;
+        dq_scaled<A32>(dq, i, r, d, rn, dn, nrm);
+        if (!unit) {
+            const float k = dot4_np(r, d) / (nrm * nrm);
+            dn = {dn.w - rn.w * k, dn.x - rn.x * k, dn.y - rn.y * k, dn.z - rn.z * k};
+        }
+        st_dq<A32>(o, i, make_float4(rn.w, rn.x, rn.y, rn.z), make_float4(dn.w, dn.x, dn.y, dn.z));
     }
 }
 

@@ -277,8 +277,9 @@ def run_ours(args):
             _lib.check(lib.pmb_from_root_positions_f32(pos.data_ptr(), par.ctypes.data, off.data_ptr(), frames, n_joints,
                                                        rots.data_ptr(), st))
 
-        def mirror_all():  # device part of mirror(mode="all"): fk_quat -> flip -> local
-            fk_quat()
+        def mirror_all():  # device part of mirror(mode="all"): fk_quat (rotations only) -> flip -> local
+            _lib.check(lib.pmb_fk_quat_f32(rot.data_ptr(), gpos.data_ptr(), 0, off.data_ptr(), 0, par.ctypes.data, frames,
+                                           n_joints, None, rots.data_ptr(), st))
             _lib.check(lib.pmb_mirror_to_local_f32(rots.data_ptr(), par.ctypes.data, None, 0, frames, n_joints,
                                                    dq.data_ptr(), st))
 

@@ -83,7 +83,8 @@ int pmb_fk_f32(const float *rot, const float *global_pos, int64_t gpos_frame_str
 
 /* Variant that emits global QUATERNIONS instead of matrices (SURVEY 8f rank 1:
  * fk -> quat.from_matrix fused away; 44J instead of 64J bytes per pose).
- *   global_rots  [n_frames][n_joints][4]   out; equals quat.from_matrix(rotmats) up to sign */
+ *   global_rots  [n_frames][n_joints][4]   out; equals quat.from_matrix(rotmats) up to sign
+ * With shared offsets, `positions` may be NULL: rotations only (what mirror needs; no translation chain). */
 int pmb_fk_quat_f32(const float *rot, const float *global_pos, int64_t gpos_frame_stride,
                     const float *offsets, int64_t offsets_frame_stride, const int64_t *parents_host,
                     int64_t n_frames, int32_t n_joints, float *positions, float *global_rots, void *stream);

@@ -359,7 +359,7 @@ int launch_fk_quat_chain(const FkArgs &a, const DeviceProps &dp) {
     const int smem = pmb::fkq_geom(group, WARPS, a.n_joints, a.n_slots).block_bytes;
     if (smem > dp.smem_optin)
         return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
-    auto kernel = pmb::fk_quat_chain_kernel<WARPS>;
+    auto kernel = a.pos ? pmb::fk_quat_chain_kernel<WARPS, true> : pmb::fk_quat_chain_kernel<WARPS, false>;
     int rc = set_smem(kernel, smem);
     if (rc) return rc;
     CUtensorMap tm;
@@ -372,7 +372,7 @@ int launch_fk_quat_chain(const FkArgs &a, const DeviceProps &dp) {
     const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
     auto magic_of = [](int d) { return static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(d)) + 1u; };
     const int tail = a.n_joints % group ? a.n_joints % group : group;
-    note_variant("fk_quat_chain_kernel<WARPS=%d> group=%d grid=%lld smem=%d", WARPS, group, blocks, smem);
+    note_variant("fk_quat_chain_kernel<WARPS=%d,POS=%d> group=%d grid=%lld smem=%d", WARPS, a.pos ? 1 : 0, group, blocks, smem);
     kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(
         tm, a.gpos, a.gstride, a.offsets, a.pos, reinterpret_cast<float4 *>(a.rout), a.n_frames, a.n_joints, a.n_slots,
         group, magic_of(group), magic_of(tail), magic_of(3 * group), magic_of(3 * tail), *a.prog);
@@ -426,14 +426,15 @@ int launch_fk(const FkArgs &a, const DeviceProps &dp) {
 int fk_common(const float *rot, const float *gpos, int64_t gstride, const float *offsets, int64_t ostride,
               const int64_t *parents_host, int64_t n_frames, int32_t n_joints, float *pos, float *rout,
               bool quat_out, void *stream) {
-    if (!rot || !gpos || !offsets || !pos || !rout) return fail(PMB_ERR_NULL, "fk: NULL array pointer");
+    const bool rotations_only = quat_out && ostride == 0 && !pos;  // fk_quat without positions (mirror)
+    if (!rot || !gpos || !offsets || (!pos && !rotations_only) || !rout) return fail(PMB_ERR_NULL, "fk: NULL array pointer");
     if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
     if (n_frames > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames must be below 2^31 per call");
     if (gstride != 0 && gstride != 3) return fail(PMB_ERR_SHAPE, "gpos_frame_stride must be 0 or 3");
     if (ostride != 0 && ostride != 3LL * n_joints)
         return fail(PMB_ERR_SHAPE, "offsets_frame_stride must be 0 or 3*n_joints");
     if (!aligned16(rot)) return fail(PMB_ERR_ALIGN, "rot must be 16-byte aligned");
-    if (!aligned16(rout) || !aligned16(pos)) return fail(PMB_ERR_ALIGN, "output arrays must be 16-byte aligned");
+    if (!aligned16(rout) || (pos && !aligned16(pos))) return fail(PMB_ERR_ALIGN, "output arrays must be 16-byte aligned");
     pmb::JointProgram prog;
     int n_slots = 0;
     int rc = check_program(parents_host, n_joints, false, prog, n_slots);
@@ -449,7 +450,7 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
         if (try_fk_lanes(a, dp, rrc, rows_first || env_int("PMB_FK_ROWS", -1) == 1)) return rrc;
         if (try_fk_rows(a, dp, rrc)) return rrc;
     }
-    if (ostride == 0 && quat_out && env_int("PMB_FKQ_MATRIX", 0) == 0) return launch_fk_quat_chain(a, dp);
+    if (ostride == 0 && quat_out && (rotations_only || env_int("PMB_FKQ_MATRIX", 0) == 0)) return launch_fk_quat_chain(a, dp);
     if (ostride == 0) return quat_out ? launch_fk<false, true>(a, dp) : launch_fk<false, false>(a, dp);
     return quat_out ? launch_fk<true, true>(a, dp) : launch_fk<true, false>(a, dp);
 }
@@ -970,15 +971,15 @@ int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_h
     }
     DeviceProps dp;
     if ((rc = device_props(dp))) return rc;
-    const int smem = pmb::frp_geom(n_joints, n_slots).block_bytes;
+    constexpr int THREADS = 128;
+    const int smem = n_joints * 16 + n_slots * THREADS * 16;
     if (smem > dp.smem_optin)
-        return fail(PMB_ERR_TOPOLOGY, "from_root_positions: %d joints with %d live branch slots do not fit in shared memory", n_joints, n_slots);
-    auto kernel = pmb::from_root_positions_kernel;
+        return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", n_slots);
+    auto kernel = pmb::from_root_positions_kernel<THREADS>;
     if ((rc = set_smem(kernel, smem))) return rc;
-    if (!aligned16(positions)) return fail(PMB_ERR_ALIGN, "from_root_positions: positions must be 16-byte aligned");
-    const long long blocks = (n_frames + 31) / 32;
+    const long long blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
-    kernel<<<static_cast<unsigned>(blocks), 32, smem, static_cast<cudaStream_t>(stream)>>>(
+    kernel<<<static_cast<unsigned>(blocks), THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
         positions, offsets, reinterpret_cast<float4 *>(rotations), n_frames, n_joints, n_slots, prog, kids);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;

@@ -41,7 +41,8 @@ __device__ __forceinline__ Quat<float> q_from_matrix_sign(const Quat<float> &q) 
     return pivot < 0.f ? Quat<float>{-q.w, -q.x, -q.y, -q.z} : q;
 }
 
-template <int WARPS>
+// POS = false: rotations only (positions == nullptr; what mirror needs: no translation chain, no position stage)
+template <int WARPS, bool POS>
 __global__ void __launch_bounds__(WARPS *kWarp)
 fk_quat_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                      const float *__restrict__ offsets, float *__restrict__ pos, float4 *__restrict__ grot,
@@ -153,8 +154,10 @@ fk_quat_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__
                             cr = {a.x, a.y, a.z, a.w};
                             ct = {b.x, b.y, b.z};
                         }
-                        const Vec3<float> v = q_rotate(cr, Vec3<float>{e.x, e.y, e.z});
-                        ct = {v.x + ct.x, v.y + ct.y, v.z + ct.z};
+                        if (POS) {
+                            const Vec3<float> v = q_rotate(cr, Vec3<float>{e.x, e.y, e.z});
+                            ct = {v.x + ct.x, v.y + ct.y, v.z + ct.z};
+                        }
                         cr = q_mul(cr, r);
                     }
                     const uint32_t sv = prog_save(code);
@@ -164,7 +167,7 @@ fk_quat_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__
                     }
                     const Quat<float> o = q_from_matrix_sign(cr);
                     qs[jj] = make_float4(o.w, o.x, o.y, o.z);
-                    ps[3 * jj] = ct.x, ps[3 * jj + 1] = ct.y, ps[3 * jj + 2] = ct.z;
+                    if (POS) ps[3 * jj] = ct.x, ps[3 * jj + 1] = ct.y, ps[3 * jj + 2] = ct.z;
                 }
             }
             gj += cnt;
@@ -184,7 +187,7 @@ fk_quat_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__
                         g[static_cast<long long>(r) * n_joints + c] = qstage[r * S4 + c];
                     }
                 }
-                {   // positions: rows of 3*gj floats -> global rows of pitch 3*n_joints floats
+                if (POS) {  // positions: rows of 3*gj floats -> global rows of pitch 3*n_joints floats
                     const uint32_t magic = (gj == group) ? magic_p_full : magic_p_tail;
                     const int w = 3 * gj, n1 = nrows * w;
                     float *g = pos + (f0 * n_joints + g0) * 3;

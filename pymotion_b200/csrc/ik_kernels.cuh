@@ -31,46 +31,25 @@ struct ChildTable {
 // reference's own float32 torch twin differs from its NumPy path by 1e-4 .. 2e-3 there, 1e-7 in the median);
 // the parity tests for this op use matching tolerances.
 // ---------------------------------------------------------------------------------------------------
-// Block = one warp = a tile of 32 frames.  The tile's positions (32 x 12 J contiguous bytes) are copied into shared
-// memory with coalesced 16-byte loads, every thread walks its frame out of shared memory, the rotations are
-// staged as float4 rows (odd float4 stride: conflict-free thread-per-frame stores) and leave as coalesced float4
-// stores -- the first version read and wrote global memory with 12 J / 16 J byte strides between lanes and ran at
-// 1.7 TB/s of its 28 J bytes per pose.
-struct FrpGeom {
-    int pos_words, rot_stride4, block_bytes;
-};
-__host__ __device__ inline FrpGeom frp_geom(int n_joints, int n_slots) {
-    FrpGeom g;
-    g.pos_words = (kWarp * 3 * n_joints + 3) & ~3;
-    g.rot_stride4 = n_joints | 1;
-    g.block_bytes = n_joints * 16 + g.pos_words * 4 + kWarp * g.rot_stride4 * 16 + n_slots * kWarp * 16;
-    return g;
-}
-__global__ void __launch_bounds__(kWarp)
+// (A tile-staged variant -- one warp per block, positions and rotations through shared memory with coalesced
+// 16-byte accesses -- was measured SLOWER: 0.54 ms against 0.36 ms at 1M x 22.  The op is bound by the IEEE
+// square roots and divisions of from_to / from_to_axis, not by its strided global accesses.)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 from_root_positions_kernel(const float *__restrict__ pos, const float *__restrict__ offsets, float4 *__restrict__ rots,
                            long long n_frames, int n_joints, int n_slots, const __grid_constant__ JointProgram prog,
                            const __grid_constant__ ChildTable kids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const FrpGeom geo = frp_geom(n_joints, n_slots);
     float4 *tab = reinterpret_cast<float4 *>(smem_raw);                 // [J] offsets
-    float *ptile = reinterpret_cast<float *>(tab + n_joints);           // [32][3J] positions of the tile
-    float4 *rstage = reinterpret_cast<float4 *>(ptile + geo.pos_words); // [32][J | 1] rotations
-    float4 *slots = rstage + kWarp * geo.rot_stride4;                   // [n_slots][32] global quaternions
-    const int lane = threadIdx.x;
-    for (int j = lane; j < n_joints; j += kWarp)
+    float4 *slots = tab + n_joints;                                      // [n_slots][THREADS] global quaternions
+    for (int j = threadIdx.x; j < n_joints; j += THREADS)
         tab[j] = make_float4(offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2], 0.f);
-    const long long f0 = static_cast<long long>(blockIdx.x) * kWarp;
-    const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
-    const int row_words = 3 * n_joints, n_words = nrows * row_words;
-    {   // tile start is 16-byte aligned (32 * 12 J bytes per tile)
-        const float *src = pos + f0 * row_words;
-        for (int i = lane; i < n_words / 4; i += kWarp) reinterpret_cast<float4 *>(ptile)[i] = __ldcs(reinterpret_cast<const float4 *>(src) + i);
-        for (int i = (n_words & ~3) + lane; i < n_words; i += kWarp) ptile[i] = src[i];
-    }
-    __syncwarp();
-    const float *P = ptile + min(lane, nrows - 1) * row_words;  // tail lanes walk a copy of the last frame
-    float4 *R = rstage + lane * geo.rot_stride4;
-    auto point = [&](int j) { return Vec3<float>{P[3 * j], P[3 * j + 1], P[3 * j + 2]}; };
+    __syncthreads();
+    const long long f = blockIdx.x * static_cast<long long>(THREADS) + threadIdx.x;
+    if (f >= n_frames) return;
+    const float *P = pos + f * n_joints * 3;
+    float4 *R = rots + f * n_joints;
+    auto point = [&](int j) { return Vec3<float>{__ldg(P + 3 * j), __ldg(P + 3 * j + 1), __ldg(P + 3 * j + 2)}; };
 
     Quat<float> cur{1.f, 0.f, 0.f, 0.f};  // global rotation of the previous joint
     for (int j = 0; j < n_joints; ++j) {
@@ -81,7 +60,7 @@ from_root_positions_kernel(const float *__restrict__ pos, const float *__restric
             if (src == kSrcReg) {
                 G = cur;
             } else {
-                const float4 s = slots[src * kWarp + lane];
+                const float4 s = slots[src * THREADS + threadIdx.x];
                 G = {s.x, s.y, s.z, s.w};
             }
         }
@@ -107,13 +86,8 @@ from_root_positions_kernel(const float *__restrict__ pos, const float *__restric
         R[j] = make_float4(rot.w, rot.x, rot.y, rot.z);
         cur = q_mul(G, q_normalize(rot, 1e-8f));
         const uint32_t sv = prog_save(code);
-        if (sv != kNoSave) slots[sv * kWarp + lane] = make_float4(cur.w, cur.x, cur.y, cur.z);
+        if (sv != kNoSave) slots[sv * THREADS + threadIdx.x] = make_float4(cur.w, cur.x, cur.y, cur.z);
     }
-    __syncwarp();
-    // rows of J float4 -> the tile's contiguous 32 * 16 J bytes
-    float4 *dst = rots + f0 * n_joints;
-    for (int r = 0; r < nrows; ++r)
-        for (int c = lane; c < n_joints; c += kWarp) __stcs(dst + static_cast<long long>(r) * n_joints + c, rstage[r * geo.rot_stride4 + c]);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -230,12 +230,11 @@ def _mirrored_local(m: rt.Marshal, q, offsets_dev, par, mapping, axis_index: int
     lead, n_joints = tuple(q.shape[:-2]), int(q.shape[-2])
     n_frames = _lead_frames(lead)
     zero = torch.zeros(3, device=m.device, dtype=torch.float32)  # np.zeros_like(global_translation): root at the origin
-    pos = m.new(lead + (n_joints, 3))
     grot = m.new(lead + (n_joints, 4))
     local = m.new(lead + (n_joints, 4))
     if n_frames > 0:
         rt.call("pmb_fk_quat_f32", m.device, rt.ptr(q), rt.ptr(zero), 0, rt.ptr(offsets_dev), 0, par.ctypes.data,
-                n_frames, n_joints, rt.ptr(pos), rt.ptr(grot), m.stream())
+                n_frames, n_joints, None, rt.ptr(grot), m.stream())  # positions = NULL: rotations only
         rt.call("pmb_mirror_to_local_f32", m.device, rt.ptr(grot), par.ctypes.data,
                 None if mapping is None else mapping.ctypes.data, axis_index, n_frames, n_joints, rt.ptr(local),
                 m.stream())

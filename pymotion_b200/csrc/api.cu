@@ -134,9 +134,18 @@ int make_rot_map(CUtensorMap &tm, const float *rot, int64_t n_frames, int32_t n_
     cuuint32_t box[2] = {static_cast<cuuint32_t>(4 * chunk), static_cast<cuuint32_t>(box_frames)};
     cuuint32_t estr[2] = {1, 1};
     const CUtensorMapSwizzle sw = chunk == 8 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    // L2 promotion: the granule L2 fetches from DRAM for a box row (experiment knob PMB_TMA_L2PROMO = 0 none,
+    // 1 = 64 B, 2 = 128 B, 3 = 256 B)
+    // Measured (profiles/r1_sweep_l2promo.jsonl): 256 B granules are worth +0.6 % at 22 joints, +4 % at 52, +5 % at 65
+    // (a frame's quaternion row spans 1.4 .. 4 granules and the next chunk of the same frames finds them in L2).
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char *env = getenv("PMB_TMA_L2PROMO")) {
+        const int v = atoi(env);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(rot), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PMB_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
     return PMB_OK;
 }
@@ -198,7 +207,9 @@ int launch_fk_rows_cfg(const FkArgs &a, const DeviceProps &dp, int team_cap) {
     const long long blocks = std::min<long long>(tiles, static_cast<long long>(per_sm) * dp.sm_count);
     note_variant("fk_rows_kernel<S=%d,VEC=%d> grid=%lld (%d teams/SM) smem=%d", S, VEC, blocks, per_sm, smem);
     kernel<<<static_cast<unsigned>(blocks), pmb::kRowThreads, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos,
-                                                                                a.rout, a.n_frames, a.n_joints, *a.prog);
+                                                                                a.rout, a.n_frames, a.n_joints,
+                                                                                env_int("PMB_ST_HINT", 0),
+                                                                                env_int("PMB_L2_PREFETCH", 0) ? a.rot : nullptr, *a.prog);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
@@ -229,7 +240,8 @@ int launch_fk_lanes_cfg(const FkArgs &a, const DeviceProps &dp, int block_cap) {
     const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
     note_variant("fk_lanes_kernel<FR=%d,WARPS=%d> grid=%lld (%d warps/SM) smem=%d", FR, WARPS, blocks, per_sm * WARPS, smem);
     kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos, a.rout,
-                                                                        a.n_frames, a.n_joints, *a.prog);
+                                                                        a.n_frames, a.n_joints, env_int("PMB_ST_HINT", 0),
+                                                                        env_int("PMB_L2_PREFETCH", 0) ? a.rot : nullptr, *a.prog);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }

@@ -46,7 +46,8 @@ template <int FR, int WARPS>
 __global__ void __launch_bounds__(WARPS *kWarp)
 fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                 const float *__restrict__ offsets, float *__restrict__ pos, float *__restrict__ rout,
-                long long n_frames, int n_joints, const __grid_constant__ JointProgram prog) {
+                long long n_frames, int n_joints, int st_hint, const float *__restrict__ rot_prefetch,
+                const __grid_constant__ JointProgram prog) {
     constexpr int C = kChunk;
     constexpr int BOX = FR * 128;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
@@ -143,6 +144,9 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             if (c0 == 0) {
                 const long long next_tile = tile + tile_stride;
                 if (next_tile < n_tiles) gnext = __ldg(gpos + min(next_tile * FR + f, n_frames - 1) * gstride + a);
+                // the NEXT tile's quaternions (FR * 16 J contiguous bytes) into L2, a whole tile ahead of its boxes
+                if (lane == 0 && rot_prefetch && next_tile + 1 <= n_tiles - 1)
+                    bulk_prefetch_l2(rot_prefetch + next_tile * (FR * 4 * n_joints), static_cast<uint32_t>(FR * 16 * n_joints));
                 if (lane == 0 && draining) bulk_wait_read0();  // the previous tile has left the stage
                 __syncwarp();
             }
@@ -175,8 +179,14 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             fence_proxy_async_smem();  // this lane's stage writes -> visible to the async proxy
             __syncwarp();
             if (lane == 0) {
-                bulk_store(rg, smem_u32(Rst), static_cast<uint32_t>(FR * rpitch * 4));
-                bulk_store(pg, smem_u32(Pst), static_cast<uint32_t>(FR * ppitch * 4));
+                if (st_hint) {
+                    const uint64_t pol = l2_policy_evict_first();
+                    bulk_store_hint(rg, smem_u32(Rst), static_cast<uint32_t>(FR * rpitch * 4), pol);
+                    bulk_store_hint(pg, smem_u32(Pst), static_cast<uint32_t>(FR * ppitch * 4), pol);
+                } else {
+                    bulk_store(rg, smem_u32(Rst), static_cast<uint32_t>(FR * rpitch * 4));
+                    bulk_store(pg, smem_u32(Pst), static_cast<uint32_t>(FR * ppitch * 4));
+                }
                 bulk_commit();
                 draining = true;
             }

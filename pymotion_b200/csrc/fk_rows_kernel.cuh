@@ -261,7 +261,8 @@ template <int S, int VEC>
 __global__ void __launch_bounds__(kRowThreads, 5)
 fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                const float *__restrict__ offsets, float *__restrict__ pos, float *__restrict__ rout,
-               long long n_frames, int n_joints, const __grid_constant__ JointProgram prog) {
+               long long n_frames, int n_joints, int st_hint, const float *__restrict__ rot_prefetch,
+               const __grid_constant__ JointProgram prog) {
     constexpr int C = kChunk;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -308,6 +309,9 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
         if (lane == 0) {
             uint32_t k = 0;
             for (long long t = blockIdx.x; t < n_tiles; t += tile_stride) {
+                // the team's NEXT tile (32 * 16 J contiguous bytes) into L2, a whole tile ahead of its boxes
+                if (rot_prefetch && t + tile_stride < n_tiles - 1)
+                    bulk_prefetch_l2(rot_prefetch + (t + tile_stride) * (kWarp * 4 * n_joints), static_cast<uint32_t>(kWarp * 16 * n_joints));
                 for (int c0 = 0; c0 < n_joints; c0 += C, ++k) {
                     const uint32_t buf = k % S;
                     if (k >= S) mbar_wait_long(empty0 + 8 * buf, ((k / S) - 1) & 1);  // all three row warps have read it
@@ -330,8 +334,14 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
                 const uint32_t rbytes = static_cast<uint32_t>(nrows * rpitch * 4), pbytes = static_cast<uint32_t>(nrows * ppitch * 4);
                 // a full tile is two multiples of 128 bytes; a remainder tile can leave up to 3 words past the
                 // last 16-byte unit, stored directly
-                if (rbytes & ~15u) bulk_store(rg, smem_u32(Rst), rbytes & ~15u);
-                if (pbytes & ~15u) bulk_store(pg, smem_u32(Pst), pbytes & ~15u);
+                if (st_hint) {
+                    const uint64_t pol = l2_policy_evict_first();
+                    if (rbytes & ~15u) bulk_store_hint(rg, smem_u32(Rst), rbytes & ~15u, pol);
+                    if (pbytes & ~15u) bulk_store_hint(pg, smem_u32(Pst), pbytes & ~15u, pol);
+                } else {
+                    if (rbytes & ~15u) bulk_store(rg, smem_u32(Rst), rbytes & ~15u);
+                    if (pbytes & ~15u) bulk_store(pg, smem_u32(Pst), pbytes & ~15u);
+                }
                 bulk_commit();
                 for (uint32_t w = (rbytes & ~15u) / 4; w < rbytes / 4; ++w) rg[w] = Rst[w];
                 for (uint32_t w = (pbytes & ~15u) / 4; w < pbytes / 4; ++w) pg[w] = Pst[w];

@@ -208,7 +208,7 @@ int launch_fk_rows_cfg(const FkArgs &a, const DeviceProps &dp, int team_cap) {
     note_variant("fk_rows_kernel<S=%d,VEC=%d> grid=%lld (%d teams/SM) smem=%d", S, VEC, blocks, per_sm, smem);
     kernel<<<static_cast<unsigned>(blocks), pmb::kRowThreads, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos,
                                                                                 a.rout, a.n_frames, a.n_joints,
-                                                                                env_int("PMB_ST_HINT", 0),
+                                                                                env_int("PMB_ST_HINT", 0) | (env_int("PMB_FK_TILE_ORDER", 0) << 1),
                                                                                 env_int("PMB_L2_PREFETCH", 0) ? a.rot : nullptr, *a.prog);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;

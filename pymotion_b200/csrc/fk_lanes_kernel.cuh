@@ -179,7 +179,7 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             fence_proxy_async_smem();  // this lane's stage writes -> visible to the async proxy
             __syncwarp();
             if (lane == 0) {
-                if (st_hint) {
+                if (st_hint & 1) {
                     const uint64_t pol = l2_policy_evict_first();
                     bulk_store_hint(rg, smem_u32(Rst), static_cast<uint32_t>(FR * rpitch * 4), pol);
                     bulk_store_hint(pg, smem_u32(Pst), static_cast<uint32_t>(FR * ppitch * 4), pol);

@@ -133,7 +133,7 @@ struct RowCtx {
     uint32_t rst, pst;            // shared addresses of the stage (rotation rows, positions)
     uint32_t full0, empty0, stage_full, stage_free, fence_word;
     const float *gpos;
-    long long gstride, n_frames, n_tiles, tile_stride, first_tile;
+    long long gstride, n_frames, n_tiles, tile_stride, first_tile;  // n_tiles here = end of this team's tile range
     int n_joints, lane;
 };
 
@@ -278,8 +278,14 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
                    stage_free = stage_full + 8;
     const uint32_t box0 = smem_u32(boxes);
 
-    const long long n_tiles = (n_frames + kWarp - 1) / kWarp;
-    const long long tile_stride = gridDim.x;
+    // tile order (experiment, bit 1 of st_hint): 0 = round robin over the teams (a window of consecutive tiles slides
+    // through the arrays), 1 = one contiguous range of tiles per team
+    const long long n_tiles_all = (n_frames + kWarp - 1) / kWarp;
+    const bool blocked = (st_hint & 2) != 0;
+    const long long per_team = (n_tiles_all + gridDim.x - 1) / gridDim.x;
+    const long long tile_stride = blocked ? 1 : gridDim.x;
+    const long long tile_first = blocked ? blockIdx.x * per_team : blockIdx.x;
+    const long long n_tiles = blocked ? min(n_tiles_all, tile_first + per_team) : n_tiles_all;  // end of this team's range
     const int rpitch = 9 * n_joints, ppitch = 3 * n_joints;
 
     if (threadIdx.x == 0) {
@@ -308,7 +314,7 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
         // ---- loader: the team's chunks in processing order, across its tiles -----------------------
         if (lane == 0) {
             uint32_t k = 0;
-            for (long long t = blockIdx.x; t < n_tiles; t += tile_stride) {
+            for (long long t = tile_first; t < n_tiles; t += tile_stride) {
                 // the team's NEXT tile (32 * 16 J contiguous bytes) into L2, a whole tile ahead of its boxes
                 if (rot_prefetch && t + tile_stride < n_tiles - 1)
                     bulk_prefetch_l2(rot_prefetch + (t + tile_stride) * (kWarp * 4 * n_joints), static_cast<uint32_t>(kWarp * 16 * n_joints));
@@ -326,7 +332,7 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
         // ---- drainer: stage -> HBM through the TMA engine ------------------------------------------
         if (lane == 0) {
             uint32_t it = 0;
-            for (long long t = blockIdx.x; t < n_tiles; t += tile_stride, ++it) {
+            for (long long t = tile_first; t < n_tiles; t += tile_stride, ++it) {
                 const long long f0 = t * kWarp;
                 const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
                 mbar_wait_long(stage_full, it & 1);
@@ -334,7 +340,7 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
                 const uint32_t rbytes = static_cast<uint32_t>(nrows * rpitch * 4), pbytes = static_cast<uint32_t>(nrows * ppitch * 4);
                 // a full tile is two multiples of 128 bytes; a remainder tile can leave up to 3 words past the
                 // last 16-byte unit, stored directly
-                if (st_hint) {
+                if (st_hint & 1) {
                     const uint64_t pol = l2_policy_evict_first();
                     if (rbytes & ~15u) bulk_store_hint(rg, smem_u32(Rst), rbytes & ~15u, pol);
                     if (pbytes & ~15u) bulk_store_hint(pg, smem_u32(Pst), pbytes & ~15u, pol);
@@ -360,7 +366,7 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
     cx.full0 = full0, cx.empty0 = empty0, cx.stage_full = stage_full, cx.stage_free = stage_free;
     cx.fence_word = stage_free + 8 + 4 * threadIdx.x;
     cx.gpos = gpos, cx.gstride = gstride, cx.n_frames = n_frames, cx.n_tiles = n_tiles, cx.tile_stride = tile_stride;
-    cx.first_tile = blockIdx.x, cx.n_joints = n_joints, cx.lane = lane;
+    cx.first_tile = tile_first, cx.n_joints = n_joints, cx.lane = lane;
     if (warp == 0) fk_row_walk<S, VEC, 0>(cx);
     else if (warp == 1) fk_row_walk<S, VEC, 1>(cx);
     else fk_row_walk<S, VEC, 2>(cx);

@@ -223,10 +223,10 @@ inline int fk_rows_teams(int stages, const FkArgs &a, const DeviceProps &dp) {
 }
 
 // ---- fk, lane = (frame, row) kernel (fk_lanes_kernel.cuh) ---------------------------------
-template <int FR, int WARPS>
-int launch_fk_lanes_cfg(const FkArgs &a, const DeviceProps &dp, int block_cap) {
-    auto kernel = pmb::fk_lanes_kernel<FR, WARPS>;
-    const int smem = pmb::fk_lanes_geom(FR, WARPS, a.n_joints).block_bytes;
+template <int FR, int WARPS, int NB>
+int launch_fk_lanes_nb(const FkArgs &a, const DeviceProps &dp, int block_cap) {
+    auto kernel = pmb::fk_lanes_kernel<FR, WARPS, NB>;
+    const int smem = pmb::fk_lanes_geom(FR, WARPS, a.n_joints, NB).block_bytes;
     if (smem > dp.smem_optin) return fail(PMB_ERR_SHAPE, "fk lane kernel: %d joints do not fit in shared memory", a.n_joints);
     int rc = set_smem(kernel, smem);
     if (rc) return rc;
@@ -238,12 +238,20 @@ int launch_fk_lanes_cfg(const FkArgs &a, const DeviceProps &dp, int block_cap) {
     if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk lane kernel does not fit on an SM (%d bytes of shared memory)", smem);
     per_sm = std::max(1, std::min(per_sm, block_cap));
     const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
-    note_variant("fk_lanes_kernel<FR=%d,WARPS=%d> grid=%lld (%d warps/SM) smem=%d", FR, WARPS, blocks, per_sm * WARPS, smem);
+    note_variant("fk_lanes_kernel<FR=%d,WARPS=%d,NB=%d> grid=%lld (%d warps/SM) smem=%d", FR, WARPS, NB, blocks, per_sm * WARPS, smem);
     kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos, a.rout,
                                                                         a.n_frames, a.n_joints, env_int("PMB_ST_HINT", 0),
                                                                         env_int("PMB_L2_PREFETCH", 0) ? a.rot : nullptr, *a.prog);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
+}
+
+template <int FR, int WARPS>
+int launch_fk_lanes_cfg(const FkArgs &a, const DeviceProps &dp, int block_cap, int n_boxes) {
+    const int nb = env_int("PMB_FK_NB", n_boxes);  // TMA boxes in flight per warp
+    if (nb == 3) return launch_fk_lanes_nb<FR, WARPS, 3>(a, dp, block_cap);
+    if (nb == 4) return launch_fk_lanes_nb<FR, WARPS, 4>(a, dp, block_cap);
+    return launch_fk_lanes_nb<FR, WARPS, 2>(a, dp, block_cap);
 }
 
 // Worst-case number of lanes of one stage store that fall into the same shared-memory bank: lane = (frame, row)
@@ -255,7 +263,7 @@ inline int fk_lanes_bank_degree(int fr, int n_joints) {
 }
 
 struct FkLanesPlan {
-    int fr = 0, warps = 0, frames_in_flight = 0;
+    int fr = 0, warps = 0, frames_in_flight = 0, n_boxes = 2, warps_sm = 0;
 };
 // The tile size / block shape that keeps the most frames in flight per SM (what the throughput of the large
 // skeletons follows): FR = 10 needs an even joint count, blocks of 1, 2 or 4 warps.
@@ -273,8 +281,17 @@ inline FkLanesPlan fk_lanes_plan(const FkArgs &a, const DeviceProps &dp) {
             const int degree = fk_lanes_bank_degree(fr, a.n_joints);
             const int weight = degree <= 1 ? 100 : degree == 2 ? 90 : degree == 3 ? 80 : 50;
             const int fif = warps_sm * fr * weight;
-            if (fif > best.frames_in_flight) best = {fr, warps, fif};
+            if (fif > best.frames_in_flight) best = {fr, warps, fif, 2, warps_sm};
         }
+    }
+    // A third TMA box per warp when it is free (same number of blocks per SM) and the SM is short of warps to hide
+    // the load latency with: measured +3.5 % at 65 joints (8 warps per SM), nothing at 40 joints (12 warps).
+    if (best.fr && best.warps_sm <= 8) {
+        auto blocks_of = [&](int nb) {
+            const int bytes = pmb::fk_lanes_geom(best.fr, best.warps, a.n_joints, nb).block_bytes;
+            return bytes > dp.smem_optin ? 0 : std::min(32, (dp.smem_optin + 1024) / (bytes + 1024));
+        };
+        if (blocks_of(3) == blocks_of(2)) best.n_boxes = 3;
     }
     return best;
 }
@@ -299,8 +316,10 @@ bool try_fk_lanes(const FkArgs &a, const DeviceProps &dp, int &rc, bool rows_pre
         if (fk_lanes_bank_degree(fr, a.n_joints) >= 4) return false;
     }
     const int cap = env_int("PMB_FK_BLOCKS_PER_SM", std::max(1, 12 / std::max(1, warps)));
-    if (fr == 10) rc = warps == 1 ? launch_fk_lanes_cfg<10, 1>(a, dp, cap) : warps == 2 ? launch_fk_lanes_cfg<10, 2>(a, dp, cap) : launch_fk_lanes_cfg<10, 4>(a, dp, cap);
-    else rc = warps == 1 ? launch_fk_lanes_cfg<8, 1>(a, dp, cap) : warps == 2 ? launch_fk_lanes_cfg<8, 2>(a, dp, cap) : launch_fk_lanes_cfg<8, 4>(a, dp, cap);
+    // the plan's ring depth only holds for the plan's own shape
+    const int nb = (fr == plan.fr && warps == plan.warps) ? plan.n_boxes : 2;
+    if (fr == 10) rc = warps == 1 ? launch_fk_lanes_cfg<10, 1>(a, dp, cap, nb) : warps == 2 ? launch_fk_lanes_cfg<10, 2>(a, dp, cap, nb) : launch_fk_lanes_cfg<10, 4>(a, dp, cap, nb);
+    else rc = warps == 1 ? launch_fk_lanes_cfg<8, 1>(a, dp, cap, nb) : warps == 2 ? launch_fk_lanes_cfg<8, 2>(a, dp, cap, nb) : launch_fk_lanes_cfg<8, 4>(a, dp, cap, nb);
     return true;
 }
 

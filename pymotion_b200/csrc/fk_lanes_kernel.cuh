@@ -32,17 +32,18 @@ namespace pmb {
 struct FkLanesGeom {
     int box_bytes, tab_bytes, warp_bytes, block_bytes;
 };
-__host__ __device__ inline FkLanesGeom fk_lanes_geom(int fr, int warps, int n_joints) {
+__host__ __device__ inline FkLanesGeom fk_lanes_geom(int fr, int warps, int n_joints, int n_boxes = 2) {
     FkLanesGeom g;
     g.box_bytes = fr * 128;                                    // FR frames x 8 joints x 16 bytes
     g.tab_bytes = ((n_joints + kChunk) * 16 + 127) & ~127;     // padded: the tail chunk and the one-ahead prefetch read past J
-    // per warp: 2 boxes | rotation stage | position stage | 2 mbarriers | 32 fence words
-    g.warp_bytes = ((2 * g.box_bytes + fr * 48 * n_joints + 16 + 128) + 127) & ~127;
+    // per warp: NB boxes | rotation stage | position stage | NB mbarriers (32 bytes reserved) | 32 fence words
+    g.warp_bytes = ((n_boxes * g.box_bytes + fr * 48 * n_joints + 32 + 128) + 127) & ~127;
     g.block_bytes = 128 + g.tab_bytes + warps * g.warp_bytes;
     return g;
 }
 
-template <int FR, int WARPS>
+// NB: TMA boxes in flight per warp (ring depth, 2 .. 4)
+template <int FR, int WARPS, int NB>
 __global__ void __launch_bounds__(WARPS *kWarp)
 fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                 const float *__restrict__ offsets, float *__restrict__ pos, float *__restrict__ rout,
@@ -53,16 +54,16 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    const FkLanesGeom geo = fk_lanes_geom(FR, WARPS, n_joints);
+    const FkLanesGeom geo = fk_lanes_geom(FR, WARPS, n_joints, NB);
 
     float4 *tab = reinterpret_cast<float4 *>(smem_raw);
     unsigned char *mine = smem_raw + geo.tab_bytes + warp * geo.warp_bytes;
     const float4 *boxes = reinterpret_cast<const float4 *>(mine);
-    float *Rst = reinterpret_cast<float *>(mine + 2 * BOX);
+    float *Rst = reinterpret_cast<float *>(mine + NB * BOX);
     float *Pst = Rst + FR * 9 * n_joints;
     const uint32_t box0 = smem_u32(mine);
-    const uint32_t bar0 = smem_u32(Pst + FR * 3 * n_joints);   // 2 mbarriers (8-byte aligned: all sizes above are multiples of 16)
-    const uint32_t fence_word = bar0 + 16 + 4 * lane;
+    const uint32_t bar0 = smem_u32(Pst + FR * 3 * n_joints);   // NB mbarriers (8-byte aligned: all sizes above are multiples of 16)
+    const uint32_t fence_word = bar0 + 32 + 4 * lane;
 
     // Joint table: offset (x, y, z) | parent index if the parent's row has to be fetched from the stage, -1 if it
     // is the previous joint (still in registers).  offsets[0] is ignored by the reference (the root translation
@@ -78,7 +79,8 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
         tab[j] = e;
     }
     if (lane == 0) {
-        mbar_init(bar0, 1), mbar_init(bar0 + 8, 1);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) mbar_init(bar0 + 8 * b, 1);
         fence_barrier_init();
     }
     __syncthreads();  // the table; from here on the warps never meet again
@@ -96,7 +98,7 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     // 128-byte hardware swizzle: 16-byte chunk c of box row r sits at chunk c ^ ((address >> 7) & 7); boxes are
     // only 128-byte aligned here, so the row's phase includes the box base
     const float4 *in_row0 = boxes + f * C;
-    const int swz0 = ((box0 >> 7) + f) & 7, swz1 = (((box0 + BOX) >> 7) + f) & 7;
+    const int swz_base = (box0 >> 7) + f;  // + box index * (BOX / 128)
     const float id0 = a == 0 ? 1.f : 0.f, id1 = a == 1 ? 1.f : 0.f, id2 = a == 2 ? 1.f : 0.f;
 
     // TMA producer (lane 0): the warp's chunks in processing order, across its tiles
@@ -110,7 +112,10 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             if (la_c0 >= n_joints) la_c0 = 0, la_tile += tile_stride;
         }
     };
-    if (lane == 0) issue_next(0), issue_next(1);
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) issue_next(b);
+    }
 
     float gnext = 0.f;  // root position component of the NEXT tile, fetched a tile early
     if (tile < n_tiles) gnext = __ldg(gpos + min(tile * FR + f, n_frames - 1) * gstride + a);
@@ -125,11 +130,11 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
 
         for (int c0 = 0; c0 < n_joints; c0 += C) {
             const int cnt = active ? n_joints - c0 : 0;  // joints left (>= 8 except in a partial last chunk); 0 = never store
-            const uint32_t buf = k & 1;
-            mbar_wait(bar0 + 8 * buf, (k >> 1) & 1);
+            const uint32_t buf = k % NB;
+            mbar_wait(bar0 + 8 * buf, (k / NB) & 1);
             ++k;
             const float4 *in_row = in_row0 + buf * (BOX / 16);
-            const int swz = buf ? swz1 : swz0;
+            const int swz = (swz_base + buf * (BOX / 128)) & 7;
             float4 q[C];
 #pragma unroll
             for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
@@ -140,7 +145,7 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
             }
             __syncwarp();
-            if (lane == 0) issue_next(buf);  // refill with the chunk two ahead (this tile's or the next tile's)
+            if (lane == 0) issue_next(buf);  // refill with the chunk NB ahead (this tile's or the next tile's)
             if (c0 == 0) {
                 const long long next_tile = tile + tile_stride;
                 if (next_tile < n_tiles) gnext = __ldg(gpos + min(next_tile * FR + f, n_frames - 1) * gstride + a);

@@ -27,6 +27,10 @@
 #include "fk_rows_kernel.cuh"  // rot_scale, load_parent_row_if, store_row_if, mbar_arrive
 #include "tma.cuh"
 
+#ifndef PMB_LANES_HOIST
+#define PMB_LANES_HOIST 0
+#endif
+
 namespace pmb {
 
 struct FkLanesGeom {
@@ -146,6 +150,14 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             }
             __syncwarp();
             if (lane == 0) issue_next(buf);  // refill with the chunk NB ahead (this tile's or the next tile's)
+#if PMB_LANES_HOIST
+            // the eight normalisation scales of the chunk, ahead of the walk and of the block boundary below (which
+            // keeps ptxas from sinking the MUFU chains back into the walk, where their latency showed as ~15 % of
+            // the warp's stall samples)
+            float sc[C];
+#pragma unroll
+            for (int jj = 0; jj < C; ++jj) sc[jj] = rot_scale(q[jj], 1e-8f);
+#endif
             if (c0 == 0) {
                 const long long next_tile = tile + tile_stride;
                 if (next_tile < n_tiles) gnext = __ldg(gpos + min(next_tile * FR + f, n_frames - 1) * gstride + a);
@@ -165,7 +177,11 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
                 const float4 e_next = tab[j + 1];
                 const int p = __float_as_int(e.w);  // parent whose row must come from the stage, or -1
                 load_parent_row_if(p, rrow + 36 * p, prow + 12 * p, r0, r1, r2, pp);
+#if PMB_LANES_HOIST
+                const float s = sc[jj];
+#else
                 const float s = rot_scale(q[jj], 1e-8f);
+#endif
                 const float w = q[jj].x, x = q[jj].y, y = q[jj].z, z = q[jj].w;
                 pp = r0 * e.x + r1 * e.y + r2 * e.z + pp;
                 const float cx_ = r1 * z - r2 * y, cy_ = r2 * x - r0 * z, cz_ = r0 * y - r1 * x;

@@ -179,10 +179,11 @@ def test_fk_full_size_1m_x_22_vs_c_oracle(sk):
         assert_allclose(rotm[sl].cpu().numpy(), want_rotm, **TOL)
 
 
-def test_fk_4m_x_65_invariants_and_slabs(sk):
-    """BASELINE config 4 (4M x 65, deep hierarchy): invariants on the full batch,
-    oracle on the first / last / a middle 64k-frame window."""
-    par = parents_of("deep65")
+@pytest.mark.parametrize("name", ["deep65", "smplh52"])
+def test_fk_4m_invariants_and_slabs(sk, name):
+    """BASELINE config 4 (4M x 65, deep hierarchy) and the per-GPU shard of config 5 (4M x 52): invariants on the
+    full batch, oracle on the first / last / a middle 64k-frame window."""
+    par = parents_of(name)
     dev = torch.device("cuda")
     n = 4_000_000
     rot, gp, off = synth_torch(n, par, dev, seed=4321)
@@ -519,3 +520,23 @@ def test_to_root_dual_quat_every_group(sk, monkeypatch, group, name, n_frames):
     rot, gp, off = synth_numpy(n_frames, par, seed=7 * len(par) + n_frames)
     dq = sk.to_root_dual_quat(rot, gp, par, off)
     assert_allclose(dq, orc.to_root_dual_quat(rot, gp, par, off), **TOL)
+
+
+def test_frame_shards_on_two_devices(sk):
+    """Section 8e: the frame axis shards with no data-path collective.  Two shards computed on two GPUs of the box
+    (one process, the library's per-device state) equal the single-GPU result bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from pymotion_b200.sharding import shard_bounds
+
+    par = parents_of("body22")
+    n = 100_003
+    rot, gp, off = synth_numpy(n, par, seed=99)
+    full_pos, full_rotm = sk.fk(torch.from_numpy(rot).cuda(0), torch.from_numpy(gp).cuda(0), torch.from_numpy(off).cuda(0), par)
+    for rank in range(2):
+        lo, hi = shard_bounds(n, 2, rank)
+        dev = torch.device("cuda", rank)
+        pos, rotm = sk.fk(torch.from_numpy(rot[lo:hi]).to(dev), torch.from_numpy(gp[lo:hi]).to(dev), torch.from_numpy(off).to(dev), par)
+        assert pos.device == dev
+        assert torch.equal(pos.cpu(), full_pos[lo:hi].cpu())
+        assert torch.equal(rotm.cpu(), full_rotm[lo:hi].cpu())

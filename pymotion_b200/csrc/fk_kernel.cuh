@@ -101,7 +101,7 @@ __device__ __forceinline__ void copy_out_periodic(const float *__restrict__ stag
     constexpr int P = L / 32;     // stores per period
     constexpr int RPP = L / WV;   // rows per period
     static_assert(32 % RPP == 0 && P <= 9, "group geometry must give a short period");
-    using V = typename std::conditional<VEC == 2, float2, float>::type;
+    using V = typename std::conditional<VEC == 4, float4, typename std::conditional<VEC == 2, float2, float>::type>::type;
     int soff[P], goff[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) {

@@ -175,7 +175,9 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             for (int jj = 0; jj < C; ++jj) {
                 const int j = c0 + jj;
                 const float4 e_next = tab[j + 1];
-                const int p = __float_as_int(e.w);  // parent whose row must come from the stage, or -1
+                // parent whose row must come from the stage, or -1; the idle lanes (which shadow lane 0's addresses)
+                // never read the stage
+                const int p = active ? __float_as_int(e.w) : -1;
                 load_parent_row_if(p, rrow + 36 * p, prow + 12 * p, r0, r1, r2, pp);
 #if PMB_LANES_HOIST
                 const float s = sc[jj];

@@ -14,9 +14,20 @@
 // `group` joints.  Algorithmic HBM traffic: 44*J + 12 bytes per pose (16J + 12 in, 16J + 12J out).
 #pragma once
 #include "common.cuh"
+#include "fk_kernel.cuh"  // copy_out_periodic
 #include "tma.cuh"
 
 namespace pmb {
+
+// Full flush groups of the common sizes go out with the short-period lane map of fk_kernel.cuh (a lane's stage /
+// global offsets repeat every few stores, so each store costs LDS + STG instead of a division and two multiplies:
+// the generic loop was ~30 % of this kernel's instructions).
+template <int G, bool POS>
+__device__ __forceinline__ void fkq_flush_full(const float4 *qstage, const float *pstage, float4 *gq, float *gp, int n_joints,
+                                               int lane) {
+    copy_out_periodic<4 * G, 4 * (G | 1), 4>(reinterpret_cast<const float *>(qstage), reinterpret_cast<float *>(gq), 4 * n_joints, lane);
+    if (POS) copy_out_periodic<3 * G, (3 * G) | 1, 1>(pstage, gp, 3 * n_joints, lane);
+}
 
 struct FkqGeom {
     int stride4;      // quaternion stage row stride in float4
@@ -175,28 +186,39 @@ fk_quat_chain_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__
             if (gj == group || last_chunk) {
                 __syncwarp();
                 const int g0 = c0 + cnt - gj;  // first joint of the group
-                {   // quaternions: rows of gj float4 -> global rows of pitch n_joints float4
-                    const uint32_t magic = (gj == group) ? magic_q_full : magic_q_tail;
-                    const int n4 = nrows * gj;
-                    float4 *g = grot + f0 * n_joints + g0;
+                float4 *gq = grot + f0 * n_joints + g0;
+                float *gpp = POS ? pos + (f0 * n_joints + g0) * 3 : nullptr;
+                const bool full = gj == group && nrows == kWarp;
+                if (full && group == 16) {
+                    fkq_flush_full<16, POS>(qstage, pstage, gq, gpp, n_joints, lane);
+                } else if (full && group == 8) {
+                    fkq_flush_full<8, POS>(qstage, pstage, gq, gpp, n_joints, lane);
+                } else if (full && group == 24) {
+                    fkq_flush_full<24, POS>(qstage, pstage, gq, gpp, n_joints, lane);
+                } else if (full && group == 32) {
+                    fkq_flush_full<32, POS>(qstage, pstage, gq, gpp, n_joints, lane);
+                } else {
+                    {   // quaternions: rows of gj float4 -> global rows of pitch n_joints float4
+                        const uint32_t magic = (gj == group) ? magic_q_full : magic_q_tail;
+                        const int n4 = nrows * gj;
 #pragma unroll 4
-                    for (int i = lane; i < n4; i += kWarp) {
-                        // (a remainder group of ONE joint has no 32-bit magic: 2^32 / 1 + 1 wraps)
-                        const int r = gj == 1 ? i : static_cast<int>(__umulhi(static_cast<uint32_t>(i), magic));
-                        const int c = i - r * gj;
-                        g[static_cast<long long>(r) * n_joints + c] = qstage[r * S4 + c];
+                        for (int i = lane; i < n4; i += kWarp) {
+                            // (a remainder group of ONE joint has no 32-bit magic: 2^32 / 1 + 1 wraps)
+                            const int r = gj == 1 ? i : static_cast<int>(__umulhi(static_cast<uint32_t>(i), magic));
+                            const int c = i - r * gj;
+                            gq[static_cast<long long>(r) * n_joints + c] = qstage[r * S4 + c];
+                        }
                     }
-                }
-                if (POS) {  // positions: rows of 3*gj floats -> global rows of pitch 3*n_joints floats
-                    const uint32_t magic = (gj == group) ? magic_p_full : magic_p_tail;
-                    const int w = 3 * gj, n1 = nrows * w;
-                    float *g = pos + (f0 * n_joints + g0) * 3;
-                    const int pitch = 3 * n_joints;
+                    if (POS) {  // positions: rows of 3*gj floats -> global rows of pitch 3*n_joints floats
+                        const uint32_t magic = (gj == group) ? magic_p_full : magic_p_tail;
+                        const int w = 3 * gj, n1 = nrows * w;
+                        const int pitch = 3 * n_joints;
 #pragma unroll 4
-                    for (int i = lane; i < n1; i += kWarp) {
-                        const int r = static_cast<int>(__umulhi(static_cast<uint32_t>(i), magic));
-                        const int c = i - r * w;
-                        g[static_cast<long long>(r) * pitch + c] = pstage[r * SP + c];
+                        for (int i = lane; i < n1; i += kWarp) {
+                            const int r = static_cast<int>(__umulhi(static_cast<uint32_t>(i), magic));
+                            const int c = i - r * w;
+                            gpp[static_cast<long long>(r) * pitch + c] = pstage[r * SP + c];
+                        }
                     }
                 }
                 __syncwarp();

@@ -133,6 +133,7 @@ struct RowCtx {
     uint32_t rst, pst;            // shared addresses of the stage (rotation rows, positions)
     uint32_t full0, empty0, stage_full, stage_free, fence_word;
     const float *gpos;
+    float *pos, *rout;
     long long gstride, n_frames, n_tiles, tile_stride, first_tile;  // n_tiles here = end of this team's tile range
     int n_joints, lane;
 };
@@ -251,9 +252,26 @@ __device__ __forceinline__ void fk_row_walk(const RowCtx &cx) {
                 e = e_next;
             }
         }
-        fence_proxy_async_smem();  // this lane's stage writes -> visible to the async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(cx.stage_full);
+        const long long f0 = tile * kWarp;
+        if (cx.n_frames - f0 >= kWarp) {
+            fence_proxy_async_smem();  // this lane's stage writes -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cx.stage_full);
+        } else if (f0 + lane < cx.n_frames) {
+            // Remainder tile (the last tile of the batch, fewer than 32 frames): its span need not be a multiple of
+            // 16 bytes, so it does not go through the TMA engine.  Every lane copies out the rows IT wrote: no other
+            // thread touches them, nothing to synchronise.
+            float *rg = cx.rout + (f0 + lane) * 9 * n_joints + 3 * A;
+            float *pg = cx.pos + (f0 + lane) * 3 * n_joints + A;
+            for (int j = 0; j < n_joints; ++j) {
+                float v0, v1, v2, vp;
+                asm volatile("ld.shared.f32 %0, [%4];\n ld.shared.f32 %1, [%4+4];\n ld.shared.f32 %2, [%4+8];\n ld.shared.f32 %3, [%5];"
+                             : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(vp)
+                             : "r"(rrow + 36 * j), "r"(prow + 12 * j));
+                rg[9 * j] = v0, rg[9 * j + 1] = v1, rg[9 * j + 2] = v2;
+                pg[3 * j] = vp;
+            }
+        }
     }
 }
 
@@ -334,23 +352,20 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
             uint32_t it = 0;
             for (long long t = tile_first; t < n_tiles; t += tile_stride, ++it) {
                 const long long f0 = t * kWarp;
-                const int nrows = static_cast<int>(min(static_cast<long long>(kWarp), n_frames - f0));
+                if (n_frames - f0 < kWarp) break;  // the remainder tile is written by the row warps themselves
                 mbar_wait_long(stage_full, it & 1);
                 float *rg = rout + f0 * rpitch, *pg = pos + f0 * ppitch;
-                const uint32_t rbytes = static_cast<uint32_t>(nrows * rpitch * 4), pbytes = static_cast<uint32_t>(nrows * ppitch * 4);
-                // a full tile is two multiples of 128 bytes; a remainder tile can leave up to 3 words past the
-                // last 16-byte unit, stored directly
+                const uint32_t rbytes = static_cast<uint32_t>(kWarp * rpitch * 4), pbytes = static_cast<uint32_t>(kWarp * ppitch * 4);
+                // two contiguous, 128-byte aligned spans
                 if (st_hint & 1) {
                     const uint64_t pol = l2_policy_evict_first();
-                    if (rbytes & ~15u) bulk_store_hint(rg, smem_u32(Rst), rbytes & ~15u, pol);
-                    if (pbytes & ~15u) bulk_store_hint(pg, smem_u32(Pst), pbytes & ~15u, pol);
+                    bulk_store_hint(rg, smem_u32(Rst), rbytes, pol);
+                    bulk_store_hint(pg, smem_u32(Pst), pbytes, pol);
                 } else {
-                    if (rbytes & ~15u) bulk_store(rg, smem_u32(Rst), rbytes & ~15u);
-                    if (pbytes & ~15u) bulk_store(pg, smem_u32(Pst), pbytes & ~15u);
+                    bulk_store(rg, smem_u32(Rst), rbytes);
+                    bulk_store(pg, smem_u32(Pst), pbytes);
                 }
                 bulk_commit();
-                for (uint32_t w = (rbytes & ~15u) / 4; w < rbytes / 4; ++w) rg[w] = Rst[w];
-                for (uint32_t w = (pbytes & ~15u) / 4; w < pbytes / 4; ++w) pg[w] = Pst[w];
                 bulk_wait_read0();  // the engine has read the stage: the row warps may overwrite it
                 mbar_arrive(stage_free);
             }
@@ -365,6 +380,7 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
     cx.rst = smem_u32(Rst), cx.pst = smem_u32(Pst);
     cx.full0 = full0, cx.empty0 = empty0, cx.stage_full = stage_full, cx.stage_free = stage_free;
     cx.fence_word = stage_free + 8 + 4 * threadIdx.x;
+    cx.pos = pos, cx.rout = rout;
     cx.gpos = gpos, cx.gstride = gstride, cx.n_frames = n_frames, cx.n_tiles = n_tiles, cx.tile_stride = tile_stride;
     cx.first_tile = tile_first, cx.n_joints = n_joints, cx.lane = lane;
     if (warp == 0) fk_row_walk<S, VEC, 0>(cx);

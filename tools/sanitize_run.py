@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Small-shape pass over every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
+
+    compute-sanitizer --tool memcheck python tools/sanitize_run.py
+
+Checks results against the oracle too, so a sanitizer-clean run is also a correct one."""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+from oracle import pymotion_oracle as orc  # noqa: E402
+from pymotion_b200.ops import skeleton as sk  # noqa: E402
+from pymotion_b200.rotations import dual_quat as dq  # noqa: E402
+from pymotion_b200.rotations import quat  # noqa: E402
+from pymotion_b200.topologies import parents_of, synth_numpy  # noqa: E402
+
+KNOBS = [{}, {"PMB_FK_ROWS": "1"}, {"PMB_FK_ROWS": "1", "PMB_FK_STAGES": "3", "PMB_FK_BLOCKS_PER_SM": "1"},
+         {"PMB_FK_LANES": "1"}, {"PMB_FK_LANES": "1", "PMB_FK_NB": "3", "PMB_FK_BLOCKS_PER_SM": "1", "PMB_FK_WARPS": "1"},
+         {"PMB_FK_LANES": "0", "PMB_FK_ROWS": "0"}, {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "4"}]
+
+
+def main():
+    n_checked = 0
+    for name, frames in (("body22", 1203), ("smplh52", 611), ("deep65", 395), ("chain3", 77)):
+        par = parents_of(name)
+        rot, gp, off = synth_numpy(frames, par, seed=frames)
+        want_pos, want_rotm = orc.fk(rot, gp, off, par)
+        for knobs in KNOBS:
+            for k in [k for k in os.environ if k.startswith("PMB_")]:
+                os.environ.pop(k)
+            os.environ.update(knobs)
+            pos, rotm = sk.fk(rot, gp, off, par)
+            np.testing.assert_allclose(pos, want_pos, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(rotm, want_rotm, rtol=1e-5, atol=1e-5)
+            n_checked += 1
+        for k in [k for k in os.environ if k.startswith("PMB_")]:
+            os.environ.pop(k)
+        p2, gq = sk.fk_quat(rot, gp, off, par)
+        np.testing.assert_allclose(p2, want_pos, rtol=1e-5, atol=1e-5)
+        d = sk.to_root_dual_quat(rot, gp, par, off)
+        np.testing.assert_allclose(d, orc.to_root_dual_quat(rot, gp, par, off), rtol=1e-5, atol=1e-5)
+        t, r = sk.from_root_dual_quat(d, par)
+        np.testing.assert_allclose(r, rot, rtol=1e-5, atol=1e-5)
+        sk.from_global_rotations(gq, par)
+        centred = (want_pos - want_pos[:, :1]).astype(np.float32)
+        sk.from_root_positions(centred, par, off)
+        for mode in ("all", "positions"):
+            sk.mirror(rot, gp, par, off, mode=mode)
+        quat.unroll(rot, 0)
+        dq.unroll(d, 0)
+        dq.normalize(d)
+        dq.is_unit(d)
+        quat.to_matrix(rot)
+        quat.slerp(rot, rot[::-1].copy(), 0.3)
+        n_checked += 12
+    print(f"sanitize_run ok: {n_checked} kernel-family launches checked")
+
+
+if __name__ == "__main__":
+    main()

@@ -8,8 +8,8 @@
 // carries three times as many warps (what limits 52- and 65-joint skeletons: the stage is 1536 J bytes per
 // tile whatever the mapping), and the chain state is 4 registers.  No local matrix is formed: a row times
 // R(q^) is the row rotated by the conjugate quaternion (two cross products), and the normalisation of q
-// collapses into one scale 2 / (|q| + eps)^2 per joint, computed for a whole chunk ahead of the branchy
-// tree walk.
+// collapses into one scale 2 / (|q| + eps)^2 per joint.  The walk is branch free (predicated PTX for the parent
+// fetch and the tail-chunk guard).
 //
 //   in    a loader thread streams the tile's quaternions as TMA boxes of 8 joints x 32 frames (128-byte
 //         swizzle) through an S-deep ring; full / empty mbarriers, the three row warps release a box as soon
@@ -19,7 +19,8 @@
 //         tile's output, so it already holds every ancestor: no slots;
 //   out   the stage (32 x 36J and 32 x 12J bytes, both multiples of 128) is handed to the TMA engine by a
 //         drainer thread as two contiguous line-aligned bulk stores while the row warps wait for
-//         `stage_free`; the other teams on the SM cover the drain.
+//         `stage_free`; the other teams on the SM cover the drain.  The remainder tile of a batch (fewer than 32
+//         frames: its span need not be a multiple of 16 bytes) is copied out by the lanes that wrote it.
 //
 // Block = 1 team = 5 warps: rows 0..2, loader, drainer.  Algorithmic HBM traffic 64*J + 12 bytes per pose.
 #pragma once

@@ -18,6 +18,7 @@
 #include "fk_quat_kernel.cuh"
 #include "fk_rows_kernel.cuh"
 #include "fk_lanes_kernel.cuh"
+#include "fk_lanes_g_kernel.cuh"
 #include "ik_kernels.cuh"
 #include "joint_program.h"
 #include "misc_ops.cuh"
@@ -254,6 +255,42 @@ int launch_fk_lanes_cfg(const FkArgs &a, const DeviceProps &dp, int block_cap, i
     return launch_fk_lanes_nb<FR, WARPS, 2>(a, dp, block_cap);
 }
 
+// ---- fk, lane kernel with a grouped stage (fk_lanes_g_kernel.cuh) ---------------------------
+template <int NB, int G>
+int launch_fk_lanes_g_cfg(const FkArgs &a, const DeviceProps &dp) {
+    constexpr int FR = 10, WARPS = 4;
+    auto kernel = pmb::fk_lanes_g_kernel<FR, WARPS, NB, G>;
+    const int smem = pmb::fk_lanes_g_geom(FR, WARPS, a.n_joints, a.n_slots, NB, G).block_bytes;
+    if (smem > dp.smem_optin)
+        return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
+    int rc = set_smem(kernel, smem);
+    if (rc) return rc;
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk, FR))) return rc;
+    const long long tiles = (a.n_frames + FR - 1) / FR;
+    int per_sm = 0;
+    PMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk grouped lane kernel does not fit on an SM (%d bytes of shared memory)", smem);
+    per_sm = std::max(1, std::min(per_sm, env_int("PMB_FK_BLOCKS_PER_SM", 3)));  // 12 walking warps per SM
+    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
+    note_variant("fk_lanes_g_kernel<FR=%d,WARPS=%d,NB=%d,G=%d> grid=%lld (%d warps/SM) smem=%d", FR, WARPS, NB, G, blocks,
+                 per_sm * WARPS, smem);
+    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos, a.rout,
+                                                                        a.n_frames, a.n_joints, a.n_slots, *a.prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// PMB_FK_LG = 16 | 32 forces the grouped lane kernel with that flush group (experiments / tests); PMB_FK_NB = 2 | 3.
+bool try_fk_lanes_g(const FkArgs &a, const DeviceProps &dp, int &rc) {
+    const int g = env_int("PMB_FK_LG", 0);
+    if (g != 16 && g != 32) return false;
+    const int nb = env_int("PMB_FK_NB", 2);
+    if (g == 32) rc = nb == 3 ? launch_fk_lanes_g_cfg<3, 32>(a, dp) : launch_fk_lanes_g_cfg<2, 32>(a, dp);
+    else rc = nb == 3 ? launch_fk_lanes_g_cfg<3, 16>(a, dp) : launch_fk_lanes_g_cfg<2, 16>(a, dp);
+    return true;
+}
+
 // Worst-case number of lanes of one stage store that fall into the same shared-memory bank: lane = (frame, row)
 // puts the frames of a tile 9J words apart, so only (9J mod 32) matters.  1 = conflict free.
 inline int fk_lanes_bank_degree(int fr, int n_joints) {
@@ -477,6 +514,7 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
              static_cast<cudaStream_t>(stream)};
     if (ostride == 0 && !quat_out) {
         int rrc = PMB_OK;
+        if (try_fk_lanes_g(a, dp, rrc)) return rrc;
         const bool rows_first = fk_rows_preferred(a, dp) && env_int("PMB_FK_ROWS", -1) != 0;
         if (try_fk_lanes(a, dp, rrc, rows_first || env_int("PMB_FK_ROWS", -1) == 1)) return rrc;
         if (try_fk_rows(a, dp, rrc)) return rrc;

@@ -89,18 +89,18 @@ __host__ __device__ inline FkGeom fk_geom(int group, int vec, int rw, int warps,
     return g;
 }
 
-// Warp-cooperative copy of a FULL padded stage (32 rows x W words, row stride S) to global rows of
+// Warp-cooperative copy of a FULL padded stage (ROWS rows x W words, row stride S) to global rows of
 // pitch `pitch` words, in units of VEC words.  Store k of the warp serves flat unit 32k + lane ->
 // (row, column); that map repeats every P stores / RPP rows, so a lane computes its P offsets once
 // and each store costs LDS + STG.
-template <int W, int S, int VEC>
+template <int W, int S, int VEC, int ROWS = 32>
 __device__ __forceinline__ void copy_out_periodic(const float *__restrict__ stage, float *__restrict__ gtile, int pitch,
                                                   int lane) {
     constexpr int WV = W / VEC;
     constexpr int L = ce_lcm(32, WV);
     constexpr int P = L / 32;     // stores per period
     constexpr int RPP = L / WV;   // rows per period
-    static_assert(32 % RPP == 0 && P <= 9, "group geometry must give a short period");
+    static_assert(ROWS % RPP == 0 && P <= 9, "group geometry must give a short period");
     using V = typename std::conditional<VEC == 4, float4, typename std::conditional<VEC == 2, float2, float>::type>::type;
     int soff[P], goff[P];
 #pragma unroll
@@ -111,7 +111,7 @@ __device__ __forceinline__ void copy_out_periodic(const float *__restrict__ stag
         goff[k] = dr * pitch + col * VEC;
     }
 #pragma unroll 2
-    for (int g = 0; g < 32 / RPP; ++g) {
+    for (int g = 0; g < ROWS / RPP; ++g) {
         V v[P];
 #pragma unroll
         for (int k = 0; k < P; ++k) v[k] = *reinterpret_cast<const V *>(stage + g * RPP * S + soff[k]);

@@ -511,6 +511,28 @@ def test_fk_lane_kernel(sk, monkeypatch, knobs, name, n_frames):
         assert_allclose(rotm, want_rotm, **TOL)
 
 
+@pytest.mark.parametrize("knobs", [
+    {"PMB_FK_LG": "32"},
+    {"PMB_FK_LG": "16"},
+    {"PMB_FK_LG": "32", "PMB_FK_NB": "3", "PMB_FK_BLOCKS_PER_SM": "1"},   # many tiles per warp, deeper ring
+    {"PMB_FK_LG": "16", "PMB_FK_NB": "3"},
+])
+@pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
+                                           ("body32", 5_009), ("body40", 3_001), ("body22", 7)])
+def test_fk_grouped_lane_kernel(sk, monkeypatch, knobs, name, n_frames):
+    """The lane kernel with a grouped stage (flush groups of 16 / 32 joints, branch rows in slots): every joint
+    count is bank-conflict free, remainder groups (22 = 16 + 6, 65 = 2 x 32 + 1) and remainder tiles included."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=7 * len(par) + n_frames)
+    want_pos, want_rotm = orc.fk(rot, gp, off, par)
+    for _ in range(2):
+        pos, rotm = sk.fk(rot, gp, off, par)
+        assert_allclose(pos, want_pos, **TOL)
+        assert_allclose(rotm, want_rotm, **TOL)
+
+
 @pytest.mark.parametrize("group", [None, "8", "16", "24"])
 @pytest.mark.parametrize("name,n_frames", [("body22", 4099), ("smplh52", 2050), ("deep65", 1031), ("chain3", 777)])
 def test_to_root_dual_quat_every_group(sk, monkeypatch, group, name, n_frames):

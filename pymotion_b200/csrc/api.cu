@@ -224,10 +224,10 @@ inline int fk_rows_teams(int stages, const FkArgs &a, const DeviceProps &dp) {
 }
 
 // ---- fk, lane = (frame, row) kernel (fk_lanes_kernel.cuh) ---------------------------------
-template <int FR, int WARPS, int NB>
+template <int FR, int WARPS, int NB, bool TILE_IN = false>
 int launch_fk_lanes_nb(const FkArgs &a, const DeviceProps &dp, int block_cap) {
-    auto kernel = pmb::fk_lanes_kernel<FR, WARPS, NB>;
-    const int smem = pmb::fk_lanes_geom(FR, WARPS, a.n_joints, NB).block_bytes;
+    auto kernel = pmb::fk_lanes_kernel<FR, WARPS, NB, TILE_IN>;
+    const int smem = pmb::fk_lanes_geom(FR, WARPS, a.n_joints, NB, TILE_IN).block_bytes;
     if (smem > dp.smem_optin) return fail(PMB_ERR_SHAPE, "fk lane kernel: %d joints do not fit in shared memory", a.n_joints);
     int rc = set_smem(kernel, smem);
     if (rc) return rc;
@@ -239,10 +239,11 @@ int launch_fk_lanes_nb(const FkArgs &a, const DeviceProps &dp, int block_cap) {
     if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk lane kernel does not fit on an SM (%d bytes of shared memory)", smem);
     per_sm = std::max(1, std::min(per_sm, block_cap));
     const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
-    note_variant("fk_lanes_kernel<FR=%d,WARPS=%d,NB=%d> grid=%lld (%d warps/SM) smem=%d", FR, WARPS, NB, blocks, per_sm * WARPS, smem);
+    note_variant("fk_lanes_kernel<FR=%d,WARPS=%d,NB=%d,TILE_IN=%d> grid=%lld (%d warps/SM) smem=%d", FR, WARPS, NB, int(TILE_IN), blocks,
+                 per_sm * WARPS, smem);
     kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos, a.rout,
                                                                         a.n_frames, a.n_joints, env_int("PMB_ST_HINT", 0),
-                                                                        env_int("PMB_L2_PREFETCH", 0) ? a.rot : nullptr, *a.prog);
+                                                                        (TILE_IN || env_int("PMB_L2_PREFETCH", 0)) ? a.rot : nullptr, *a.prog);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
@@ -250,6 +251,10 @@ int launch_fk_lanes_nb(const FkArgs &a, const DeviceProps &dp, int block_cap) {
 template <int FR, int WARPS>
 int launch_fk_lanes_cfg(const FkArgs &a, const DeviceProps &dp, int block_cap, int n_boxes) {
     const int nb = env_int("PMB_FK_NB", n_boxes);  // TMA boxes in flight per warp
+    if (env_int("PMB_FK_TILE_IN", 0) == 1 && a.n_joints % 4 != 0) {  // whole-tile contiguous input (experiment)
+        if (nb == 3) return launch_fk_lanes_nb<FR, WARPS, 3, true>(a, dp, block_cap);
+        return launch_fk_lanes_nb<FR, WARPS, 2, true>(a, dp, block_cap);
+    }
     if (nb == 3) return launch_fk_lanes_nb<FR, WARPS, 3>(a, dp, block_cap);
     if (nb == 4) return launch_fk_lanes_nb<FR, WARPS, 4>(a, dp, block_cap);
     return launch_fk_lanes_nb<FR, WARPS, 2>(a, dp, block_cap);

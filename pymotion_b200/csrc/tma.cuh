@@ -46,6 +46,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (contiguous range, multiple of 16 bytes), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(gsrc),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 // 1-D bulk copy shared -> global (TMA engine, no register traffic); completion tracked per thread by bulk groups
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {

@@ -494,6 +494,8 @@ def test_fk_quat_every_variant(sk, monkeypatch, knobs, name, n_frames):
     {"PMB_FK_LANES": "1", "PMB_FK_WARPS": "2", "PMB_FK_BLOCKS_PER_SM": "1"},  # many tiles per warp
     {"PMB_FK_LANES": "1", "PMB_FK_NB": "3"},                               # deeper TMA ring
     {"PMB_FK_LANES": "1", "PMB_FK_NB": "4", "PMB_FK_WARPS": "1"},
+    {"PMB_FK_LANES": "1", "PMB_FK_TILE_IN": "1"},                          # whole-tile contiguous input
+    {"PMB_FK_LANES": "1", "PMB_FK_TILE_IN": "1", "PMB_FK_NB": "3", "PMB_FK_BLOCKS_PER_SM": "1"},
 ])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
                                            ("body32", 5_009), ("body22", 7)])

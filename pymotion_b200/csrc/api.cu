@@ -534,6 +534,9 @@ inline int ew_grid(int64_t n, int threads, const DeviceProps &dp) {
     return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(dp.sm_count) * 16)));
 }
 
+// divisor of div_small (dq_kernels.cuh): floor(2^32 / d) + 1, and 0 for d = 1 (which has no 32-bit magic)
+inline uint32_t magic_small(int d) { return d <= 1 ? 0u : static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(d)) + 1u; }
+
 int tile_frames(int n_joints, int cap_elems) {
     int fb = (cap_elems / n_joints) & ~3;
     return std::max(4, std::min(64, fb));
@@ -701,7 +704,7 @@ int pmb_from_root_dual_quat_f32(const float *dq, const int64_t *parents_host, in
     if ((rc = set_smem(kernel, smem))) return rc;
     const long long blocks = (n_frames + fb - 1) / fb;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
-    const uint32_t magic = static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(n_joints)) + 1u;
+    const uint32_t magic = magic_small(n_joints);
     kernel<<<static_cast<unsigned>(blocks), THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4 *>(dq), translations, reinterpret_cast<float4 *>(rotations), n_frames, n_joints,
         fb, magic, prog);
@@ -725,7 +728,7 @@ int pmb_from_global_rotations_f32(const float *global_quats, const int64_t *pare
     const int smem = (n_joints * 2 + 15) & ~15;
     const long long blocks = (n_frames + fb - 1) / fb;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
-    const uint32_t magic = static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(n_joints)) + 1u;
+    const uint32_t magic = magic_small(n_joints);
     pmb::from_global_rotations_kernel<THREADS><<<static_cast<unsigned>(blocks), THREADS, smem,
                                                  static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4 *>(global_quats), reinterpret_cast<float4 *>(local_quats), n_frames, n_joints, fb,
@@ -1080,7 +1083,7 @@ int pmb_mirror_to_local_f32(const float *global_quats, const int64_t *parents_ho
     const int fb = tile_frames(n_joints, 4096);
     const long long blocks = (n_frames + fb - 1) / fb;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
-    const uint32_t magic = static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(n_joints)) + 1u;
+    const uint32_t magic = magic_small(n_joints);
     // the two vector components that change sign (skeleton.py:307-315): X -> (y, z), Y -> (x, z), Z -> (x, y)
     const float fx = mirror_axis == 0 ? 1.f : -1.f, fy = mirror_axis == 1 ? 1.f : -1.f, fz = mirror_axis == 2 ? 1.f : -1.f;
     pmb::mirror_to_local_kernel<THREADS><<<static_cast<unsigned>(blocks), THREADS, (4 * n_joints + 15) & ~15, static_cast<cudaStream_t>(stream)>>>(

@@ -179,9 +179,12 @@ to_root_dq_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__res
 
 // ---------------------------------------------------------------------------
 // Tiles of FB frames x J joints handled by one block, one thread per element.
-// i / J for i < 2^16 through a multiply-high (magic = floor(2^32 / J) + 1).
+// i / J for i < 2^16 through a multiply-high (magic = floor(2^32 / J) + 1; J = 1 has no 32-bit magic and is
+// passed as 0).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int div_small(int i, uint32_t magic) { return static_cast<int>(__umulhi(static_cast<uint32_t>(i), magic)); }
+__device__ __forceinline__ int div_small(int i, uint32_t magic) {
+    return magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(i), magic)) : i;
+}
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)

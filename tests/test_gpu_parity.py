@@ -333,6 +333,38 @@ def test_from_global_rotations(sk, golden_dq):
     assert_allclose(np.abs(np.sum(local * rot, axis=-1)), 1.0, atol=1e-5)
 
 
+@pytest.mark.parametrize("n_frames", [1, 33, 1000, 5001])
+def test_single_joint_skeleton_every_op(sk, n_frames):
+    """A skeleton of ONE joint (parents = [0]) through every op of the path: the element-per-thread kernels divide by
+    the joint count with a multiply-high, and 1 is the divisor that has no 32-bit magic."""
+    par = np.array([0])
+    rng = np.random.default_rng(n_frames)
+    rot = rng.normal(size=(n_frames, 1, 4)).astype(np.float32)
+    rot /= np.linalg.norm(rot, axis=-1, keepdims=True)
+    gp = rng.normal(size=(n_frames, 3)).astype(np.float32)
+    off = np.zeros((1, 3), np.float32)
+    pos, rotm = sk.fk(rot, gp, off, par)
+    wp, wr = orc.fk(rot, gp, off, par)
+    assert_allclose(pos, wp, **TOL)
+    assert_allclose(rotm, wr, **TOL)
+    pos_q, grot = sk.fk_quat(rot, gp, off, par)
+    assert_allclose(pos_q, wp, **TOL)
+    assert_allclose(np.abs(np.sum(grot * rot, axis=-1)), 1.0, atol=1e-5)
+    dq = sk.to_root_dual_quat(rot, gp, par, off)
+    want = orc.to_root_dual_quat(rot, gp, par, off)
+    assert_allclose(dq, want, **TOL)
+    trans, rots = sk.from_root_dual_quat(want.astype(np.float32), par)
+    wt, wq = orc.from_root_dual_quat(want, par)
+    assert_allclose(trans, wt, **TOL)
+    assert_allclose(rots, wq, **TOL)
+    assert_allclose(sk.from_global_rotations(rot, par), orc.from_global_rotations(rot, par), **TOL)
+    r, t, o, _ = sk.mirror(rot, gp, par, off, mode="all", axis="X")
+    mr, mt, mo, _ = orc.mirror(rot, gp, par, off, mode="all", axis="X")
+    assert_allclose(np.abs(np.sum(r * mr, axis=-1)), 1.0, atol=1e-5)
+    assert_allclose(t, mt, atol=0)
+    assert_allclose(o, mo, atol=0)
+
+
 # ---------------------------------------------------------------- primitives
 def test_quat_primitives_vs_reference(quat, dquat, golden_quat):
     g = golden_quat

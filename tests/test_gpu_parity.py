@@ -333,6 +333,32 @@ def test_from_global_rotations(sk, golden_dq):
     assert_allclose(np.abs(np.sum(local * rot, axis=-1)), 1.0, atol=1e-5)
 
 
+def test_random_trees_every_chain_op(sk):
+    """Random joint orders (2 .. 512 joints, branches up to 6 joints back) through the other walks of the path:
+    fk_quat, to / from_root_dual_quat, from_global_rotations.  Deep chains accumulate rounding, so the tolerance
+    scales with the size of the values."""
+    rng = np.random.default_rng(11)
+    for n_joints in (2, 7, 8, 40, 129, 512):
+        par = np.zeros(n_joints, dtype=np.int64)
+        for i in range(1, n_joints):
+            par[i] = rng.integers(max(0, i - 6), i)
+        rot, gp, off = synth_numpy(70, par, seed=1000 + n_joints)
+        rot = (rot / np.linalg.norm(rot, axis=-1, keepdims=True)).astype(np.float32)
+        want_pos, want_rotm = orc.fk(rot, gp, off, par)
+        pos, grot = sk.fk_quat(rot, gp, off, par)
+        assert_allclose(pos, want_pos, rtol=RTOL, atol=ATOL * max(1.0, np.abs(want_pos).max()))
+        assert_allclose(orc.quat_to_matrix(grot.astype(np.float64)), want_rotm, rtol=RTOL, atol=5 * ATOL)
+        local = sk.from_global_rotations(grot, par)
+        assert_allclose(np.abs(np.sum(local * rot, axis=-1)), 1.0, atol=5 * ATOL)
+        dq = sk.to_root_dual_quat(rot, gp, par, off)
+        want = orc.to_root_dual_quat(rot, gp, par, off)
+        assert_allclose(dq, want, rtol=RTOL, atol=5 * ATOL * max(1.0, np.abs(want).max()))
+        trans, rots = sk.from_root_dual_quat(want.astype(np.float32), par)
+        wt, wr = orc.from_root_dual_quat(want.astype(np.float32), par)
+        assert_allclose(trans, wt, rtol=RTOL, atol=5 * ATOL * max(1.0, np.abs(want).max()))
+        assert_allclose(rots, wr, rtol=RTOL, atol=5 * ATOL)
+
+
 @pytest.mark.parametrize("n_frames", [1, 33, 1000, 5001])
 def test_single_joint_skeleton_every_op(sk, n_frames):
     """A skeleton of ONE joint (parents = [0]) through every op of the path: the element-per-thread kernels divide by

@@ -25,26 +25,40 @@ KNOBS = [{}, {"PMB_FK_ROWS": "1"}, {"PMB_FK_ROWS": "1", "PMB_FK_STAGES": "3", "P
 
 def main():
     n_checked = 0
-    for name, frames in (("body22", 1203), ("smplh52", 611), ("deep65", 395), ("chain3", 77)):
-        par = parents_of(name)
+    rng = np.random.default_rng(3)
+    shapes = [(parents_of(name), frames) for name, frames in (("body22", 1203), ("smplh52", 611), ("deep65", 395), ("chain3", 77))]
+    shapes.append((np.array([0]), 70))  # a single joint
+    for n_joints, frames in ((129, 45), (512, 40)):  # random joint orders, up to the largest skeleton the ABI takes
+        par = np.zeros(n_joints, dtype=np.int64)
+        for i in range(1, n_joints):
+            par[i] = rng.integers(max(0, i - 6), i)
+        shapes.append((par, frames))
+    for par, frames in shapes:
         rot, gp, off = synth_numpy(frames, par, seed=frames)
+        rot = (rot / np.linalg.norm(rot, axis=-1, keepdims=True)).astype(np.float32)
         want_pos, want_rotm = orc.fk(rot, gp, off, par)
+        scale = max(1.0, float(np.abs(want_pos).max()))  # deep chains accumulate rounding
         for knobs in KNOBS:
             for k in [k for k in os.environ if k.startswith("PMB_")]:
                 os.environ.pop(k)
             os.environ.update(knobs)
-            pos, rotm = sk.fk(rot, gp, off, par)
-            np.testing.assert_allclose(pos, want_pos, rtol=1e-5, atol=1e-5)
-            np.testing.assert_allclose(rotm, want_rotm, rtol=1e-5, atol=1e-5)
+            try:
+                pos, rotm = sk.fk(rot, gp, off, par)
+            except Exception as e:  # a FORCED variant may not fit the largest skeletons; the default policy must
+                if knobs and ("fit" in str(e) or "variant" in str(e)):
+                    continue
+                raise
+            np.testing.assert_allclose(pos, want_pos, rtol=1e-5, atol=1e-5 * scale)
+            np.testing.assert_allclose(rotm, want_rotm, rtol=1e-5, atol=5e-5)
             n_checked += 1
         for k in [k for k in os.environ if k.startswith("PMB_")]:
             os.environ.pop(k)
         p2, gq = sk.fk_quat(rot, gp, off, par)
-        np.testing.assert_allclose(p2, want_pos, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(p2, want_pos, rtol=1e-5, atol=1e-5 * scale)
         d = sk.to_root_dual_quat(rot, gp, par, off)
-        np.testing.assert_allclose(d, orc.to_root_dual_quat(rot, gp, par, off), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(d, orc.to_root_dual_quat(rot, gp, par, off), rtol=1e-5, atol=5e-5 * scale)
         t, r = sk.from_root_dual_quat(d, par)
-        np.testing.assert_allclose(r, rot, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(r, rot, rtol=1e-5, atol=5e-5)
         sk.from_global_rotations(gq, par)
         centred = (want_pos - want_pos[:, :1]).astype(np.float32)
         sk.from_root_positions(centred, par, off)

@@ -316,12 +316,38 @@ def run_ours(args):
     value = world * frames * args.steps / (ms_max * 1e-3)
 
     if args.kernel_only:
+        gather = None
+        if args.all_gather and world > 1:
+            # the OPTIONAL exchange of SURVEY 8e: every rank ends up with the positions of all frames (NCCL all-gather
+            # of equal frame blocks).  Timed on its own, never part of poses/s.
+            from pymotion_b200 import sharding
+
+            for _ in range(2):
+                full = sharding.all_gather_frames(pos, frames * world)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            g0.record(stream)
+            for _ in range(reps):
+                full = sharding.all_gather_frames(pos, frames * world)
+            g1.record(stream)
+            torch.cuda.synchronize(dev)
+            tg = torch.tensor([g0.elapsed_time(g1) / reps], device=dev, dtype=torch.float64)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            same = bool(torch.equal(full[rank * frames:(rank + 1) * frames], pos))
+            shard_bytes = pos.numel() * 4
+            gather = {"ms": float(tg.item()), "shard_bytes": shard_bytes, "received_bytes_per_rank": shard_bytes * (world - 1),
+                      "GBps_received_per_rank": shard_bytes * (world - 1) / (float(tg.item()) * 1e-3) / 1e9,
+                      "own_block_intact": same, "includes": "NCCL all_gather_into_tensor into one [F, J, 3] array (equal shards: no extra copy)"}
+            del full
         if rank == 0:
             bytes_per_launch = op_bytes_per_pose(args.op, n_joints) * frames
             kernel_ms = ms_max / args.steps
-            print(json.dumps({"workload": args.workload, "op": args.op, "ms_per_step": kernel_ms, "value": value,
-                              "GBps": bytes_per_launch / (kernel_ms * 1e-3) / 1e9,
-                              "env_chunk": os.environ.get("PMB_FK_CHUNK")}), flush=True)
+            line = {"workload": args.workload, "op": args.op, "n_gpus": world, "ms_per_step": kernel_ms, "value": value,
+                    "GBps": bytes_per_launch / (kernel_ms * 1e-3) / 1e9, "env_chunk": os.environ.get("PMB_FK_CHUNK")}
+            if gather:
+                line["all_gather_positions"] = gather
+            print(json.dumps(line), flush=True)
         sampler.stop_flag.set()
         if world > 1:
             dist.destroy_process_group()
@@ -436,6 +462,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="development: skip the e2e and CPU legs")
     ap.add_argument("--op", default="fk", choices=DEV_OPS, help="with --kernel-only: which op of the path to time")
+    ap.add_argument("--all-gather", action="store_true",
+                    help="with --kernel-only under torchrun: also time the optional all-gather of positions")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

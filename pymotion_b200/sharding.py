@@ -41,7 +41,12 @@ def all_gather_frames(local: torch.Tensor, n_frames: int, group=None) -> torch.T
         padded = torch.zeros((biggest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         padded[: local.shape[0]] = local
     out = torch.empty((world, biggest) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather(list(out.unbind(0)), padded.contiguous(), group=group)  # equal counts: ring / NVLS on NCCL, works on gloo
+    if local.is_cuda:  # NCCL writes every block straight into its place of the one output buffer
+        dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), padded.contiguous(), group=group)  # gloo (CPU tests)
+    if min(sizes) == biggest:
+        return out.view((world * biggest,) + tuple(local.shape[1:]))  # equal shards: the buffer IS the result
     return torch.cat([out[r, : sizes[r]] for r in range(world)], dim=0)
 
 

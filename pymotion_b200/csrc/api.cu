@@ -1054,6 +1054,19 @@ int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_h
         return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", n_slots);
     auto kernel = pmb::from_root_positions_kernel<THREADS>;
     if ((rc = set_smem(kernel, smem))) return rc;
+    // Thread = frame reads its positions row 12 bytes at a time, so the op lives on L1 hits, and L1 is what the
+    // shared-memory carve-out leaves of the SM's 256 KB.  Left to the driver, the carve-out is sized for the nine
+    // blocks the registers allow: with many live branch slots (2 KB each per block) that takes nearly all of it
+    // (measured at 4M x 65, 10 slots: 46 % L1 hits, 7.5 x the input re-read from L2, 10.4 ms).  Ask for what six
+    // blocks need instead; the occupancy follows the carve-out.  Measured (profiles/r1_sweep_frp_carveout.jsonl):
+    // 4M x 65 10.42 -> 4.79 ms (4.95 for 3 .. 4 blocks, 8.2 for 2), 4M x 52 3.84 -> 3.66 ms, 1M x 22 0.366 -> 0.360 ms.
+    {
+        const int target = std::max(1, std::min(9, env_int("PMB_FRP_BLOCKS_PER_SM", 6)));
+        const int want = target * (smem + 1024);
+        const int pct = std::max(1, std::min(100, (want * 100 + dp.smem_optin - 1) / dp.smem_optin));
+        PMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        note_variant("from_root_positions_kernel<%d> smem=%d carveout=%d%% (for %d blocks/SM)", THREADS, smem, pct, target);
+    }
     const long long blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
     kernel<<<static_cast<unsigned>(blocks), THREADS, smem, static_cast<cudaStream_t>(stream)>>>(

@@ -698,7 +698,11 @@ int pmb_from_root_dual_quat_f32(const float *dq, const int64_t *parents_host, in
     if (rc) return rc;
     if (n_frames == 0) return PMB_OK;
     constexpr int THREADS = 256;
-    const int fb = tile_frames(n_joints, 4096);
+    // Elements (frame, joint) per block tile.  The translations stage costs 12 bytes of shared memory per element and
+    // every thread has one 32-byte element in flight, so the tile size sets the bytes in flight per SM: 2304 elements
+    // (27 KB) lets the 8 blocks of 256 threads the SM can hold all be resident.  Measured against the 4096 of the
+    // first half (profiles/r1_sweep_frdq_tile.jsonl): 4M x 52 2.249 -> 1.888 ms, 4M x 65 2.756 -> 2.319 ms, 1M x 22 unchanged.
+    const int fb = tile_frames(n_joints, env_int("PMB_FRDQ_ELEMS", 2304));
     const int smem = ((fb * n_joints * 12 + 15) & ~15) + ((n_joints * 2 + 15) & ~15);
     auto kernel = pmb::from_root_dq_kernel<THREADS>;
     if ((rc = set_smem(kernel, smem))) return rc;

@@ -1188,7 +1188,14 @@ int pmb_interpolate_positions_f32(const double *sample_times, const double *orig
 int pmb_vec_normalize_f32(const float *v, float eps, float *out, int64_t n, int32_t k, void *stream) {
     if (k < 1) return fail(PMB_ERR_SHAPE, "%s: k < 1", __func__);
     PMB_EW_PROLOGUE(n, v, out);
-    pmb::vec_normalize_kernel<<<grid_, 256, 0, st_>>>(v, eps, out, n, k);
+    if (k == 3 && aligned16(v) && aligned16(out) && n >= 4 && env_int("PMB_VEC3_X4", 1)) {
+        const int64_t n4 = n / 4;
+        pmb::vec3_normalize_x4_kernel<<<ew_grid(n4, 256, dp_), 256, 0, st_>>>((const float4 *)v, eps, (float4 *)out, n4);
+        PMB_CUDA(cudaGetLastError());
+        if (n % 4) pmb::vec_normalize_kernel<<<1, 32, 0, st_>>>(v + 12 * n4, eps, out + 12 * n4, n % 4, 3);
+    } else {
+        pmb::vec_normalize_kernel<<<grid_, 256, 0, st_>>>(v, eps, out, n, k);
+    }
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }

@@ -133,4 +133,24 @@ __global__ void vec_normalize_kernel(const float *v, float eps, float *out, long
     }
 }
 
+// 3-vectors, four per thread: 48 contiguous bytes = three 16-byte loads in flight per thread instead of three 4-byte
+// ones, same arithmetic as above (16-byte aligned arrays; the host sends the last n % 4 vectors through the generic
+// kernel).
+__global__ void vec3_normalize_x4_kernel(const float4 *__restrict__ v, float eps, float4 *__restrict__ out, long long n4) {
+    PMB_GRID_STRIDE(i, n4) {
+        const float4 a = __ldcs(v + 3 * i), b = __ldcs(v + 3 * i + 1), c = __ldcs(v + 3 * i + 2);
+        // vectors: (a.x a.y a.z) (a.w b.x b.y) (b.z b.w c.x) (c.y c.z c.w)
+        auto inv_len = [eps](float x, float y, float z) {
+            float n2 = 0.f;
+            n2 += x * x, n2 += y * y, n2 += z * z;
+            return sqrtf(n2) + eps;
+        };
+        const float d0 = inv_len(a.x, a.y, a.z), d1 = inv_len(a.w, b.x, b.y), d2 = inv_len(b.z, b.w, c.x),
+                    d3 = inv_len(c.y, c.z, c.w);
+        __stcs(out + 3 * i, make_float4(a.x / d0, a.y / d0, a.z / d0, a.w / d1));
+        __stcs(out + 3 * i + 1, make_float4(b.x / d1, b.y / d1, b.z / d2, b.w / d2));
+        __stcs(out + 3 * i + 2, make_float4(c.x / d2, c.y / d3, c.z / d3, c.w / d3));
+    }
+}
+
 }  // namespace pmb

@@ -89,3 +89,23 @@ def test_vector_normalize(mods, golden_misc):
     assert_allclose(vec.normalize(g["f32/vec"], eps=1e-3), g["f32/vec_normalize_eps"], **TOL)
     assert_allclose(vec.normalize(g["f32/vec5"]), g["f32/vec5_normalize"], **TOL)
     assert_array_equal(vec.normalize(g["f32/vec"])[0, 0], 0.0)  # the null vector stays null (0 / eps)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 7, 1001, 4098, 65539])
+def test_vector_normalize_vec3_paths(mods, monkeypatch, n):
+    """3-vectors go four per thread when the arrays are 16-byte aligned (the last n % 4 through the generic kernel):
+    same bits as the generic kernel, on aligned and on 12-byte-offset arrays, and the oracle's values."""
+    *_, vec = mods
+    rng = np.random.default_rng(n)
+    v = rng.normal(size=(n + 1, 3)).astype(np.float32)
+    v[n // 2] = 0.0
+    want = orc.vec_normalize(v)
+    fast = vec.normalize(v)
+    assert_allclose(fast, want, **TOL)
+    monkeypatch.setenv("PMB_VEC3_X4", "0")
+    assert_array_equal(vec.normalize(v), fast)
+    monkeypatch.delenv("PMB_VEC3_X4")
+    t = torch.from_numpy(v).cuda()
+    shifted = vec.normalize(t[1:])  # data pointer 12 bytes past a 16-byte boundary: generic kernel
+    assert isinstance(shifted, torch.Tensor)
+    assert_array_equal(shifted.cpu().numpy(), fast[1:])

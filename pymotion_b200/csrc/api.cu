@@ -991,8 +991,13 @@ int pmb_unroll_f32(const float *x, int32_t width, int64_t n_steps, int64_t n_col
     PMB_CUDA(cudaGetLastError());
     pmb::unroll_chunks_kernel<<<static_cast<unsigned>(n_cols), 256, 0, st>>>(agg, chunks, n_cols);
     PMB_CUDA(cudaGetLastError());
-    pmb::unroll_apply_kernel<<<ew_grid(n_steps * n_cols, 256, dp), 256, 0, st>>>(
-        reinterpret_cast<const float4 *>(x), w4, n_steps, n_cols, local, agg, reinterpret_cast<float4 *>(out));
+    if (n_cols <= 512 && env_int("PMB_UNROLL_CHUNK_APPLY", 1))
+        pmb::unroll_apply_chunk_kernel<<<static_cast<unsigned>(chunks), 256, 0, st>>>(
+            reinterpret_cast<const float4 *>(x), w4, n_steps, static_cast<int>(n_cols), magic_small(static_cast<int>(n_cols)),
+            local, agg, reinterpret_cast<float4 *>(out));
+    else
+        pmb::unroll_apply_kernel<<<ew_grid(n_steps * n_cols, 256, dp), 256, 0, st>>>(
+            reinterpret_cast<const float4 *>(x), w4, n_steps, n_cols, local, agg, reinterpret_cast<float4 *>(out));
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }

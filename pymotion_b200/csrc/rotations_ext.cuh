@@ -10,6 +10,7 @@
 // 1e-5 against the NumPy reference.
 #pragma once
 #include "common.cuh"
+#include "dq_kernels.cuh"
 #include "elementwise.cuh"
 
 namespace pmb {
@@ -246,29 +247,42 @@ __device__ __forceinline__ uint8_t unroll_combine(uint8_t p, uint8_t c) {
     const uint8_t neg = (c & 2) ? (c & 1) : ((p ^ c) & 1);
     return neg | ((p | c) & 2);
 }
-__global__ void unroll_local_kernel(const float4 *x, int w4, long long n_steps, long long n_cols, long long n_chunks,
-                                    uint8_t *local, uint8_t *agg) {
-    // one thread per (chunk, column), columns fastest: neighbouring threads read neighbouring quaternions
+__global__ void unroll_local_kernel(const float4 *__restrict__ x, int w4, long long n_steps, long long n_cols,
+                                    long long n_chunks, uint8_t *__restrict__ local, uint8_t *__restrict__ agg) {
+    // one thread per (chunk, column), columns fastest: neighbouring threads read neighbouring quaternions.  The steps
+    // of a chunk are fetched eight at a time, so a thread has 128 bytes in flight instead of 16 (the chain over the
+    // steps is cheap; what this kernel waits for is memory).
+    constexpr int B = 8;
     const long long id = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (id >= n_chunks * n_cols) return;
     const long long c = id / n_cols, m = id - c * n_cols, t0 = c * kUnrollChunk;
     const long long t1 = min(t0 + kUnrollChunk, n_steps);
     float4 prev = t0 > 0 ? __ldg(x + ((t0 - 1) * n_cols + m) * w4) : make_float4(0.f, 0.f, 0.f, 0.f);
     uint8_t state = 0;
-    for (long long t = t0; t < t1; ++t) {
-        const float4 cur = __ldg(x + (t * n_cols + m) * w4);
-        uint8_t el;
-        if (t == 0) {
-            el = 2;  // the first entry keeps its cover
-        } else {
-            // np.sum(r[i] * r[i - 1], axis=-1): separate roundings
-            const float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cur.x, prev.x), __fmul_rn(cur.y, prev.y)), __fmul_rn(cur.z, prev.z)),
-                                      __fmul_rn(cur.w, prev.w));
-            el = d < 0.f ? 1 : (d > 0.f ? 0 : 2);
+    for (long long tb = t0; tb < t1; tb += B) {
+        float4 buf[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k)
+            if (tb + k < t1) buf[k] = __ldg(x + ((tb + k) * n_cols + m) * w4);
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const long long t = tb + k;
+            if (t < t1) {
+                const float4 cur = buf[k];
+                uint8_t el;
+                if (t == 0) {
+                    el = 2;  // the first entry keeps its cover
+                } else {
+                    // np.sum(r[i] * r[i - 1], axis=-1): separate roundings
+                    const float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(cur.x, prev.x), __fmul_rn(cur.y, prev.y)), __fmul_rn(cur.z, prev.z)),
+                                              __fmul_rn(cur.w, prev.w));
+                    el = d < 0.f ? 1 : (d > 0.f ? 0 : 2);
+                }
+                state = unroll_combine(state, el);
+                local[t * n_cols + m] = state;
+                prev = cur;
+            }
         }
-        state = unroll_combine(state, el);
-        local[t * n_cols + m] = state;
-        prev = cur;
     }
     agg[c * n_cols + m] = state;
 }
@@ -296,12 +310,34 @@ __global__ void __launch_bounds__(256) unroll_chunks_kernel(uint8_t *agg, long l
         run = unroll_combine(run, a);
     }
 }
-__global__ void unroll_apply_kernel(const float4 *x, int w4, long long n_steps, long long n_cols, const uint8_t *local,
-                                    const uint8_t *agg, float4 *o) {
+__global__ void unroll_apply_kernel(const float4 *__restrict__ x, int w4, long long n_steps, long long n_cols,
+                                    const uint8_t *__restrict__ local, const uint8_t *__restrict__ agg, float4 *__restrict__ o) {
     const long long n = n_steps * n_cols;
     PMB_GRID_STRIDE(i, n) {
         const long long t = i / n_cols, m = i - t * n_cols;
         const uint8_t s = unroll_combine(agg[(t / kUnrollChunk) * n_cols + m], local[i]);
+        const float f = (s & 1) ? -1.f : 1.f;
+        for (int k = 0; k < w4; ++k) {
+            const float4 v = __ldcs(x + i * w4 + k);
+            __stcs(o + i * w4 + k, make_float4(f * v.x, f * v.y, f * v.z, f * v.w));
+        }
+    }
+}
+
+// The same for n_cols <= 512: one block per chunk, so the column of an element comes from a 16-bit multiply-high
+// (div_small, dq_kernels.cuh) instead of two 64-bit divisions per element.
+__global__ void __launch_bounds__(256)
+unroll_apply_chunk_kernel(const float4 *__restrict__ x, int w4, long long n_steps, int n_cols, uint32_t magic,
+                          const uint8_t *__restrict__ local, const uint8_t *__restrict__ agg, float4 *__restrict__ o) {
+    const long long c = blockIdx.x, t0 = c * kUnrollChunk;
+    const int steps = static_cast<int>(min(static_cast<long long>(kUnrollChunk), n_steps - t0));
+    const int n_el = steps * n_cols;  // <= 128 * 512 = 2^16
+    const long long base = t0 * n_cols;
+    const uint8_t *a = agg + c * n_cols;
+    for (int il = threadIdx.x; il < n_el; il += 256) {
+        const int m = il - div_small(il, magic) * n_cols;
+        const long long i = base + il;
+        const uint8_t s = unroll_combine(a[m], local[i]);
         const float f = (s & 1) ? -1.f : 1.f;
         for (int k = 0; k < w4; ++k) {
             const float4 v = __ldcs(x + i * w4 + k);

@@ -235,6 +235,50 @@ def test_fk_on_side_stream(sk, golden_fk):
     assert_allclose(pos.cpu().numpy(), g["body22/pos"], **TOL)
 
 
+def test_concurrent_threads_on_their_own_streams(sk):
+    """calls from several host threads, each on its own CUDA stream, are independent (ctypes drops the
+    GIL for the duration of a call, so the host side of the library really runs concurrently): every thread gets the
+    bits the same call gives alone, and a failing call in one thread does not disturb the others' error state."""
+    import threading
+
+    dev = torch.device("cuda")
+    jobs = []
+    for k, (name, n_frames) in enumerate((("body22", 3001), ("smplh52", 1500), ("deep65", 777), ("body22", 64))):
+        par = parents_of(name)
+        rot, gp, off = synth_torch(n_frames, par, dev, seed=900 + k)
+        pos, rotm = sk.fk(rot, gp, off, par)
+        dq = sk.to_root_dual_quat(rot, gp, par, off)
+        jobs.append((par, rot, gp, off, pos.clone(), rotm.clone(), dq.clone()))
+    torch.cuda.synchronize()
+    failures = []
+
+    def work(k):
+        par, rot, gp, off, want_pos, want_rotm, want_dq = jobs[k]
+        stream = torch.cuda.Stream()
+        try:
+            with torch.cuda.stream(stream):
+                for it in range(25):
+                    pos, rotm = sk.fk(rot, gp, off, par)
+                    dq = sk.to_root_dual_quat(rot, gp, par, off)
+                    if k == 3 and it % 5 == 0:  # an error path in the middle of everyone else's launches
+                        bad = par.copy()
+                        bad[3] = 7
+                        with pytest.raises(ValueError):
+                            sk.fk(rot, gp, off, bad)
+                    stream.synchronize()
+                    if not (torch.equal(pos, want_pos) and torch.equal(rotm, want_rotm) and torch.equal(dq, want_dq)):
+                        failures.append((k, it))
+        except Exception as e:  # noqa: BLE001 -- reported by the main thread
+            failures.append((k, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not failures, failures
+
+
 # ---------------------------------------------------------------- dual quaternions
 @pytest.mark.parametrize("case", ["chain3_ident", "chain3_rot"])
 def test_dq_chain3_goldens(sk, dquat, quat, golden_dq, case):

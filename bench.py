@@ -31,7 +31,11 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-METRIC = "skeleton poses/sec (22 joints)"
+METRIC = "skeleton poses/sec (22 joints)"  # BASELINE.json; other workloads carry their own joint count
+
+
+def metric_of(n_joints: int) -> str:
+    return f"skeleton poses/sec ({n_joints} joints)"
 UNIT = "poses/s"
 
 WORKLOADS = {
@@ -196,7 +200,7 @@ def run_reference(args):
     value = sample * args.steps / dt
     line = {
         "impl": "reference",
-        "metric": METRIC,
+        "metric": metric_of(len(par)),
         "value": value,
         "unit": UNIT,
         "n_gpus": args.gpus,
@@ -408,7 +412,7 @@ def run_ours(args):
         kernel_ms = ms_max / args.steps
         achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC,
+            "metric": metric_of(n_joints),
             "value": value,
             "unit": UNIT,
             "n_gpus": world,

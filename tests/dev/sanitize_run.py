@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Small-shape pass over every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
 
-    compute-sanitizer --tool memcheck python tools/sanitize_run.py
+    compute-sanitizer --tool memcheck python tests/dev/sanitize_run.py
 
 Checks results against the oracle too, so a sanitizer-clean run is also a correct one."""
 import os
 import sys
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 
 import numpy as np  # noqa: E402

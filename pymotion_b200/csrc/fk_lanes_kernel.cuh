@@ -30,8 +30,24 @@
 #ifndef PMB_LANES_HOIST
 #define PMB_LANES_HOIST 0
 #endif
+#ifndef PMB_LANES_XOR
+#define PMB_LANES_XOR 1  // box / table reads through 32-bit shared addresses (one XOR per swizzled read)
+#endif
 
 namespace pmb {
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// read-only data (the joint table): free to be scheduled and merged by the compiler
+__device__ __forceinline__ float4 lds128_ro(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 
 struct FkLanesGeom {
     int box_bytes, tab_bytes, warp_bytes, block_bytes;
@@ -71,6 +87,7 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     float *Rst = reinterpret_cast<float *>(mine + NB * BOX);
     float *Pst = Rst + FR * 9 * n_joints;
     const uint32_t box0 = smem_u32(mine);
+    const uint32_t tab0 = smem_u32(tab);
     const uint32_t bar0 = smem_u32(Pst + FR * 3 * n_joints);   // NB mbarriers (8-byte aligned: all sizes above are multiples of 16)
     const uint32_t fence_word = bar0 + 32 + 4 * lane;
 
@@ -168,10 +185,19 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
                 const uint32_t buf = k % NB;
                 mbar_wait(bar0 + 8 * buf, (k / NB) & 1);
                 ++k;
+#if PMB_LANES_XOR
+                // the box row of this lane's frame is 128-byte aligned, so chunk (jj ^ swz) of it is at
+                // (row | swz << 4) ^ (jj << 4): one XOR per read
+                const uint32_t row = box0 + buf * BOX + f * 128;
+                const uint32_t row_swz = row | (((row >> 7) & 7u) << 4);
+#pragma unroll
+                for (int jj = 0; jj < C; ++jj) q[jj] = lds128(row_swz ^ (jj << 4));
+#else
                 const float4 *in_row = in_row0 + buf * (BOX / 16);
                 const int swz = (swz_base + buf * (BOX / 128)) & 7;
 #pragma unroll
                 for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj ^ swz];
+#endif
                 {   // the loads must have LANDED before the box is refilled through the async proxy (see fk_kernel.cuh)
                     uint32_t acc = 0;
 #pragma unroll
@@ -201,11 +227,20 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
 
             // Branch-free walk over the chunk (see fk_rows_kernel.cuh).  Joints past the end of the skeleton are
             // zero quaternions (TMA fill) with padded table entries: identity steps whose stores are predicated off.
+#if PMB_LANES_XOR
+            const uint32_t tab_c0 = tab0 + c0 * 16;
+            float4 e = lds128_ro(tab_c0);
+#else
             float4 e = tab[c0];
+#endif
 #pragma unroll
             for (int jj = 0; jj < C; ++jj) {
                 const int j = c0 + jj;
+#if PMB_LANES_XOR
+                const float4 e_next = lds128_ro(tab_c0 + 16 * (jj + 1));
+#else
                 const float4 e_next = tab[j + 1];
+#endif
                 // parent whose row must come from the stage, or -1; the idle lanes (which shadow lane 0's addresses)
                 // never read the stage
                 const int p = active ? __float_as_int(e.w) : -1;

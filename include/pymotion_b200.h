@@ -21,7 +21,8 @@
  *    the parameter name ends in `_host`;
  *  - arrays are dense row-major float32: quaternion = 4 floats (w,x,y,z),
  *    dual quaternion = 8 floats (real wxyz | dual wxyz), rotation matrix = 9
- *    floats m[r][c], vector = 3 floats; `_f64` twins take double;
+ *    floats m[r][c], vector = 3 floats.  There are no float64 entry points (north_star: fp32,
+ *    HBM-bound); the Python layer rounds float64 callers to float32 with a one-time PrecisionWarning;
  *  - the caller owns every buffer; the library never allocates user-visible
  *    memory, never frees and never writes an input;
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
@@ -106,16 +107,24 @@ int pmb_from_root_dual_quat_f32(const float *dq, const int64_t *parents_host, in
 int pmb_from_global_rotations_f32(const float *global_quats, const int64_t *parents_host, int64_t n_frames,
                                   int32_t n_joints, float *local_quats, void *stream);
 
-/* ---- host-buffer (end-to-end) entry point -------------------------------- */
+/* ---- host-buffer (end-to-end) entry points ------------------------------- */
 
-/* fk on HOST buffers: splits the frame axis into chunks of `chunk_frames`
- * (0 = library default) and pipelines H2D copy / kernel / D2H copy over two
- * internal streams and device staging buffers owned by the library (freed by
- * pmb_release_workspace()).  Blocks until the outputs are in host memory.
- * Host buffers should be page-locked for full PCIe rate. */
+/* fk on HOST buffers (the reference's own calling convention, ops/skeleton.py:16: arrays in
+ * host memory in, arrays in host memory out).  The frame axis is cut into chunks of
+ * `chunk_frames` (0 = library default, ~48 MB of traffic per chunk) and H2D copy / kernel /
+ * D2H copy are pipelined over two internal streams.  Page-locked buffers are DMA'd directly;
+ * pageable buffers (plain malloc / NumPy memory) go through a page-locked staging ring filled
+ * and drained by a few library-owned host threads.  Workspaces (device + pinned staging) are
+ * per device and per concurrent caller, owned by the library, freed by pmb_release_workspace().
+ * Blocks until the outputs are in host memory; on error no copy is left in flight.
+ * pmb_fk_quat_f32_host returns global quaternions (16 J instead of 36 J bytes per frame back
+ * over PCIe) -- what every in-repo consumer of fk computes next (ops/skeleton.py:322, :140). */
 int pmb_fk_f32_host(const float *rot_host, const float *global_pos_host, const float *offsets_host,
                     const int64_t *parents_host, int64_t n_frames, int32_t n_joints,
                     float *positions_host, float *rotmats_host, int64_t chunk_frames);
+int pmb_fk_quat_f32_host(const float *rot_host, const float *global_pos_host, const float *offsets_host,
+                         const int64_t *parents_host, int64_t n_frames, int32_t n_joints,
+                         float *positions_host, float *global_rots_host, int64_t chunk_frames);
 void pmb_release_workspace(void);
 
 /* ---- element-wise quaternion primitives (n = number of quaternions) ----- */
@@ -211,6 +220,20 @@ int pmb_vec_normalize_f32(const float *v, float eps, float *out, int64_t n, int3
  * none), bits 16-30 = parent index.  Returns the number of slots (>= 0) or a
  * negative pmb_status. */
 int pmb_build_joint_program(const int64_t *parents_host, int32_t n_joints, uint32_t *codes_out);
+
+/* Builds the schedule the fk track kernel executes for `parents_host` with `n_tracks` (1..8)
+ * independent joints per step: codes_out[step * n_tracks + track], bits 0-9 joint, bits 10-19
+ * parent, bit 20 = the parent is the same track's previous item (kept in registers), bit 21 =
+ * no-op.  Every joint appears exactly once, after its parent's step.  Returns the number of
+ * steps (> 0) or a negative pmb_status (PMB_ERR_SHAPE if codes_capacity is too small). */
+int pmb_build_track_schedule(const int64_t *parents_host, int32_t n_joints, int32_t n_tracks,
+                             uint32_t *codes_out, int32_t codes_capacity);
+
+/* Kernel-variant knobs (PMB_FK_*, PMB_DQ_*, ...) are honoured only when PMB_EXPERIMENT=1 is in
+ * the environment, and are read once; this re-reads them (sweeps and the forced-variant tests
+ * switch variants inside one process).  Not for production use, not thread-safe against
+ * concurrent launches. */
+void pmb_reload_knobs(void);
 
 #ifdef __cplusplus
 }

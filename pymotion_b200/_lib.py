@@ -26,12 +26,15 @@ SIGNATURES = {
     "pmb_status_string": [ctypes.c_int],
     "pmb_device_info": [_vp, _vp, _vp, ctypes.c_char_p, ctypes.c_int],
     "pmb_build_joint_program": [_vp, _i32, _vp],
+    "pmb_build_track_schedule": [_vp, _i32, _i32, _vp, _i32],
+    "pmb_reload_knobs": [],
     "pmb_fk_f32": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp],
     "pmb_fk_quat_f32": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp],
     "pmb_to_root_dual_quat_f32": [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
     "pmb_from_root_dual_quat_f32": [_vp, _vp, _i64, _i32, _vp, _vp, _vp],
     "pmb_from_global_rotations_f32": [_vp, _vp, _i64, _i32, _vp, _vp],
     "pmb_fk_f32_host": [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64],
+    "pmb_fk_quat_f32_host": [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64],
     "pmb_release_workspace": [],
     "pmb_quat_mul_f32": [_vp, _vp, _vp, _i64, _vp],
     "pmb_quat_mul_vec_f32": [_vp, _vp, _vp, _i64, _vp],
@@ -68,7 +71,7 @@ SIGNATURES = {
     "pmb_interpolate_positions_f32": [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
     "pmb_vec_normalize_f32": [_vp, _f32, _vp, _i64, _i32, _vp],
 }
-_RESTYPES = {"pmb_last_error": ctypes.c_char_p, "pmb_last_variant": ctypes.c_char_p, "pmb_status_string": ctypes.c_char_p, "pmb_release_workspace": None,
+_RESTYPES = {"pmb_last_error": ctypes.c_char_p, "pmb_last_variant": ctypes.c_char_p, "pmb_status_string": ctypes.c_char_p, "pmb_release_workspace": None, "pmb_reload_knobs": None,
              "pmb_unroll_workspace_bytes": ctypes.c_int64}
 
 _lib = None

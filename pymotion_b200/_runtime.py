@@ -68,6 +68,13 @@ class Marshal:
     def dev(self, a) -> torch.Tensor:
         """float32, on the compute device; NOT necessarily contiguous."""
         if isinstance(a, torch.Tensor):
+            if a.requires_grad and torch.is_grad_enabled():
+                # the reference's torch twins are differentiable (ops/skeleton_torch.py:60-63 clones for
+                # exactly that); these kernels have no backward, and handing back a tensor without a graph
+                # would train with a silent zero gradient
+                raise RuntimeError(
+                    "pymotion_b200 kernels are forward-only: an input has requires_grad=True. Call under "
+                    "torch.no_grad() / pass x.detach(), or use the reference's torch twin where gradients are needed")
             return a.to(device=self.device, dtype=torch.float32, non_blocking=True)
         return torch.as_tensor(np.asarray(a), device=self.device).to(torch.float32)
 

@@ -1,0 +1,418 @@
+// libpymotion_b200.so, fk translation unit: pmb_fk_f32 / pmb_fk_quat_f32 and the launch policy that picks one of
+// the fk kernels (track, row-team, lane, thread-per-frame) from the joint count and the topology.
+// Host side only validates, looks up the per-topology program, picks a launch configuration and launches.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "fk_kernel.cuh"
+#include "fk_lanes_kernel.cuh"
+#include "fk_quat_kernel.cuh"
+#include "fk_rows_kernel.cuh"
+#include "fk_tracks_kernel.cuh"
+#include "host_common.h"
+
+using namespace pmbh;
+
+namespace {
+
+struct FkArgs {
+    const float *rot, *gpos, *offsets;
+    long long gstride, ostride;
+    float *pos, *rout;
+    long long n_frames;
+    int n_joints, n_slots;
+    const pmb::JointProgram *prog;
+    const int64_t *parents_host;
+    cudaStream_t stream;
+};
+
+// ---- thread-per-frame kernel (fk_kernel.cuh) ---------------------------------------------------
+template <int G, int WARPS, int VEC, bool PF, bool QO>
+int launch_fk_cfg(const FkArgs &a, const DeviceProps &dp) {
+    auto kernel = pmb::fk_chain_kernel<G, WARPS, VEC, PF, QO>;
+    const int smem = pmb::fk_geom(G, VEC, QO ? 4 : 9, WARPS, a.n_joints, a.n_slots).block_bytes;
+    int per_sm = 0, rc = kernel_fit(kernel, dp, WARPS * 32, smem, per_sm);
+    if (rc) return rc;
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk kernel does not fit on an SM (%d bytes of shared memory)", smem);
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk))) return rc;
+    // persistent grid: as many blocks as are resident at once; warps walk the tiles round robin
+    const long long tiles = (a.n_frames + 31) / 32;
+    per_sm = std::max(1, std::min(per_sm, knob(K_FK_BLOCKS_PER_SM, per_sm)));
+    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
+    note_variant("fk_chain_kernel<G=%d,WARPS=%d,VEC=%d,PF=%d,QO=%d> grid=%lld smem=%d", G, WARPS, VEC, int(PF), int(QO), blocks, smem);
+    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.ostride, a.pos, a.rout,
+                                                                        a.n_frames, a.n_joints, a.n_slots, *a.prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// ---- row-team kernel (fk_rows_kernel.cuh) ------------------------------------------------------
+template <int S, int VEC>
+int launch_fk_rows_cfg(const FkArgs &a, const DeviceProps &dp, int team_cap) {
+    auto kernel = pmb::fk_rows_kernel<S, VEC>;
+    const int smem = pmb::fk_rows_geom(S, a.n_joints).block_bytes;
+    int per_sm = 0, rc = kernel_fit(kernel, dp, pmb::kRowThreads, smem, per_sm);
+    if (rc) return rc;
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk row kernel does not fit on an SM (%d bytes of shared memory)", smem);
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk))) return rc;
+    const long long tiles = (a.n_frames + 31) / 32;
+    if (team_cap > 0) per_sm = std::min(per_sm, team_cap);
+    per_sm = std::max(1, std::min(per_sm, knob(K_FK_BLOCKS_PER_SM, per_sm)));
+    const long long blocks = std::min<long long>(tiles, static_cast<long long>(per_sm) * dp.sm_count);
+    note_variant("fk_rows_kernel<S=%d,VEC=%d> grid=%lld (%d teams/SM) smem=%d", S, VEC, blocks, per_sm, smem);
+    kernel<<<static_cast<unsigned>(blocks), pmb::kRowThreads, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos, a.rout,
+                                                                                a.n_frames, a.n_joints, *a.prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// Teams (blocks) of the row kernel that fit on an SM with S box stages: every block also costs 1 KB of
+// system shared memory.
+inline int fk_rows_teams(int stages, const FkArgs &a, const DeviceProps &dp) {
+    const int bytes = pmb::fk_rows_geom(stages, a.n_joints).block_bytes;
+    if (bytes > dp.smem_optin) return 0;
+    return std::min(12, (dp.smem_optin + 1024) / (bytes + 1024));
+}
+
+// ---- lane = (frame, row) kernel (fk_lanes_kernel.cuh) --------------------------------------------
+template <int FR, int WARPS, int NB>
+int launch_fk_lanes_nb(const FkArgs &a, const DeviceProps &dp, int block_cap) {
+    auto kernel = pmb::fk_lanes_kernel<FR, WARPS, NB>;
+    const int smem = pmb::fk_lanes_geom(FR, WARPS, a.n_joints, NB).block_bytes;
+    if (smem > dp.smem_optin) return fail(PMB_ERR_SHAPE, "fk lane kernel: %d joints do not fit in shared memory", a.n_joints);
+    int per_sm = 0, rc = kernel_fit(kernel, dp, WARPS * 32, smem, per_sm);
+    if (rc) return rc;
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk lane kernel does not fit on an SM (%d bytes of shared memory)", smem);
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk, FR))) return rc;
+    const long long tiles = (a.n_frames + FR - 1) / FR;
+    per_sm = std::max(1, std::min(per_sm, block_cap));
+    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
+    note_variant("fk_lanes_kernel<FR=%d,WARPS=%d,NB=%d> grid=%lld (%d warps/SM) smem=%d", FR, WARPS, NB, blocks, per_sm * WARPS, smem);
+    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos, a.rout, a.n_frames,
+                                                                        a.n_joints, *a.prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+template <int FR, int WARPS>
+int launch_fk_lanes_cfg(const FkArgs &a, const DeviceProps &dp, int block_cap, int n_boxes) {
+    const int nb = knob(K_FK_NB, n_boxes);  // TMA boxes in flight per warp
+    if (nb == 3) return launch_fk_lanes_nb<FR, WARPS, 3>(a, dp, block_cap);
+    if (nb == 4) return launch_fk_lanes_nb<FR, WARPS, 4>(a, dp, block_cap);
+    return launch_fk_lanes_nb<FR, WARPS, 2>(a, dp, block_cap);
+}
+
+// Worst-case number of lanes of one stage store that fall into the same shared-memory bank: lane = (frame, row)
+// puts the frames of a tile 9J words apart, so only (9J mod 32) matters.  1 = conflict free.
+inline int fk_lanes_bank_degree(int fr, int n_joints) {
+    int count[32] = {0}, worst = 0;
+    for (int f = 0; f < fr; ++f) worst = std::max(worst, ++count[(f * 9 * n_joints) & 31]);
+    return worst;
+}
+
+struct FkLanesPlan {
+    int fr = 0, warps = 0, frames_in_flight = 0, n_boxes = 2, warps_sm = 0;
+};
+// The tile size / block shape that keeps the most frames in flight per SM (what the throughput of the large
+// skeletons follows): FR = 10 needs an even joint count, blocks of 1, 2 or 4 warps.
+inline FkLanesPlan fk_lanes_plan(const FkArgs &a, const DeviceProps &dp) {
+    FkLanesPlan best;
+    for (int fr : {10, 8}) {
+        if (fr == 10 && a.n_joints % 2) continue;
+        for (int warps : {4, 2, 1}) {
+            const int bytes = pmb::fk_lanes_geom(fr, warps, a.n_joints).block_bytes;
+            if (bytes > dp.smem_optin) continue;
+            const int blocks = std::min(32, (dp.smem_optin + 1024) / (bytes + 1024));
+            const int warps_sm = std::min(blocks * warps, 12);  // measured at 22 joints: beyond 12 walking warps per SM it gets slower
+            // ... discounted by the bank conflicts of that tile size (measured: J = 40, 100 frames 3-way 5.33 TB/s
+            // against 96 frames 2-way 5.61; J = 52, 80 frames 2-way 5.00 against 64 frames conflict-free 4.56)
+            const int degree = fk_lanes_bank_degree(fr, a.n_joints);
+            const int weight = degree <= 1 ? 100 : degree == 2 ? 90 : degree == 3 ? 80 : 50;
+            const int fif = warps_sm * fr * weight;
+            if (fif > best.frames_in_flight) best = {fr, warps, fif, 2, warps_sm};
+        }
+    }
+    // A third TMA box per warp when it is free (same number of blocks per SM) and the SM is short of warps to hide
+    // the load latency with: measured +3.5 % at 65 joints (8 warps per SM), nothing at 40 joints (12 warps).
+    if (best.fr && best.warps_sm <= 8) {
+        auto blocks_of = [&](int nb) {
+            const int bytes = pmb::fk_lanes_geom(best.fr, best.warps, a.n_joints, nb).block_bytes;
+            return bytes > dp.smem_optin ? 0 : std::min(32, (dp.smem_optin + 1024) / (bytes + 1024));
+        };
+        if (blocks_of(3) == blocks_of(2)) best.n_boxes = 3;
+    }
+    return best;
+}
+
+// PMB_FK_LANES = 0 / 1 forces; PMB_FK_FR = 8 | 10, PMB_FK_WARPS = 1 | 2 | 4 pick the shape.
+bool try_fk_lanes(const FkArgs &a, const DeviceProps &dp, int &rc, bool rows_preferred) {
+    const int force = knob(K_FK_LANES, -1);
+    if (force == 0) return false;
+    if (force != 1 && (knob_set(K_FK_GROUP) || knob_set(K_FK_ROWS))) return false;  // another kernel is being forced
+    FkLanesPlan plan = fk_lanes_plan(a, dp);
+    if (plan.fr == 0) {
+        if (force == 1) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_LANES=1: the lane kernel does not fit"); return true; }
+        return false;
+    }
+    int fr = knob(K_FK_FR, plan.fr);
+    if (fr != 10 || a.n_joints % 2) fr = 8;  // the spans of 10 frames are 16-byte multiples only for an even joint count
+    const int warps = knob(K_FK_WARPS, plan.warps);
+    if (force != 1) {
+        if (rows_preferred) return false;
+        // a dense stage whose frames collide in 4 or more banks (J = 16, 32, 48, 64, ...: measured 2.0 TB/s at
+        // J = 32) belongs to the thread-per-frame kernel with its padded stage
+        if (fk_lanes_bank_degree(fr, a.n_joints) >= 4) return false;
+    }
+    const int cap = knob(K_FK_BLOCKS_PER_SM, std::max(1, 12 / std::max(1, warps)));
+    // the plan's ring depth only holds for the plan's own shape
+    const int nb = (fr == plan.fr && warps == plan.warps) ? plan.n_boxes : 2;
+    if (fr == 10) rc = warps == 1 ? launch_fk_lanes_cfg<10, 1>(a, dp, cap, nb) : warps == 2 ? launch_fk_lanes_cfg<10, 2>(a, dp, cap, nb) : launch_fk_lanes_cfg<10, 4>(a, dp, cap, nb);
+    else rc = warps == 1 ? launch_fk_lanes_cfg<8, 1>(a, dp, cap, nb) : warps == 2 ? launch_fk_lanes_cfg<8, 2>(a, dp, cap, nb) : launch_fk_lanes_cfg<8, 4>(a, dp, cap, nb);
+    return true;
+}
+
+// ---- track kernel (fk_tracks_kernel.cuh) -------------------------------------------------------
+struct FkTracksShape {
+    int fr = 0, warps = 0, blocks = 0, smem = 0;  // frames per tile, warps per block, blocks per SM
+};
+// The block shape that puts the most warps (= frames in flight) on an SM: every block carries its own copy of the
+// schedule table and costs 1 KB of system shared memory.
+inline FkTracksShape fk_tracks_shape(int fr, int n_joints, int n_items, int warps_cap, const DeviceProps &dp) {
+    FkTracksShape best;
+    for (int blocks = 1; blocks <= 4; ++blocks)
+        for (int warps = 8; warps >= 1; --warps) {
+            const int smem = pmb::fk_tracks_geom(fr, warps, n_joints, n_items).block_bytes;
+            if (smem > dp.smem_optin || blocks * (smem + 1024) > dp.smem_sm) continue;
+            if (blocks * warps > warps_cap) continue;
+            if (blocks * warps > best.blocks * best.warps) best = {fr, warps, blocks, smem};
+            break;  // fewer warps per block only lowers the product for this block count
+        }
+    return best;
+}
+
+template <int U, int D>
+int launch_fk_tracks_cfg(const FkArgs &a, const DeviceProps &dp, const FkTracksShape &sh, const pmb::TrackProgram &tp, int n_steps) {
+    auto kernel = pmb::fk_tracks_kernel<U, D>;
+    int per_sm = 0, rc = kernel_fit(kernel, dp, sh.warps * 32, sh.smem, per_sm);
+    if (rc) return rc;
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk track kernel does not fit on an SM (%d bytes of shared memory)", sh.smem);
+    per_sm = std::min(per_sm, sh.blocks);
+    const long long tiles = (a.n_frames + sh.fr - 1) / sh.fr;
+    const long long blocks = std::min<long long>((tiles + sh.warps - 1) / sh.warps, static_cast<long long>(per_sm) * dp.sm_count);
+    note_variant("fk_tracks_kernel<U=%d,D=%d> FR=%d steps=%d grid=%lld x %d warps (%d warps/SM) smem=%d", U, D, sh.fr, n_steps, blocks,
+                 sh.warps, per_sm * sh.warps, sh.smem);
+    kernel<<<static_cast<unsigned>(blocks), sh.warps * 32, sh.smem, a.stream>>>(
+        reinterpret_cast<const float4 *>(a.rot), a.gpos, a.gstride, a.offsets, a.pos, a.rout, a.n_frames, a.n_joints, n_steps, sh.fr,
+        knob(K_FK_L2_PREFETCH, 1), tp);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+// PMB_FK_TRACKS = 0 / 1 forces; PMB_FK_U = 1 | 2 | 4 tracks, PMB_FK_D ring depth, PMB_FK_FR = 8 | 10,
+// PMB_FK_WARPS_PER_SM caps the resident warps.
+bool try_fk_tracks(const FkArgs &a, const DeviceProps &dp, int &rc) {
+    const int force = knob(K_FK_TRACKS, -1);
+    if (force == 0) return false;
+    if (force != 1) return false;  // not part of the default policy yet
+    const int U = knob(K_FK_U, 2), D = knob(K_FK_D, U == 4 ? 2 : 4);
+    const pmb::TrackProgram *tp = nullptr;
+    int n_steps = 0;
+    if ((rc = track_program(a.parents_host, a.n_joints, U, tp, n_steps))) return true;
+    if (n_steps == 0) { rc = fail(PMB_ERR_SHAPE, "track schedule with %d tracks does not fit", U); return true; }
+    const int fr = knob(K_FK_FR, 10);
+    const FkTracksShape sh = fk_tracks_shape(fr, a.n_joints, n_steps * U, knob(K_FK_WARPS_PER_SM, 16), dp);
+    if (sh.fr == 0) { rc = fail(PMB_ERR_SHAPE, "fk track kernel: %d joints do not fit in shared memory", a.n_joints); return true; }
+#define PMB_TRACKS_CASE(u, d) \
+    if (U == u && D == d) { rc = launch_fk_tracks_cfg<u, d>(a, dp, sh, *tp, n_steps); return true; }
+    PMB_TRACKS_CASE(1, 4) PMB_TRACKS_CASE(1, 8) PMB_TRACKS_CASE(2, 2) PMB_TRACKS_CASE(2, 4) PMB_TRACKS_CASE(3, 2) PMB_TRACKS_CASE(3, 3)
+    PMB_TRACKS_CASE(4, 2) PMB_TRACKS_CASE(4, 3)
+#undef PMB_TRACKS_CASE
+    rc = fail(PMB_ERR_SHAPE, "PMB_FK_U=%d / PMB_FK_D=%d select no available variant", U, D);
+    return true;
+}
+
+// Which fk kernel (shared offsets, matrices out) -- measured on B200, DESIGN.md section 4:
+//   row-team kernel      skeletons small enough for >= 4 teams per SM (J <= 30) with J not a multiple of 4
+//                        (1M x 22: 0.2316 ms against 0.2415 ms thread-per-frame, 0.2326 ms lanes);
+//   lane kernel          everything larger (2M x 40: 5.6 TB/s against 5.15; 4M x 52: 5.0 against 4.76; 4M x 65:
+//                        4.4, as the row kernel, against 3.9), unless
+//   thread-per-frame     the dense stage of the lane kernel would put >= 4 frames in one bank (J = 16, 32, 48,
+//                        64, ...: 2.0 TB/s at J = 32 against 5.6), per-frame offsets, or a forced variant.
+// Bank conflicts of the row-team kernel (lane = frame, 32 lanes 9J words apart): J odd: none; J = 2 (mod 4):
+// none with its 64-bit stores; J = 0 (mod 4): 4-way (J = 52: 4.5 TB/s) up to 32-way (J = 32: 0.84 TB/s).
+bool fk_rows_preferred(const FkArgs &a, const DeviceProps &dp) {
+    return fk_rows_teams(2, a, dp) >= 4 && a.n_joints % 4 != 0;
+}
+
+bool try_fk_rows(const FkArgs &a, const DeviceProps &dp, int &rc) {
+    const int force = knob(K_FK_ROWS, -1);
+    if (force == 0) return false;
+    if (force != 1 && (knob_set(K_FK_GROUP) || knob_set(K_FK_WARPS))) return false;  // a chain-kernel variant is being forced
+    int stages = knob(K_FK_STAGES, -1);
+    int team_cap = 0;  // 0: as many as fit
+    if (stages < 0) {
+        const int t2 = fk_rows_teams(2, a, dp);
+        if (t2 >= 4) {
+            stages = 2, team_cap = 4;
+        } else {
+            stages = 2;
+            for (int s = 3; s <= 4; ++s)
+                if (fk_rows_teams(s, a, dp) == t2) stages = s;  // the deepest ring that does not cost a team
+        }
+    }
+    const int teams = (stages >= 2 && stages <= 4) ? fk_rows_teams(stages, a, dp) : 0;
+    if (teams < 1) {
+        if (force == 1) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_ROWS=1: the row kernel does not fit (stages %d)", stages); return true; }
+        return false;
+    }
+    if (force != 1 && !fk_rows_preferred(a, dp)) return false;
+    if (a.n_joints % 2 == 0)
+        rc = stages == 2 ? launch_fk_rows_cfg<2, 2>(a, dp, team_cap) : stages == 3 ? launch_fk_rows_cfg<3, 2>(a, dp, team_cap) : launch_fk_rows_cfg<4, 2>(a, dp, team_cap);
+    else
+        rc = stages == 2 ? launch_fk_rows_cfg<2, 1>(a, dp, team_cap) : stages == 3 ? launch_fk_rows_cfg<3, 1>(a, dp, team_cap) : launch_fk_rows_cfg<4, 1>(a, dp, team_cap);
+    return true;
+}
+
+// ---- fk_quat, quaternion-chain kernel (fk_quat_kernel.cuh) ------------------------------------
+int launch_fk_quat_chain(const FkArgs &a, const DeviceProps &dp) {
+    constexpr int WARPS = 4;
+    // like to_root_dual_quat: the largest flush group that still lets TWO 4-warp blocks share an SM
+    const int budget = (dp.smem_optin - 2048) / 2;
+    int group = a.n_joints;
+    if (pmb::fkq_geom(group, WARPS, a.n_joints, a.n_slots).block_bytes > budget) {
+        group = ((a.n_joints + 7) / 8) * 8;
+        while (group > 8 && pmb::fkq_geom(group, WARPS, a.n_joints, a.n_slots).block_bytes > budget) group -= 8;
+    }
+    // ... unless that leaves flushes of 8 joints (deep orderings with many live slots): measured at 4M x 65,
+    // one block per SM flushing 24 joints at a time beats two blocks flushing 8 (3.16 ms vs 3.87 ms)
+    if (group < 16 && a.n_joints > 16) {
+        int g1 = 24;
+        while (g1 > 8 && pmb::fkq_geom(g1, WARPS, a.n_joints, a.n_slots).block_bytes > dp.smem_optin) g1 -= 8;
+        if (g1 > group) group = g1;
+    }
+    if (knob_set(K_FKQ_GROUP)) {
+        const int v = knob(K_FKQ_GROUP, 0);
+        if (v >= a.n_joints) group = a.n_joints;  // whole rows
+        else if (v >= 8 && v % 8 == 0) group = v;
+    }
+    const int smem = pmb::fkq_geom(group, WARPS, a.n_joints, a.n_slots).block_bytes;
+    if (smem > dp.smem_optin)
+        return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
+    auto kernel = a.pos ? pmb::fk_quat_chain_kernel<WARPS, true> : pmb::fk_quat_chain_kernel<WARPS, false>;
+    int per_sm = 0, rc = kernel_fit(kernel, dp, WARPS * 32, smem, per_sm);
+    if (rc) return rc;
+    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk_quat kernel does not fit on an SM");
+    CUtensorMap tm;
+    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk))) return rc;
+    per_sm = std::max(1, std::min(per_sm, knob(K_FKQ_BLOCKS_PER_SM, per_sm)));
+    const long long tiles = (a.n_frames + 31) / 32;
+    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
+    auto magic_of = [](int d) { return static_cast<uint32_t>((1ULL << 32) / static_cast<uint32_t>(d)) + 1u; };
+    const int tail = a.n_joints % group ? a.n_joints % group : group;
+    note_variant("fk_quat_chain_kernel<WARPS=%d,POS=%d> group=%d grid=%lld smem=%d", WARPS, a.pos ? 1 : 0, group, blocks, smem);
+    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(
+        tm, a.gpos, a.gstride, a.offsets, a.pos, reinterpret_cast<float4 *>(a.rout), a.n_frames, a.n_joints, a.n_slots, group,
+        magic_of(group), magic_of(tail), magic_of(3 * group), magic_of(3 * tail), *a.prog);
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
+inline bool fk_fits(int group, int vec, int rw, int warps, const FkArgs &a, const DeviceProps &dp) {
+    return pmb::fk_geom(group, vec, rw, warps, a.n_joints, a.n_slots).block_bytes <= dp.smem_optin;
+}
+
+// Output flush group (see fk_kernel.cuh): whole rows if a block of >= 4 warps fits, else the largest group
+// that does.  FULL = the main entry point gets every variant; the rarer ones (per-frame offsets, quaternion
+// output) get the two extremes only, to keep the build small.
+template <int VEC, bool PF, bool QO, bool FULL>
+int launch_fk_group(const FkArgs &a, const DeviceProps &dp) {
+    constexpr int RW = QO ? 4 : 9;
+    const int force_group = knob(K_FK_GROUP, -1);
+    const int force_warps = knob(K_FK_WARPS, -1);
+    auto want = [&](int group, int warps) {
+        if (force_group >= 0 && force_group != group) return false;
+        if (force_warps >= 0 && force_warps != warps) return false;
+        return fk_fits(group, VEC, RW, warps, a, dp);
+    };
+    // Measured on B200: whole-row staging with 4 warps per SM is the fastest layout whenever it
+    // fits (1M x 22: 0.242 ms; 5 warps 0.262, 3 warps 0.298); otherwise the largest flush group that keeps
+    // 4 warps per block wins (4M x 52: G = 16 4.77 TB/s vs dense with 2 warps 3.2 TB/s).
+    // (whole rows are bank-conflict free only for odd J or J = 2 mod 4; unless forced, other joint counts take a
+    // padded flush group)
+    const bool dense_ok = QO || force_group == 0 || a.n_joints % 4 != 0;
+    if (dense_ok && want(0, 4)) return launch_fk_cfg<0, 4, VEC, PF, QO>(a, dp);
+    if constexpr (FULL) {
+        if (force_warps == 5 && want(0, 5)) return launch_fk_cfg<0, 5, VEC, PF, QO>(a, dp);
+        if (force_warps == 2 && want(0, 2)) return launch_fk_cfg<0, 2, VEC, PF, QO>(a, dp);
+        if (want(32, 4)) return launch_fk_cfg<32, 4, VEC, PF, QO>(a, dp);
+        if (want(16, 4)) return launch_fk_cfg<16, 4, VEC, PF, QO>(a, dp);
+    }
+    if (want(8, 4)) return launch_fk_cfg<8, 4, VEC, PF, QO>(a, dp);
+    if (want(8, 1)) return launch_fk_cfg<8, 1, VEC, PF, QO>(a, dp);
+    if (force_group >= 0 || force_warps >= 0) return fail(PMB_ERR_SHAPE, "PMB_FK_GROUP / PMB_FK_WARPS select no available variant");
+    return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", a.n_slots);
+}
+
+template <bool PF, bool QO>
+int launch_fk(const FkArgs &a, const DeviceProps &dp) {
+    // 64-bit staging / stores need 8-byte aligned rows: even joint count.
+    if ((a.n_joints % 2) == 0) return launch_fk_group<2, PF, QO, !PF && !QO>(a, dp);
+    return launch_fk_group<1, PF, QO, !PF && !QO>(a, dp);
+}
+
+int fk_common(const float *rot, const float *gpos, int64_t gstride, const float *offsets, int64_t ostride,
+              const int64_t *parents_host, int64_t n_frames, int32_t n_joints, float *pos, float *rout, bool quat_out,
+              void *stream) {
+    const bool rotations_only = quat_out && ostride == 0 && !pos;  // fk_quat without positions (mirror)
+    if (!rot || !gpos || !offsets || (!pos && !rotations_only) || !rout) return fail(PMB_ERR_NULL, "fk: NULL array pointer");
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
+    if (n_frames > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames must be below 2^31 per call");
+    if (gstride != 0 && gstride != 3) return fail(PMB_ERR_SHAPE, "gpos_frame_stride must be 0 or 3");
+    if (ostride != 0 && ostride != 3LL * n_joints) return fail(PMB_ERR_SHAPE, "offsets_frame_stride must be 0 or 3*n_joints");
+    if (!aligned16(rot)) return fail(PMB_ERR_ALIGN, "rot must be 16-byte aligned");
+    if (!aligned16(rout) || (pos && !aligned16(pos))) return fail(PMB_ERR_ALIGN, "output arrays must be 16-byte aligned");
+    const pmb::JointProgram *prog = nullptr;
+    int n_slots = 0;
+    int rc = joint_program(parents_host, n_joints, false, prog, n_slots);
+    if (rc) return rc;
+    if (n_frames == 0) return PMB_OK;
+    DeviceProps dp;
+    if ((rc = device_props(dp))) return rc;
+    FkArgs a{rot, gpos, offsets, gstride, ostride, pos, rout, n_frames, n_joints, n_slots, prog, parents_host,
+             static_cast<cudaStream_t>(stream)};
+    if (ostride == 0 && !quat_out) {
+        int rrc = PMB_OK;
+        if (try_fk_tracks(a, dp, rrc)) return rrc;
+        const bool rows_first = fk_rows_preferred(a, dp) && knob(K_FK_ROWS, -1) != 0;
+        if (try_fk_lanes(a, dp, rrc, rows_first || knob(K_FK_ROWS, -1) == 1)) return rrc;
+        if (try_fk_rows(a, dp, rrc)) return rrc;
+    }
+    if (ostride == 0 && quat_out && (rotations_only || knob(K_FKQ_MATRIX, 0) == 0)) return launch_fk_quat_chain(a, dp);
+    if (ostride == 0) return quat_out ? launch_fk<false, true>(a, dp) : launch_fk<false, false>(a, dp);
+    return quat_out ? launch_fk<true, true>(a, dp) : launch_fk<true, false>(a, dp);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pmb_fk_f32(const float *rot, const float *global_pos, int64_t gpos_frame_stride, const float *offsets,
+               int64_t offsets_frame_stride, const int64_t *parents_host, int64_t n_frames, int32_t n_joints, float *positions,
+               float *rotmats, void *stream) {
+    return fk_common(rot, global_pos, gpos_frame_stride, offsets, offsets_frame_stride, parents_host, n_frames, n_joints, positions,
+                     rotmats, false, stream);
+}
+
+int pmb_fk_quat_f32(const float *rot, const float *global_pos, int64_t gpos_frame_stride, const float *offsets,
+                    int64_t offsets_frame_stride, const int64_t *parents_host, int64_t n_frames, int32_t n_joints, float *positions,
+                    float *global_rots, void *stream) {
+    return fk_common(rot, global_pos, gpos_frame_stride, offsets, offsets_frame_stride, parents_host, n_frames, n_joints, positions,
+                     global_rots, true, stream);
+}
+
+}  // extern "C"

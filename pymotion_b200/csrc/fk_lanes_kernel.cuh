@@ -52,10 +52,9 @@ __device__ __forceinline__ float4 lds128_ro(uint32_t addr) {
 struct FkLanesGeom {
     int box_bytes, tab_bytes, warp_bytes, block_bytes;
 };
-// tile_in: the input ring holds whole tiles (FR x 16 J contiguous bytes + one chunk of slack) instead of boxes
-__host__ __device__ inline FkLanesGeom fk_lanes_geom(int fr, int warps, int n_joints, int n_boxes = 2, bool tile_in = false) {
+__host__ __device__ inline FkLanesGeom fk_lanes_geom(int fr, int warps, int n_joints, int n_boxes = 2) {
     FkLanesGeom g;
-    g.box_bytes = tile_in ? ((fr * 16 * n_joints + 128 + 127) & ~127) : fr * 128;  // FR frames x 8 joints x 16 bytes
+    g.box_bytes = fr * 128;  // FR frames x 8 joints x 16 bytes
     g.tab_bytes = ((n_joints + kChunk) * 16 + 127) & ~127;     // padded: the tail chunk and the one-ahead prefetch read past J
     // per warp: NB boxes | rotation stage | position stage | NB mbarriers (32 bytes reserved) | 32 fence words
     g.warp_bytes = ((n_boxes * g.box_bytes + fr * 48 * n_joints + 32 + 128) + 127) & ~127;
@@ -64,21 +63,18 @@ __host__ __device__ inline FkLanesGeom fk_lanes_geom(int fr, int warps, int n_jo
 }
 
 // NB: TMA boxes in flight per warp (ring depth, 2 .. 4).
-// TILE_IN: the quaternions of a tile arrive as ONE contiguous bulk copy (FR x 16 J bytes, row-major as in global
-// memory) instead of swizzled boxes of 8 joints: one sequential DRAM burst per tile.  The per-lane 16-byte reads of
-// the row-major image are conflict free unless J is a multiple of 4 (the 3-4 frames of an 8-lane phase are J float4
-// apart), which is when the host uses it.
-template <int FR, int WARPS, int NB, bool TILE_IN = false>
+// (Measured and retired, see experiments/retired/README.md: whole-tile contiguous input, L2 prefetch of the next
+// tile, evict-first stores.)
+template <int FR, int WARPS, int NB>
 __global__ void __launch_bounds__(WARPS *kWarp)
 fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                 const float *__restrict__ offsets, float *__restrict__ pos, float *__restrict__ rout,
-                long long n_frames, int n_joints, int st_hint, const float *__restrict__ rot_prefetch,
-                const __grid_constant__ JointProgram prog) {
+                long long n_frames, int n_joints, const __grid_constant__ JointProgram prog) {
     constexpr int C = kChunk;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    const FkLanesGeom geo = fk_lanes_geom(FR, WARPS, n_joints, NB, TILE_IN);
+    const FkLanesGeom geo = fk_lanes_geom(FR, WARPS, n_joints, NB);
     const int BOX = geo.box_bytes;  // bytes of one input buffer (a box, or a whole tile)
 
     float4 *tab = reinterpret_cast<float4 *>(smem_raw);
@@ -132,18 +128,10 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
     int la_c0 = 0;
     auto issue_next = [&](int buf) {
         if (la_tile < n_tiles) {
-            if (TILE_IN) {
-                const long long rows = min(static_cast<long long>(FR), n_frames - la_tile * FR);
-                const uint32_t bytes = static_cast<uint32_t>(rows * 16 * n_joints);
-                mbar_arrive_expect_tx(bar0 + 8 * buf, bytes);
-                bulk_load_1d(box0 + buf * BOX, rot_prefetch + la_tile * (FR * 4 * n_joints), bytes, bar0 + 8 * buf);
-                la_tile += tile_stride;
-            } else {
-                mbar_arrive_expect_tx(bar0 + 8 * buf, BOX);
-                tma_load_2d(box0 + buf * BOX, &tm_rot, 4 * la_c0, static_cast<int>(la_tile * FR), bar0 + 8 * buf);
-                la_c0 += C;
-                if (la_c0 >= n_joints) la_c0 = 0, la_tile += tile_stride;
-            }
+            mbar_arrive_expect_tx(bar0 + 8 * buf, BOX);
+            tma_load_2d(box0 + buf * BOX, &tm_rot, 4 * la_c0, static_cast<int>(la_tile * FR), bar0 + 8 * buf);
+            la_c0 += C;
+            if (la_c0 >= n_joints) la_c0 = 0, la_tile += tile_stride;
         }
     };
     if (lane == 0) {
@@ -165,23 +153,7 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
         for (int c0 = 0; c0 < n_joints; c0 += C) {
             const int cnt = active ? n_joints - c0 : 0;  // joints left (>= 8 except in a partial last chunk); 0 = never store
             float4 q[C];
-            if (TILE_IN) {
-                // one buffer per TILE: wait at its first chunk, release it after the last chunk's loads
-                const uint32_t buf = k % NB;
-                if (c0 == 0) mbar_wait(bar0 + 8 * buf, (k / NB) & 1);
-                const float4 *in_row = boxes + buf * (BOX / 16) + f * n_joints + c0;
-#pragma unroll
-                for (int jj = 0; jj < C; ++jj) q[jj] = in_row[jj];  // (a partial last chunk reads into the buffer's slack)
-                if (c0 + C >= n_joints) {
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int jj = 0; jj < C; ++jj) acc |= __float_as_uint(q[jj].x);
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
-                    __syncwarp();
-                    if (lane == 0) issue_next(buf);
-                    ++k;
-                }
-            } else {
+            {
                 const uint32_t buf = k % NB;
                 mbar_wait(bar0 + 8 * buf, (k / NB) & 1);
                 ++k;
@@ -218,9 +190,6 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             if (c0 == 0) {
                 const long long next_tile = tile + tile_stride;
                 if (next_tile < n_tiles) gnext = __ldg(gpos + min(next_tile * FR + f, n_frames - 1) * gstride + a);
-                // the NEXT tile's quaternions (FR * 16 J contiguous bytes) into L2, a whole tile ahead of its boxes
-                if (!TILE_IN && lane == 0 && rot_prefetch && next_tile + 1 <= n_tiles - 1)
-                    bulk_prefetch_l2(rot_prefetch + next_tile * (FR * 4 * n_joints), static_cast<uint32_t>(FR * 16 * n_joints));
                 if (lane == 0 && draining) bulk_wait_read0();  // the previous tile has left the stage
                 __syncwarp();
             }
@@ -268,14 +237,8 @@ fk_lanes_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restr
             fence_proxy_async_smem();  // this lane's stage writes -> visible to the async proxy
             __syncwarp();
             if (lane == 0) {
-                if (st_hint & 1) {
-                    const uint64_t pol = l2_policy_evict_first();
-                    bulk_store_hint(rg, smem_u32(Rst), static_cast<uint32_t>(FR * rpitch * 4), pol);
-                    bulk_store_hint(pg, smem_u32(Pst), static_cast<uint32_t>(FR * ppitch * 4), pol);
-                } else {
-                    bulk_store(rg, smem_u32(Rst), static_cast<uint32_t>(FR * rpitch * 4));
-                    bulk_store(pg, smem_u32(Pst), static_cast<uint32_t>(FR * ppitch * 4));
-                }
+                bulk_store(rg, smem_u32(Rst), static_cast<uint32_t>(FR * rpitch * 4));
+                bulk_store(pg, smem_u32(Pst), static_cast<uint32_t>(FR * ppitch * 4));
                 bulk_commit();
                 draining = true;
             }

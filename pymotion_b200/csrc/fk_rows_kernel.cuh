@@ -135,7 +135,7 @@ struct RowCtx {
     uint32_t full0, empty0, stage_full, stage_free, fence_word;
     const float *gpos;
     float *pos, *rout;
-    long long gstride, n_frames, n_tiles, tile_stride, first_tile;  // n_tiles here = end of this team's tile range
+    long long gstride, n_frames, n_tiles, tile_stride, first_tile;
     int n_joints, lane;
 };
 
@@ -280,8 +280,7 @@ template <int S, int VEC>
 __global__ void __launch_bounds__(kRowThreads, 5)
 fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                const float *__restrict__ offsets, float *__restrict__ pos, float *__restrict__ rout,
-               long long n_frames, int n_joints, int st_hint, const float *__restrict__ rot_prefetch,
-               const __grid_constant__ JointProgram prog) {
+               long long n_frames, int n_joints, const __grid_constant__ JointProgram prog) {
     constexpr int C = kChunk;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -297,14 +296,11 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
                    stage_free = stage_full + 8;
     const uint32_t box0 = smem_u32(boxes);
 
-    // tile order (experiment, bit 1 of st_hint): 0 = round robin over the teams (a window of consecutive tiles slides
-    // through the arrays), 1 = one contiguous range of tiles per team
-    const long long n_tiles_all = (n_frames + kWarp - 1) / kWarp;
-    const bool blocked = (st_hint & 2) != 0;
-    const long long per_team = (n_tiles_all + gridDim.x - 1) / gridDim.x;
-    const long long tile_stride = blocked ? 1 : gridDim.x;
-    const long long tile_first = blocked ? blockIdx.x * per_team : blockIdx.x;
-    const long long n_tiles = blocked ? min(n_tiles_all, tile_first + per_team) : n_tiles_all;  // end of this team's range
+    // tiles go round robin over the teams: a window of consecutive tiles slides through the arrays (measured: one
+    // contiguous range of tiles per team is 4 % slower)
+    const long long n_tiles = (n_frames + kWarp - 1) / kWarp;
+    const long long tile_stride = gridDim.x;
+    const long long tile_first = blockIdx.x;
     const int rpitch = 9 * n_joints, ppitch = 3 * n_joints;
 
     if (threadIdx.x == 0) {
@@ -334,9 +330,6 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
         if (lane == 0) {
             uint32_t k = 0;
             for (long long t = tile_first; t < n_tiles; t += tile_stride) {
-                // the team's NEXT tile (32 * 16 J contiguous bytes) into L2, a whole tile ahead of its boxes
-                if (rot_prefetch && t + tile_stride < n_tiles - 1)
-                    bulk_prefetch_l2(rot_prefetch + (t + tile_stride) * (kWarp * 4 * n_joints), static_cast<uint32_t>(kWarp * 16 * n_joints));
                 for (int c0 = 0; c0 < n_joints; c0 += C, ++k) {
                     const uint32_t buf = k % S;
                     if (k >= S) mbar_wait_long(empty0 + 8 * buf, ((k / S) - 1) & 1);  // all three row warps have read it
@@ -358,14 +351,8 @@ fk_rows_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restri
                 float *rg = rout + f0 * rpitch, *pg = pos + f0 * ppitch;
                 const uint32_t rbytes = static_cast<uint32_t>(kWarp * rpitch * 4), pbytes = static_cast<uint32_t>(kWarp * ppitch * 4);
                 // two contiguous, 128-byte aligned spans
-                if (st_hint & 1) {
-                    const uint64_t pol = l2_policy_evict_first();
-                    bulk_store_hint(rg, smem_u32(Rst), rbytes, pol);
-                    bulk_store_hint(pg, smem_u32(Pst), pbytes, pol);
-                } else {
-                    bulk_store(rg, smem_u32(Rst), rbytes);
-                    bulk_store(pg, smem_u32(Pst), pbytes);
-                }
+                bulk_store(rg, smem_u32(Rst), rbytes);
+                bulk_store(pg, smem_u32(Pst), pbytes);
                 bulk_commit();
                 bulk_wait_read0();  // the engine has read the stage: the row warps may overwrite it
                 mbar_arrive(stage_free);

@@ -57,11 +57,15 @@ def fk_sharded(rot, global_pos, offsets, parents, gather_positions: bool = False
     are all-gathered (the optional exchange of BASELINE.json config 5) and returned in full."""
     from .ops import skeleton
 
+    rot, global_pos, offsets = torch.as_tensor(rot), torch.as_tensor(global_pos), torch.as_tensor(offsets)
+    if rot.dim() != 3:
+        raise ValueError(f"fk_sharded shards the leading axis of rot [n_frames, n_joints, 4], got {tuple(rot.shape)}")
     n_frames = rot.shape[0]
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_bounds(n_frames, world, rank)
-    gp = global_pos if global_pos.shape[0] != n_frames else global_pos[lo:hi]
-    off = offsets if offsets.dim() == 2 else offsets[lo:hi]
+    # per-frame operands are recognised by RANK (a shared [3] root position must not be sliced when n_frames == 3)
+    gp = global_pos[lo:hi] if (global_pos.dim() == rot.dim() - 1 and global_pos.shape[0] == n_frames) else global_pos
+    off = offsets[lo:hi] if offsets.dim() == 3 else offsets
     pos, rotm = skeleton.fk(rot[lo:hi], gp, off, parents)
     if gather_positions:
         pos = all_gather_frames(pos, n_frames, group)

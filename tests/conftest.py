@@ -43,3 +43,20 @@ def golden_ik():
 @pytest.fixture(scope="session")
 def golden_misc():
     return dict(np.load(os.path.join(GOLDEN, "misc.npz")))
+
+
+@pytest.fixture
+def set_knobs(monkeypatch):
+    """Force kernel variants for one test: the library honours its PMB_* experiment knobs only under
+    PMB_EXPERIMENT=1 and reads them once, so set the environment and ask it to re-read (pmb_reload_knobs)."""
+    from pymotion_b200 import _lib
+
+    def apply(knobs: dict):
+        monkeypatch.setenv("PMB_EXPERIMENT", "1")
+        for k, v in knobs.items():
+            monkeypatch.setenv(k, str(v))
+        _lib.load().pmb_reload_knobs()
+
+    yield apply
+    monkeypatch.undo()
+    _lib.load().pmb_reload_knobs()

@@ -139,3 +139,56 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "oracle" not in text.lower() or f == "_lib.py" and False, f"{f} mentions the oracle"
+
+
+def _track_schedule(lib, parents, n_tracks):
+    par = np.asarray(parents, dtype=np.int64)
+    codes = np.zeros(1024, dtype=np.uint32)
+    steps = lib.pmb_build_track_schedule(par.ctypes.data, len(par), n_tracks, codes.ctypes.data, codes.size)
+    assert steps > 0, _lib.last_error()
+    return steps, codes[: steps * n_tracks].reshape(steps, n_tracks)
+
+
+@pytest.mark.parametrize("name", ["body22", "smplh52", "deep65", "chain3", "body32"])
+@pytest.mark.parametrize("n_tracks", [1, 2, 3, 4])
+def test_track_schedule_is_a_valid_minimal_tree_schedule(name, n_tracks):
+    """The schedule of the fk track kernel: every joint exactly once, after its parent's step; `carry` only when the
+    parent is the same track's previous item; and the step count is the optimum for unit tasks with tree precedence
+    on `n_tracks` machines (Hu's bound: max over levels l of  l + ceil(#joints deeper than l / n_tracks))."""
+    lib = _lib.load()
+    par = parents_of(name)
+    n = len(par)
+    steps, code = _track_schedule(lib, par, n_tracks)
+    CARRY, NOOP = 1 << 20, 1 << 21
+    step_of, track_of = {}, {}
+    for t in range(steps):
+        for u in range(n_tracks):
+            c = int(code[t, u])
+            if c & NOOP:
+                continue
+            j, p = c & 0x3FF, (c >> 10) & 0x3FF
+            assert j not in step_of, f"joint {j} scheduled twice"
+            step_of[j], track_of[j] = t, u
+            if j == 0:
+                assert t == 0 and u == 0 and (c & CARRY)
+                continue
+            assert p == par[j]
+            assert step_of[p] < t, f"joint {j} at step {t} before its parent {p}"
+            if c & CARRY:
+                assert step_of[p] == t - 1 and track_of[p] == u
+    assert sorted(step_of) == list(range(n))
+    depth = np.zeros(n, dtype=int)
+    for i in range(1, n):
+        depth[i] = depth[par[i]] + 1
+    bound = max(l + 1 + -(-int((depth > l).sum()) // n_tracks) for l in range(int(depth.max()) + 1))
+    assert steps == max(bound, int(depth.max()) + 1)
+
+
+def test_track_schedule_rejects_bad_tables():
+    lib = _lib.load()
+    codes = np.zeros(64, dtype=np.uint32)
+    bad = np.array([0, 2, 1], dtype=np.int64)
+    assert lib.pmb_build_track_schedule(bad.ctypes.data, 3, 2, codes.ctypes.data, 64) == _lib.PMB_ERR_TOPOLOGY
+    ok = np.array([0, 0, 1], dtype=np.int64)
+    assert lib.pmb_build_track_schedule(ok.ctypes.data, 3, 9, codes.ctypes.data, 64) == _lib.PMB_ERR_SHAPE
+    assert lib.pmb_build_track_schedule(ok.ctypes.data, 3, 2, codes.ctypes.data, 2) == _lib.PMB_ERR_SHAPE

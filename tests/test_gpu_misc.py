@@ -92,7 +92,7 @@ def test_vector_normalize(mods, golden_misc):
 
 
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 7, 1001, 4098, 65539])
-def test_vector_normalize_vec3_paths(mods, monkeypatch, n):
+def test_vector_normalize_vec3_paths(mods, set_knobs, n):
     """3-vectors go four per thread when the arrays are 16-byte aligned (the last n % 4 through the generic kernel):
     same bits as the generic kernel, on aligned and on 12-byte-offset arrays, and the oracle's values."""
     *_, vec = mods
@@ -102,9 +102,9 @@ def test_vector_normalize_vec3_paths(mods, monkeypatch, n):
     want = orc.vec_normalize(v)
     fast = vec.normalize(v)
     assert_allclose(fast, want, **TOL)
-    monkeypatch.setenv("PMB_VEC3_X4", "0")
+    set_knobs({"PMB_VEC3_X4": "0"})
     assert_array_equal(vec.normalize(v), fast)
-    monkeypatch.delenv("PMB_VEC3_X4")
+    set_knobs({"PMB_VEC3_X4": "1"})
     t = torch.from_numpy(v).cuda()
     shifted = vec.normalize(t[1:])  # data pointer 12 bytes past a 16-byte boundary: generic kernel
     assert isinstance(shifted, torch.Tensor)

@@ -12,6 +12,7 @@ from numpy.testing import assert_allclose
 from oracle import oracle_c
 from oracle import pymotion_oracle as orc
 from pymotion_b200.topologies import TOPOLOGIES, parents_of, synth_numpy, synth_torch
+from pymotion_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -509,12 +510,11 @@ def test_host_buffer_entry_point(sk, golden_fk):
     {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "4", "PMB_FK_BLOCKS_PER_SM": "1"},
 ])
 @pytest.mark.parametrize("name,n_frames", [("body22", 4099), ("smplh52", 2050), ("deep65", 1031), ("chain3", 777)])
-def test_fk_every_variant(sk, monkeypatch, knobs, name, n_frames):
+def test_fk_every_variant(sk, set_knobs, knobs, name, n_frames):
     """The launch heuristic picks one variant per shape; force each of them (ragged frame counts so the
     remainder tile and remainder group paths run) and compare with the oracle.  A variant that does not
     fit the shape (e.g. whole rows of a 65-joint skeleton with 5 warps) must refuse, not fall back."""
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
+    set_knobs(knobs)
     par = parents_of(name)
     rot, gp, off = synth_numpy(n_frames, par, seed=len(par) + n_frames)
     want_pos, want_rotm = orc.fk(rot, gp, off, par)
@@ -550,12 +550,11 @@ def test_fk_every_variant(sk, monkeypatch, knobs, name, n_frames):
 ])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_050), ("deep65", 10_031), ("chain3", 777),
                                            ("body22", 31)])
-def test_fk_row_team_kernel(sk, monkeypatch, knobs, name, n_frames):
+def test_fk_row_team_kernel(sk, set_knobs, knobs, name, n_frames):
     """The row-team kernel (three warps per tile, loader and drainer threads): forced for every ring depth,
     with ragged frame counts (remainder tile through the drainer's 16-byte tail path) and with one block per
     SM so that every team walks several tiles (stage reuse, ring wrap-around)."""
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
+    set_knobs(knobs)
     par = parents_of(name)
     rot, gp, off = synth_numpy(n_frames, par, seed=3 * len(par) + n_frames)
     want_pos, want_rotm = orc.fk(rot, gp, off, par)
@@ -569,13 +568,12 @@ def test_fk_row_team_kernel(sk, monkeypatch, knobs, name, n_frames):
                                    {"PMB_FKQ_BLOCKS_PER_SM": "1"}, {"PMB_FKQ_MATRIX": "1"}])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 6_050), ("deep65", 5_031), ("chain3", 777),
                                            ("body40", 2_049)])
-def test_fk_quat_every_variant(sk, monkeypatch, knobs, name, n_frames):
+def test_fk_quat_every_variant(sk, set_knobs, knobs, name, n_frames):
     """fk_quat: the quaternion-chain kernel for every flush group (ragged frame counts: remainder tile and
     remainder group), one block per SM (several tiles per warp), and the older matrix-path kernel.  Positions
     at the hot-path tolerance; rotations equal to quat.from_matrix(fk rotmats) with the reference's sign
     convention except where from_matrix's branch test is within rounding of a tie."""
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
+    set_knobs(knobs)
     par = parents_of(name)
     rot, gp, off = synth_numpy(n_frames, par, seed=11 * len(par) + n_frames)
     want_pos, want_rotm = orc.fk(rot, gp, off, par)
@@ -596,16 +594,13 @@ def test_fk_quat_every_variant(sk, monkeypatch, knobs, name, n_frames):
     {"PMB_FK_LANES": "1", "PMB_FK_WARPS": "2", "PMB_FK_BLOCKS_PER_SM": "1"},  # many tiles per warp
     {"PMB_FK_LANES": "1", "PMB_FK_NB": "3"},                               # deeper TMA ring
     {"PMB_FK_LANES": "1", "PMB_FK_NB": "4", "PMB_FK_WARPS": "1"},
-    {"PMB_FK_LANES": "1", "PMB_FK_TILE_IN": "1"},                          # whole-tile contiguous input
-    {"PMB_FK_LANES": "1", "PMB_FK_TILE_IN": "1", "PMB_FK_NB": "3", "PMB_FK_BLOCKS_PER_SM": "1"},
 ])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
                                            ("body32", 5_009), ("body22", 7)])
-def test_fk_lane_kernel(sk, monkeypatch, knobs, name, n_frames):
+def test_fk_lane_kernel(sk, set_knobs, knobs, name, n_frames):
     """The lane = (frame, row) kernel: tiles of 8 / 10 frames per warp, forced for both tile sizes and every block
     shape, ragged frame counts (remainder tile), one block per SM (stage reuse, ring wrap-around)."""
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
+    set_knobs(knobs)
     par = parents_of(name)
     rot, gp, off = synth_numpy(n_frames, par, seed=5 * len(par) + n_frames)
     want_pos, want_rotm = orc.fk(rot, gp, off, par)
@@ -616,32 +611,79 @@ def test_fk_lane_kernel(sk, monkeypatch, knobs, name, n_frames):
 
 
 @pytest.mark.parametrize("knobs", [
-    {"PMB_FK_LG": "32"},
-    {"PMB_FK_LG": "16"},
-    {"PMB_FK_LG": "32", "PMB_FK_NB": "3", "PMB_FK_BLOCKS_PER_SM": "1"},   # many tiles per warp, deeper ring
-    {"PMB_FK_LG": "16", "PMB_FK_NB": "3"},
+    {"PMB_FK_TRACKS": "1"},                                                   # two tracks, ring depth 4, tiles of 10 frames
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_D": "4"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_D": "8", "PMB_FK_FR": "8"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_D": "2"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_D": "4", "PMB_FK_FR": "8", "PMB_FK_WARPS_PER_SM": "1"},  # many tiles per warp
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "3", "PMB_FK_D": "2"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "3", "PMB_FK_D": "3", "PMB_FK_L2_PREFETCH": "0"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "4", "PMB_FK_D": "2"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "4", "PMB_FK_D": "3", "PMB_FK_WARPS_PER_SM": "2"},
 ])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
-                                           ("body32", 5_009), ("body40", 3_001), ("body22", 7)])
-def test_fk_grouped_lane_kernel(sk, monkeypatch, knobs, name, n_frames):
-    """The lane kernel with a grouped stage (flush groups of 16 / 32 joints, branch rows in slots): every joint
-    count is bank-conflict free, remainder groups (22 = 16 + 6, 65 = 2 x 32 + 1) and remainder tiles included."""
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)
+                                           ("body32", 5_009), ("body22", 7), ("body16", 1), ("deep65", 29)])
+def test_fk_track_kernel(sk, set_knobs, knobs, name, n_frames):
+    """The track kernel (U independent joints per step from the host's level schedule, register ring of quaternions,
+    stage at the 16-byte phase of the global span with head / tail words stored by single lanes): every (U, D) that
+    is built, both tile sizes, odd joint counts with 10-frame tiles (unaligned spans), ragged frame counts (remainder
+    tile shorter than the ring), one warp per SM (stage and ring reuse across many tiles)."""
+    set_knobs(knobs)
     par = parents_of(name)
-    rot, gp, off = synth_numpy(n_frames, par, seed=7 * len(par) + n_frames)
+    rot, gp, off = synth_numpy(n_frames, par, seed=13 * len(par) + n_frames)
     want_pos, want_rotm = orc.fk(rot, gp, off, par)
     for _ in range(2):
         pos, rotm = sk.fk(rot, gp, off, par)
+        assert "fk_tracks_kernel" in _lib.load().pmb_last_variant().decode()
         assert_allclose(pos, want_pos, **TOL)
         assert_allclose(rotm, want_rotm, **TOL)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_fk_track_kernel_random_trees(sk, set_knobs, seed):
+    """Random topologies (bushy, deep, up to 200 joints) through the track schedule with 1 .. 4 tracks."""
+    rng = np.random.default_rng(1000 + seed)
+    n_joints = int(rng.integers(2, 200))
+    par = np.zeros(n_joints, dtype=np.int64)
+    for i in range(1, n_joints):
+        par[i] = rng.integers(max(0, i - 1 - int(rng.integers(0, 12))), i)
+    n_frames = int(rng.integers(1, 3000))
+    rot, gp, off = synth_numpy(n_frames, par, seed=seed)
+    want_pos, want_rotm = orc.fk(rot, gp, off, par)
+    for u, d in ((1, 4), (2, 4), (3, 3), (4, 2)):
+        set_knobs({"PMB_FK_TRACKS": "1", "PMB_FK_U": str(u), "PMB_FK_D": str(d), "PMB_FK_FR": "8" if n_joints > 150 else "10"})
+        pos, rotm = sk.fk(rot, gp, off, par)
+        assert "fk_tracks_kernel" in _lib.load().pmb_last_variant().decode()
+        assert_allclose(pos, want_pos, rtol=2e-5, atol=2e-5)
+        assert_allclose(rotm, want_rotm, rtol=2e-5, atol=2e-5)
+
+
+def test_knobs_are_ignored_without_the_experiment_switch(sk, monkeypatch):
+    """A stray PMB_* variable in a user's environment must not change which kernel runs (or make a call fail):
+    knobs are honoured only under PMB_EXPERIMENT=1."""
+    lib = _lib.load()
+    par = parents_of("body22")
+    rot, gp, off = synth_numpy(257, par, seed=5)
+    monkeypatch.delenv("PMB_EXPERIMENT", raising=False)
+    lib.pmb_reload_knobs()
+    sk.fk(rot, gp, off, par)
+    default_variant = lib.pmb_last_variant().decode()
+    monkeypatch.setenv("PMB_FK_GROUP", "8")
+    monkeypatch.setenv("PMB_FK_WARPS", "7")  # selects no variant when honoured
+    lib.pmb_reload_knobs()
+    try:
+        sk.fk(rot, gp, off, par)
+        assert lib.pmb_last_variant().decode() == default_variant
+    finally:
+        monkeypatch.undo()
+        lib.pmb_reload_knobs()
+
+
 @pytest.mark.parametrize("group", [None, "8", "16", "24"])
 @pytest.mark.parametrize("name,n_frames", [("body22", 4099), ("smplh52", 2050), ("deep65", 1031), ("chain3", 777)])
-def test_to_root_dual_quat_every_group(sk, monkeypatch, group, name, n_frames):
+def test_to_root_dual_quat_every_group(sk, set_knobs, group, name, n_frames):
     if group is not None:
-        monkeypatch.setenv("PMB_DQ_GROUP", group)
+        set_knobs({"PMB_DQ_GROUP": group})
     par = parents_of(name)
     rot, gp, off = synth_numpy(n_frames, par, seed=7 * len(par) + n_frames)
     dq = sk.to_root_dual_quat(rot, gp, par, off)

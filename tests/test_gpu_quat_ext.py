@@ -115,7 +115,7 @@ def test_unroll_fixtures(quat, dquat, golden_quat_ext, tag):
 
 
 @pytest.mark.parametrize("n_steps,n_cols", [(1, 5), (127, 3), (128, 1), (129, 22), (5000, 22), (20_011, 7), (260, 512), (300, 700)])
-def test_unroll_scan_sizes(quat, dquat, monkeypatch, n_steps, n_cols):
+def test_unroll_scan_sizes(quat, dquat, set_knobs, n_steps, n_cols):
     """Chunk boundaries of the three-kernel scan (chunks of 128 steps), exact zeros (sign reset), one column, and both
     apply kernels (one block per chunk up to 512 columns, flat beyond)."""
     rng = np.random.default_rng(n_steps + n_cols)
@@ -127,9 +127,9 @@ def test_unroll_scan_sizes(quat, dquat, monkeypatch, n_steps, n_cols):
     got = quat.unroll(x, 0)
     assert_array_equal(got, want)
     assert (np.sum(got[1:] * got[:-1], axis=-1) >= 0).all()
-    monkeypatch.setenv("PMB_UNROLL_CHUNK_APPLY", "0")
+    set_knobs({"PMB_UNROLL_CHUNK_APPLY": "0"})
     assert_array_equal(quat.unroll(x, 0), want)
-    monkeypatch.delenv("PMB_UNROLL_CHUNK_APPLY")
+    set_knobs({"PMB_UNROLL_CHUNK_APPLY": "1"})
     dq = np.concatenate([x, rng.standard_normal((n_steps, n_cols, 4)).astype(np.float32)], axis=-1)
     assert_array_equal(dquat.unroll(dq, 0), orc.dq_unroll(dq, 0))
 

@@ -1,8 +1,8 @@
 """Drop-in check: every public function of the reference modules this package mirrors exists here under the same
 module path and name, with the same positional parameters in the same order and the same defaults
 (tests/golden/signatures.json is written from the real reference by oracle/gen_signatures.py).  The NumPy module and
-its torch twin map onto ONE module here; where the twins name a parameter differently (`axis` / `dim`) both are
-accepted.  CPU only: signatures are inspected, nothing is launched."""
+its torch twin are ONE implementation here, importable under both module paths (`quat` and `quat_torch`, ...);
+where the twins name a parameter differently (`axis` / `dim`) both are accepted.  CPU only: signatures are inspected, nothing is launched."""
 import importlib
 import inspect
 import json
@@ -18,7 +18,7 @@ ALIASES = {"axis": {"axis", "dim"}, "dim": {"axis", "dim"}}
 
 @pytest.mark.parametrize("ref_module", sorted(TABLE))
 def test_public_surface_and_signatures(ref_module):
-    ours = importlib.import_module("pymotion_b200." + ref_module.replace("_torch", ""))
+    ours = importlib.import_module("pymotion_b200." + ref_module)  # the twin's own module path (alias modules)
     for name, params in TABLE[ref_module].items():
         fn = getattr(ours, name, None)
         assert callable(fn), f"{ref_module}.{name} is missing"

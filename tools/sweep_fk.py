@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Kernel-only sweep of fk launch variants in ONE process (the library reads its PMB_* knobs at every
-launch).  Each line: workload, knobs, variant picked, ms, algorithmic GB/s, max |diff| vs the first
+"""Kernel-only sweep of fk launch variants in ONE process (PMB_EXPERIMENT=1 + pmb_reload_knobs() between
+variants).  Each line: workload, knobs, variant picked, ms, algorithmic GB/s, max |diff| vs the first
 knob set of the workload.
 
     python tools/sweep_fk.py [--workloads fk_1m_x_22,fk_4m_x_52,fk_4m_x_65] [--steps 30] < knobs.txt
@@ -20,9 +20,6 @@ import torch  # noqa: E402
 from bench import WORKLOADS, op_bytes_per_pose  # noqa: E402
 from pymotion_b200 import _lib  # noqa: E402
 from pymotion_b200.topologies import parents_of, synth_torch  # noqa: E402
-
-KNOBS = ("PMB_FK_ROWS", "PMB_FK_STAGES", "PMB_FK_BLOCKS_PER_SM", "PMB_FK_GROUP", "PMB_FK_WARPS", "PMB_DQ_GROUP",
-         "PMB_DQ_BLOCKS_PER_SM", "PMB_FKQ_GROUP")
 
 
 def main():
@@ -66,6 +63,8 @@ def main():
                 if kv != "-":
                     k, v = kv.split("=")
                     os.environ[k] = v
+            os.environ["PMB_EXPERIMENT"] = "1"
+            lib.pmb_reload_knobs()
             pos.zero_(), out.zero_()
             rc = step()
             if rc != 0:

@@ -3,20 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-A "step" is one pass of the hot path (`fk`) over one resident batch.  At N GPUs
-every rank runs the same per-GPU batch on its own frames (frame-axis shard, no
-data-path collective): weak scaling, value = all frames processed / max-over-ranks
-device time.  Prints ONE JSON line on rank 0.
+A "step" is one pass of the hot path (`fk`) over one resident batch.  At N GPUs every rank runs the same per-GPU
+batch on its own frames (frame-axis shard, no data-path collective): weak scaling, value = all frames processed /
+max-over-ranks device time.  Prints ONE JSON line on rank 0.
 
-  value      kernel throughput with inputs resident in HBM (CUDA events on the launch stream)
-  roofline   algorithmic bytes (64*J + 12 per pose) / kernel time vs MEASURED_PEAKS.json
-  e2e        same metric through the public host-buffer API (pymotion_b200.ops.skeleton.fk_host):
-             pinned host inputs -> H2D -> kernel -> D2H -> pinned host outputs, all inside the timing
-  cpu_baseline  the NumPy oracle port of the reference path timed on this box's host (rank 0, N=1)
+  value         kernel throughput of BASELINE config 2 (fk, 1M frames x 22 joints per GPU) with inputs resident in
+                HBM, CUDA events on the launch stream
+  roofline      algorithmic bytes (64 J + 12 per pose) / kernel time vs MEASURED_PEAKS.json
+  extra         the other BASELINE configs measured the same way in the same run: dual-quaternion round trip
+                1M x 22 (config 3), fk 4M x 65 (config 4), fk 4M x 52 per GPU (config 5: at --gpus 8 this IS
+                32M x 52) and, for N > 1, the OPTIONAL all-gather of positions timed on its own
+  e2e           same metric through the drop-in call the reference's users make -- pymotion_b200.ops.skeleton.fk
+                (host arrays in) -> host arrays out -- with the H2D / D2H copies inside the timing: page-locked
+                host tensors (headline `e2e.value`), plain pageable NumPy arrays, and fk_quat; next to the
+                measured H2D+D2H ceiling of this box for the same byte mix
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, staged by __graft_entry__.build()) timed on this box's host:
+                BASELINE config 1 exactly (1000 x 22, best of 20, fk / to_root_dual_quat / from_root_dual_quat)
+                and a bounded single-thread sample of the 1M x 22 workload
 
-`--impl reference` times the reference's CPU algorithm instead (NumPy oracle port --
-the reference is pure Python/NumPy and is not shipped to the GPU box -- on all host
-threads it can use, frames split across a thread pool).
+`--impl reference` times the reference's own CPU implementation of the path on all host threads: the real
+`pymotion.ops.skeleton.fk` from oracle/_ref (the NumPy oracle port only if the staged reference is missing), one
+full 1M x 22 batch per step, frames split over a thread pool in cache-sized blocks (NumPy releases the GIL).
 """
 from __future__ import annotations
 
@@ -32,11 +39,13 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 METRIC = "skeleton poses/sec (22 joints)"  # BASELINE.json; other workloads carry their own joint count
+UNIT = "poses/s"
+NOMINAL_HBM_GBS = 8000.0  # the peak north_star's 70 % target refers to
 
 
 def metric_of(n_joints: int) -> str:
     return f"skeleton poses/sec ({n_joints} joints)"
-UNIT = "poses/s"
+
 
 WORKLOADS = {
     # name: (topology, frames per GPU)   -- BASELINE.json configs[1], [3], [4]
@@ -51,6 +60,7 @@ WORKLOADS = {
 }
 # --kernel-only development workloads for the other ops of the path (BASELINE.json configs[2])
 DEV_OPS = ("fk", "to_dq", "from_dq", "round_trip", "fk_quat", "from_root_positions", "mirror_all")
+REF_BLOCK_FRAMES = 2048  # frames per reference call inside a thread: the working set of one call stays in cache
 
 
 def fk_bytes_per_pose(n_joints: int) -> int:
@@ -82,6 +92,22 @@ def ncu_traffic(workload: str):
             return json.load(fh).get(workload)
     except Exception:
         return None
+
+
+def shared_config(workload: str, world: int) -> dict:
+    """The `config` object: identical in both arms (the reference arm runs the same workload on the host)."""
+    from pymotion_b200.topologies import parents_of
+
+    topo, frames = WORKLOADS[workload]
+    n_joints = len(parents_of(topo))
+    return {
+        "workload": workload,
+        "frames_per_gpu": frames,
+        "n_joints": n_joints,
+        "topology": topo,
+        "sharding": f"frame axis, {world} shard(s), no data-path collective",
+        "l2": f"working set {fk_bytes_per_pose(n_joints) * frames / 1e9:.2f} GB per launch >> 126 MB L2: no flush needed",
+    }
 
 
 class ClockSampler(threading.Thread):
@@ -124,14 +150,20 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.002)
 
-    def summary(self):
+    def summary(self, windows=None):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "note": "NVML unavailable"}
         nv = self.nv
-        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in self.windows)]
+        windows = self.windows if windows is None else windows
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
         note = "sampled inside the timed regions"
         if len(inside) < 3:
-            inside, note = self.samples, "timed region shorter than the sampling period: all samples of the run"
+            lo = min(a for a, _ in windows) - 0.05 if windows else 0.0
+            hi = max(b for _, b in windows) + 0.05 if windows else float("inf")
+            near = [s for s in self.samples if lo <= s[0] <= hi]
+            inside = near if len(near) >= 3 else self.samples
+            note = "timed region shorter than the sampling period: samples within 50 ms of it" if inside is near else \
+                "timed region shorter than the sampling period: all samples of the run"
         mhz = sorted(s[1] for s in inside)
         mask = 0
         for s in inside:
@@ -157,21 +189,33 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- reference arm
-def numpy_port_threaded(rot, gpos, offsets, parents, n_threads: int):
-    """The reference algorithm (NumPy oracle port) over frame shards on a thread
-    pool: NumPy releases the GIL inside its ufunc / matmul loops."""
+def reference_modules():
+    """(fk, to_root_dual_quat, from_root_dual_quat, kind): the real reference from oracle/_ref when it has been
+    staged (`kind: "reference"`), else the NumPy oracle port (`kind: "port"`)."""
+    from oracle import fetch_ref
+
+    mods = fetch_ref.import_reference()
+    if mods is not None:
+        sk = mods[0]
+        return sk.fk, sk.to_root_dual_quat, sk.from_root_dual_quat, "reference"
+    from oracle import pymotion_oracle as orc
+
+    return orc.fk, orc.to_root_dual_quat, orc.from_root_dual_quat, "port"
+
+
+def reference_threaded(fk, rot, gpos, offsets, parents, n_threads: int):
+    """One pass of the reference's fk over the whole batch: contiguous frame shards on a thread pool, every
+    thread calling the reference on cache-sized blocks of its shard (NumPy releases the GIL in its loops)."""
     from concurrent.futures import ThreadPoolExecutor
 
     import numpy as np
 
-    from oracle import pymotion_oracle as orc
-
     bounds = np.linspace(0, rot.shape[0], n_threads + 1).astype(int)
 
     def work(i):
-        lo, hi = bounds[i], bounds[i + 1]
-        if hi > lo:
-            orc.fk(rot[lo:hi], gpos[lo:hi], offsets, parents)
+        for lo in range(bounds[i], bounds[i + 1], REF_BLOCK_FRAMES):
+            hi = min(lo + REF_BLOCK_FRAMES, bounds[i + 1])
+            fk(rot[lo:hi], gpos[lo:hi], offsets, parents)
 
     with ThreadPoolExecutor(n_threads) as pool:
         list(pool.map(work, range(n_threads)))
@@ -181,23 +225,23 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    import numpy as np
-
     from pymotion_b200.topologies import parents_of, synth_numpy
 
-    topo, _ = WORKLOADS[args.workload]
+    topo, frames = WORKLOADS[args.workload]
     par = parents_of(topo)
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 64))
-    sample = 2000 * threads  # frames per step: keeps a step at ~0.1-0.2 s per thread
-    rot, gpos, off = synth_numpy(sample, par, seed=0)
-    for _ in range(max(1, min(args.warmup, 3))):
-        numpy_port_threaded(rot, gpos, off, par, threads)
+    fk, _, _, kind = reference_modules()
+    frames = min(frames, args.ref_frames) if args.ref_frames else frames
+    rot, gpos, off = synth_numpy(frames, par, seed=0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        reference_threaded(fk, rot, gpos, off, par, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        numpy_port_threaded(rot, gpos, off, par, threads)
+        reference_threaded(fk, rot, gpos, off, par, threads)
     dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
+    value = frames * args.steps / dt
+    what = "unmodified pymotion.ops.skeleton.fk (oracle/_ref)" if kind == "reference" else "NumPy oracle port of pymotion.ops.skeleton.fk"
     line = {
         "impl": "reference",
         "metric": metric_of(len(par)),
@@ -212,18 +256,160 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32 in / f64 chain (NumPy promotion of the reference)",
         "data": "synthetic",
-        "config": {"workload": args.workload, "sample_frames_per_step": sample, "n_joints": len(par),
-                   "note": "CPU arm: does not use GPUs; same number for every --gpus"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} frames x {len(par)} joints per step, NumPy oracle port of "
-                                   f"pymotion.ops.skeleton.fk over {threads} threads (host has {cores} cores)"},
+        "config": shared_config(args.workload, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{frames} frames x {len(par)} joints per step (one GPU's batch; the CPU arm does not use "
+                                   f"GPUs, same number for every --gpus), {what} over {threads} threads in blocks of "
+                                   f"{REF_BLOCK_FRAMES} frames (host has {cores} cores)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_leg(par, n_joints, dev, sk):
+    """Rank 0, N = 1: the reference on this box's host.  BASELINE config 1 exactly, plus a bounded single-thread
+    sample of the bench workload (the way a user of the reference calls it: one call, one thread), used as the
+    checker it is on the way."""
+    import numpy as np
+    import torch
+
+    from pymotion_b200.topologies import parents_of, synth_numpy
+
+    fk, to_dq, from_dq, kind = reference_modules()
+    # ---- BASELINE.md section 4, config 1: 1000 x 22, default_rng(0), 3 warm-ups, best / median of 20
+    par1 = parents_of("body22")
+    rot1, gpos1, off1 = synth_numpy(1000, par1, seed=0)
+    dq1 = to_dq(rot1, gpos1, par1, off1)
+
+    def best_of(fn, reps=20):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return {"best_ms": 1e3 * ts[0], "median_ms": 1e3 * ts[len(ts) // 2], "poses_per_s_best": 1000 / ts[0]}
+
+    config1 = {"shape": "1000 frames x 22 joints, fp32 inputs, np.random.default_rng(0), 3 warm-ups + best of 20",
+               "fk": best_of(lambda: fk(rot1, gpos1, off1, par1)),
+               "to_root_dual_quat": best_of(lambda: to_dq(rot1, gpos1, par1, off1)),
+               "from_root_dual_quat": best_of(lambda: from_dq(dq1, par1))}
+    # the same three calls through the drop-in, NumPy in -> NumPy out (tiny batch: launch + copy latency)
+    ours1 = {"fk": best_of(lambda: sk.fk(rot1, gpos1, off1, par1)),
+             "to_root_dual_quat": best_of(lambda: sk.to_root_dual_quat(rot1, gpos1, par1, off1)),
+             "from_root_dual_quat": best_of(lambda: sk.from_root_dual_quat(dq1, par1))}
+    config1["drop_in_same_calls"] = ours1
+    # ---- bounded sample of the bench workload, one call, one thread
+    sample = 250_000 if n_joints <= 22 else 60_000
+    c_rot, c_gpos, c_off = synth_numpy(sample, par, seed=0)
+    t0 = time.perf_counter()
+    c_pos, c_rotm = fk(c_rot, c_gpos, c_off, par)
+    dt = time.perf_counter() - t0
+    n_chk = 50_000
+    g_pos, g_rotm = sk.fk(torch.from_numpy(c_rot[:n_chk]).to(dev), torch.from_numpy(c_gpos[:n_chk]).to(dev),
+                          torch.from_numpy(c_off).to(dev), par)
+    err_p = float(np.abs(g_pos.cpu().numpy() - c_pos[:n_chk]).max())
+    err_r = float(np.abs(g_rotm.cpu().numpy() - c_rotm[:n_chk]).max())
+    what = "unmodified pymotion.ops.skeleton.fk from oracle/_ref" if kind == "reference" else "NumPy oracle port"
+    return {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{sample} frames x {n_joints} joints of the bench workload, ONE call of the {what} "
+                      f"({dt:.1f} s, 1 thread of {os.cpu_count()} host cores; NumPy runs this path single-threaded)",
+            "max_abs_err_gpu_vs_cpu": {"positions": err_p, "rotmats": err_r, "frames": n_chk},
+            "config1": config1}
+
+
 # --------------------------------------------------------------------------- our arm
+class Timer:
+    """CUDA-event timing on the launch stream, barrier + synchronize on both sides, max over ranks."""
+
+    def __init__(self, dev, stream, world, sampler):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.dev, self.stream, self.world, self.sampler = torch, dist, dev, stream, world, sampler
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run(self, step, steps: int, warmup: int):
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            step()
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        ev0.record(self.stream)
+        for _ in range(steps):
+            step()
+        ev1.record(self.stream)
+        torch.cuda.synchronize(self.dev)
+        window = (w0, time.perf_counter())
+        self.sampler.windows.append(window)
+        self.barrier()
+        return self.max_over_ranks(ev0.elapsed_time(ev1)) / steps, window
+
+
+def roofline_of(bytes_per_launch: int, kernel_ms: float, variant: str, traffic_key: str):
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(traffic_key), "peak_source": peak_src,
+            "frac_of_nominal_8000": achieved / NOMINAL_HBM_GBS, "algorithmic_bytes_per_launch": bytes_per_launch,
+            "kernel": variant}
+
+
+def link_ceiling(dev, h2d_bytes: int, d2h_bytes: int, timer: Timer):
+    """What this box's host link gives the byte mix of one e2e step: page-locked buffers, plain cudaMemcpyAsync in both
+    directions at once on two streams (all ranks at the same time, like the e2e legs)."""
+    import torch
+
+    cap = 256 << 20
+    scale = min(1.0, cap / max(h2d_bytes, d2h_bytes))
+    nh, nd = max(1 << 20, int(h2d_bytes * scale)) // 4, max(1 << 20, int(d2h_bytes * scale)) // 4
+    h_in = torch.empty(nh, dtype=torch.float32, pin_memory=True).fill_(1.0)
+    h_out = torch.empty(nd, dtype=torch.float32, pin_memory=True)
+    d_in, d_out = torch.empty(nh, device=dev), torch.ones(nd, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def both(k_in=1, k_out=1):
+        with torch.cuda.stream(s_in):
+            for _ in range(k_in):
+                d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for _ in range(k_out):
+                h_out.copy_(d_out, non_blocking=True)
+        s_in.synchronize(), s_out.synchronize()
+
+    def rate(fn, nbytes, reps=3):
+        fn()
+        timer.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        dt = timer.max_over_ranks(time.perf_counter() - t0)
+        return nbytes * reps / dt / 1e9
+
+    out = {"h2d_alone_GBps": rate(lambda: both(1, 0), 4 * nh), "d2h_alone_GBps": rate(lambda: both(0, 1), 4 * nd)}
+    t_mix = (4 * nh + 4 * nd) / rate(lambda: both(1, 1), 4 * nh + 4 * nd) / 1e9  # seconds for the scaled mix, both directions at once
+    out["concurrent_mix_GBps"] = (4 * nh + 4 * nd) / t_mix / 1e9
+    out["step_seconds_at_ceiling"] = t_mix / scale
+    out["how"] = (f"{4 * nh >> 20} MiB H2D + {4 * nd >> 20} MiB D2H of page-locked memory, cudaMemcpyAsync on two streams, "
+                  f"per rank, all {timer.world} rank(s) at once")
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -242,113 +428,81 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()  # raises if the CUDA library is missing: no fallback
-
-    topo, frames = WORKLOADS[args.workload]
-    par = parents_of(topo)
-    n_joints = len(par)
-    rot, gpos, off = synth_torch(frames, par, dev, seed=1234 + rank)
-    pos = torch.empty((frames, n_joints, 3), device=dev, dtype=torch.float32)
-    rotm = torch.empty((frames, n_joints, 3, 3), device=dev, dtype=torch.float32)
     stream = torch.cuda.current_stream(dev)
-
-    def step():
-        _lib.check(lib.pmb_fk_f32(rot.data_ptr(), gpos.data_ptr(), 3, off.data_ptr(), 0, par.ctypes.data, frames,
-                                  n_joints, pos.data_ptr(), rotm.data_ptr(), stream.cuda_stream))
-
-    if args.kernel_only and args.op != "fk":
-        if args.op == "from_root_positions":
-            step()  # needs `rotm` alive for this one launch
-            torch.cuda.synchronize(dev)
-        del rotm
-        dq = torch.empty((frames, n_joints, 8), device=dev, dtype=torch.float32)
-        rots = torch.empty((frames, n_joints, 4), device=dev, dtype=torch.float32)
-        off0 = np.zeros(3, dtype=np.float32)
-        st = stream.cuda_stream
-
-        def to_dq():
-            _lib.check(lib.pmb_to_root_dual_quat_f32(rot.data_ptr(), gpos.data_ptr(), 3, par.ctypes.data, off.data_ptr(),
-                                                     off0.ctypes.data, frames, n_joints, dq.data_ptr(), st))
-
-        def from_dq():
-            _lib.check(lib.pmb_from_root_dual_quat_f32(dq.data_ptr(), par.ctypes.data, frames, n_joints, pos.data_ptr(),
-                                                       rots.data_ptr(), st))
-
-        def fk_quat():
-            _lib.check(lib.pmb_fk_quat_f32(rot.data_ptr(), gpos.data_ptr(), 3, off.data_ptr(), 0, par.ctypes.data, frames,
-                                           n_joints, pos.data_ptr(), rots.data_ptr(), st))
-
-        def from_root_positions():
-            _lib.check(lib.pmb_from_root_positions_f32(pos.data_ptr(), par.ctypes.data, off.data_ptr(), frames, n_joints,
-                                                       rots.data_ptr(), st))
-
-        def mirror_all():  # device part of mirror(mode="all"): fk_quat (rotations only) -> flip -> local
-            _lib.check(lib.pmb_fk_quat_f32(rot.data_ptr(), gpos.data_ptr(), 0, off.data_ptr(), 0, par.ctypes.data, frames,
-                                           n_joints, None, rots.data_ptr(), st))
-            _lib.check(lib.pmb_mirror_to_local_f32(rots.data_ptr(), par.ctypes.data, None, 0, frames, n_joints,
-                                                   dq.data_ptr(), st))
-
-        to_dq()
-        step = {"to_dq": to_dq, "from_dq": from_dq, "fk_quat": fk_quat, "from_root_positions": from_root_positions,
-                "mirror_all": mirror_all, "round_trip": lambda: (to_dq(), from_dq())}[args.op]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
+    st = stream.cuda_stream
     sampler = ClockSampler(local_rank)
     sampler.start()
+    timer = Timer(dev, stream, world, sampler)
+    launches = 0  # kernels of ours launched inside timed regions
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.perf_counter()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    ev1.record(stream)
-    torch.cuda.synchronize(dev)
-    sampler.windows.append((w0, time.perf_counter()))
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    variant = lib.pmb_last_variant().decode()  # what the timed launches actually ran
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * frames * args.steps / (ms_max * 1e-3)
+    class Batch:
+        """One resident synthetic batch of a workload and the C-ABI calls on it."""
 
+        def __init__(self, workload):
+            self.workload = workload
+            self.topo, self.frames = WORKLOADS[workload]
+            self.par = parents_of(self.topo)
+            self.J = len(self.par)
+            self.rot, self.gpos, self.off = synth_torch(self.frames, self.par, dev, seed=1234 + rank)
+            self.pos = torch.empty((self.frames, self.J, 3), device=dev, dtype=torch.float32)
+            self.off0 = np.zeros(3, dtype=np.float32)
+
+        def alloc(self, *names):
+            shapes = {"rotm": (self.frames, self.J, 3, 3), "dq": (self.frames, self.J, 8), "rots": (self.frames, self.J, 4)}
+            for n in names:
+                setattr(self, n, torch.empty(shapes[n], device=dev, dtype=torch.float32))
+
+        def fk(self):
+            _lib.check(lib.pmb_fk_f32(self.rot.data_ptr(), self.gpos.data_ptr(), 3, self.off.data_ptr(), 0, self.par.ctypes.data,
+                                      self.frames, self.J, self.pos.data_ptr(), self.rotm.data_ptr(), st))
+
+        def to_dq(self):
+            _lib.check(lib.pmb_to_root_dual_quat_f32(self.rot.data_ptr(), self.gpos.data_ptr(), 3, self.par.ctypes.data,
+                                                     self.off.data_ptr(), self.off0.ctypes.data, self.frames, self.J,
+                                                     self.dq.data_ptr(), st))
+
+        def from_dq(self):
+            _lib.check(lib.pmb_from_root_dual_quat_f32(self.dq.data_ptr(), self.par.ctypes.data, self.frames, self.J,
+                                                       self.pos.data_ptr(), self.rots.data_ptr(), st))
+
+        def fk_quat(self):
+            _lib.check(lib.pmb_fk_quat_f32(self.rot.data_ptr(), self.gpos.data_ptr(), 3, self.off.data_ptr(), 0,
+                                           self.par.ctypes.data, self.frames, self.J, self.pos.data_ptr(), self.rots.data_ptr(), st))
+
+        def from_root_positions(self):
+            _lib.check(lib.pmb_from_root_positions_f32(self.pos.data_ptr(), self.par.ctypes.data, self.off.data_ptr(), self.frames,
+                                                       self.J, self.rots.data_ptr(), st))
+
+        def mirror_all(self):  # device part of mirror(mode="all"): fk_quat (rotations only) -> flip -> local
+            _lib.check(lib.pmb_fk_quat_f32(self.rot.data_ptr(), self.gpos.data_ptr(), 0, self.off.data_ptr(), 0, self.par.ctypes.data,
+                                           self.frames, self.J, None, self.rots.data_ptr(), st))
+            _lib.check(lib.pmb_mirror_to_local_f32(self.rots.data_ptr(), self.par.ctypes.data, None, 0, self.frames, self.J,
+                                                   self.dq.data_ptr(), st))
+
+    # ------------------------------------------------------------------ development mode: one op, kernel only
     if args.kernel_only:
-        gather = None
-        if args.all_gather and world > 1:
-            # the OPTIONAL exchange of SURVEY 8e: every rank ends up with the positions of all frames (NCCL all-gather
-            # of equal frame blocks).  Timed on its own, never part of poses/s.
-            from pymotion_b200 import sharding
-
-            for _ in range(2):
-                full = sharding.all_gather_frames(pos, frames * world)
-            barrier()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 5
-            g0.record(stream)
-            for _ in range(reps):
-                full = sharding.all_gather_frames(pos, frames * world)
-            g1.record(stream)
-            torch.cuda.synchronize(dev)
-            tg = torch.tensor([g0.elapsed_time(g1) / reps], device=dev, dtype=torch.float64)
-            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-            same = bool(torch.equal(full[rank * frames:(rank + 1) * frames], pos))
-            shard_bytes = pos.numel() * 4
-            gather = {"ms": float(tg.item()), "shard_bytes": shard_bytes, "received_bytes_per_rank": shard_bytes * (world - 1),
-                      "GBps_received_per_rank": shard_bytes * (world - 1) / (float(tg.item()) * 1e-3) / 1e9,
-                      "own_block_intact": same, "includes": "NCCL all_gather_into_tensor into one [F, J, 3] array (equal shards: no extra copy)"}
-            del full
+        b = Batch(args.workload)
+        if args.op == "fk":
+            b.alloc("rotm")
+            step = b.fk
+        else:
+            if args.op == "from_root_positions":
+                b.alloc("rotm")
+                b.fk()
+                torch.cuda.synchronize(dev)
+                del b.rotm
+            b.alloc("dq", "rots")
+            b.to_dq()
+            step = {"to_dq": b.to_dq, "from_dq": b.from_dq, "fk_quat": b.fk_quat, "from_root_positions": b.from_root_positions,
+                    "mirror_all": b.mirror_all, "round_trip": lambda: (b.to_dq(), b.from_dq())}[args.op]
+        kernel_ms, _ = timer.run(step, args.steps, args.warmup)
+        variant = lib.pmb_last_variant().decode()
+        gather = all_gather_leg(b, timer, world, rank, dev, stream) if (args.all_gather and world > 1) else None
         if rank == 0:
-            bytes_per_launch = op_bytes_per_pose(args.op, n_joints) * frames
-            kernel_ms = ms_max / args.steps
-            line = {"workload": args.workload, "op": args.op, "n_gpus": world, "ms_per_step": kernel_ms, "value": value,
-                    "GBps": bytes_per_launch / (kernel_ms * 1e-3) / 1e9, "env_chunk": os.environ.get("PMB_FK_CHUNK")}
+            bytes_per_launch = op_bytes_per_pose(args.op, b.J) * b.frames
+            line = {"workload": args.workload, "op": args.op, "n_gpus": world, "ms_per_step": kernel_ms,
+                    "value": world * b.frames / (kernel_ms * 1e-3), "GBps": bytes_per_launch / (kernel_ms * 1e-3) / 1e9,
+                    "variant": variant}
             if gather:
                 line["all_gather_positions"] = gather
             print(json.dumps(line), flush=True)
@@ -357,60 +511,65 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- end to end through the public host-buffer API (pinned host memory both ways)
-    e2e_steps = max(1, min(args.steps, 5))
-    h_rot = torch.empty((frames, n_joints, 4), dtype=torch.float32, pin_memory=True).copy_(rot)
-    h_gpos = torch.empty((frames, 3), dtype=torch.float32, pin_memory=True).copy_(gpos)
-    h_off = off.cpu()
-    h_pos = torch.empty((frames, n_joints, 3), dtype=torch.float32, pin_memory=True)
-    h_rotm = torch.empty((frames, n_joints, 3, 3), dtype=torch.float32, pin_memory=True)
-    sk.fk_host(h_rot, h_gpos, h_off, par, out=(h_pos, h_rotm))  # warm-up: allocates the staging workspace
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        sk.fk_host(h_rot, h_gpos, h_off, par, out=(h_pos, h_rotm))  # returns when the outputs are in host memory
-    w1 = time.perf_counter()
-    sampler.windows.append((w0, w1))
-    te = torch.tensor([w1 - w0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * frames * e2e_steps / float(te.item())
-    h2d = h_rot.numel() * 4 + h_gpos.numel() * 4 + h_off.numel() * 4
-    d2h = h_pos.numel() * 4 + h_rotm.numel() * 4
-    # the e2e result must be the same answer as the resident path
-    same = bool(torch.equal(h_pos[:4096], pos[:4096].cpu()) and torch.equal(h_rotm[-4096:], rotm[-4096:].cpu()))
-    lib.pmb_release_workspace()
+    # ------------------------------------------------------------------ headline: config 2 (or --workload)
+    main = Batch(args.workload)
+    main.alloc("rotm")
+    kernel_ms, main_window = timer.run(main.fk, args.steps, args.warmup)
+    launches += args.steps
+    variant = lib.pmb_last_variant().decode()  # what the timed launches actually ran
+    value = world * main.frames / (kernel_ms * 1e-3)
+    n_joints, frames, par = main.J, main.frames, main.par
+
+    # ------------------------------------------------------------------ end to end through the drop-in call
+    e2e = e2e_legs(main, sk, lib, timer, world, dev, sampler, args)
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_leg(par, n_joints, dev, sk)
+    del main
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ the other BASELINE configs, same run
+    extra = []
+    if not args.no_extra:
+        x_steps = max(3, min(args.steps, 20))
+
+        def record(name, baseline_config, b, op, step, n_kernels):
+            nonlocal launches
+            ms, window = timer.run(step, x_steps, 3)
+            launches += x_steps * n_kernels
+            bytes_per_launch = op_bytes_per_pose(op, b.J) * b.frames
+            extra.append({"name": name, "baseline_config": baseline_config, "op": op, "frames_per_gpu": b.frames, "n_joints": b.J,
+                          "steps": x_steps, "ms_per_step": ms, "value": world * b.frames / (ms * 1e-3), "unit": UNIT,
+                          "roofline": roofline_of(bytes_per_launch, ms, "pmb::" + lib.pmb_last_variant().decode(), name),
+                          "clocks": sampler.summary([window])})
+
+        b = Batch("fk_1m_x_22")
+        b.alloc("dq", "rots")
+        record("round_trip_1m_x_22", "configs[2]: to_root_dual_quat + from_root_dual_quat, 1M x 22", b, "round_trip",
+               lambda: (b.to_dq(), b.from_dq()), 2)
+        record("to_root_dual_quat_1m_x_22", "configs[2], first half", b, "to_dq", b.to_dq, 1)
+        record("from_root_dual_quat_1m_x_22", "configs[2], second half", b, "from_dq", b.from_dq, 1)
+        del b
+        torch.cuda.empty_cache()
+        for name, cfg in (("fk_4m_x_65", "configs[3]: fk 4M x 65 deep hierarchy"),
+                          ("fk_4m_x_52", f"configs[4]: fk 32M x 52 over 8 GPUs = 4M x 52 per GPU (this run: {world} GPU(s), "
+                                         f"{4 * world}M frames)")):
+            b = Batch(name)
+            b.alloc("rotm")
+            record(name, cfg, b, "fk", b.fk, 1)
+            if name == "fk_4m_x_52" and world > 1:
+                extra.append({"name": "all_gather_positions_4m_x_52", "baseline_config": "configs[4], OPTIONAL exchange, never part of poses/s",
+                              **all_gather_leg(b, timer, world, rank, dev, stream)})
+            del b
+            torch.cuda.empty_cache()
 
     sampler.stop_flag.set()
     sampler.join(timeout=1.0)
-    clocks = sampler.summary()
-
-    # ---- CPU baseline: the NumPy oracle port, single thread, bounded sample (rank 0, N=1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import pymotion_oracle as orc
-        from pymotion_b200.topologies import synth_numpy
-
-        sample = 400_000 if n_joints <= 22 else 100_000
-        c_rot, c_gpos, c_off = synth_numpy(sample, par, seed=0)
-        t0 = time.perf_counter()
-        c_pos, c_rotm = orc.fk(c_rot, c_gpos, c_off, par)
-        dt = time.perf_counter() - t0
-        # and use it as the checker it is: the GPU answer on the same sample
-        g_pos, g_rotm = sk.fk(torch.from_numpy(c_rot[:50_000]).to(dev), torch.from_numpy(c_gpos[:50_000]).to(dev),
-                              torch.from_numpy(c_off).to(dev), par)
-        err_p = float(np.abs(g_pos.cpu().numpy() - c_pos[:50_000]).max())
-        err_r = float(np.abs(g_rotm.cpu().numpy() - c_rotm[:50_000]).max())
-        cpu = {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{sample} frames x {n_joints} joints, one pass of the NumPy oracle port of "
-                         f"pymotion.ops.skeleton.fk ({dt:.1f} s, 1 thread of {os.cpu_count()} host cores)",
-               "max_abs_err_gpu_vs_cpu": {"positions": err_p, "rotmats": err_r}}
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         bytes_per_launch = fk_bytes_per_pose(n_joints) * frames
-        kernel_ms = ms_max / args.steps
-        achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
         line = {
             "metric": metric_of(n_joints),
             "value": value,
@@ -424,47 +583,116 @@ def run_ours(args):
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
-            "config": {
-                "workload": args.workload,
-                "frames_per_gpu": frames,
-                "n_joints": n_joints,
-                "topology": topo,
-                "sharding": f"frame axis, {world} shard(s), no data-path collective",
-                "l2": f"working set {bytes_per_launch / 1e9:.2f} GB per launch >> 126 MB L2: no flush needed",
-            },
-            "roofline": {
-                "bound": "hbm",
-                "achieved": achieved,
-                "peak": peak,
-                "unit": "GB/s",
-                "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload),
-                "peak_source": peak_src,
-                "frac_of_nominal_8000": achieved / 8000.0,
-                "algorithmic_bytes_per_launch": bytes_per_launch,
-                "kernel": "pmb::" + variant,
-            },
+            "config": shared_config(args.workload, world),
+            "roofline": roofline_of(bytes_per_launch, kernel_ms, "pmb::" + variant, args.workload),
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "pymotion_b200.ops.skeleton.fk_host (pmb_fk_f32_host)",
-                    "matches_resident_path": same},
-            "gpu_launches": args.steps,
-            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches + e2e.get("gpu_launches", 0),
+            "clocks": sampler.summary(),
+            "extra": extra,
         }
+        line["clocks"]["headline_region"] = sampler.summary([main_window])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def all_gather_leg(b, timer, world, rank, dev, stream):
+    """The OPTIONAL exchange of SURVEY 8e: every rank ends up with the positions of all frames (NCCL all-gather of
+    equal frame blocks).  Timed on its own, never part of poses/s."""
+    import torch
+
+    from pymotion_b200 import sharding
+
+    frames = b.frames
+    for _ in range(2):
+        full = sharding.all_gather_frames(b.pos, frames * world)
+    timer.barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    g0.record(stream)
+    for _ in range(reps):
+        full = sharding.all_gather_frames(b.pos, frames * world)
+    g1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = timer.max_over_ranks(g0.elapsed_time(g1) / reps)
+    same = bool(torch.equal(full[rank * frames:(rank + 1) * frames], b.pos))
+    shard_bytes = b.pos.numel() * 4
+    del full
+    return {"ms": ms, "shard_bytes": shard_bytes, "received_bytes_per_rank": shard_bytes * (world - 1),
+            "GBps_received_per_rank": shard_bytes * (world - 1) / (ms * 1e-3) / 1e9, "own_block_intact": same,
+            "includes": "NCCL all_gather_into_tensor into one [F, J, 3] array (equal shards: no extra copy)"}
+
+
+def e2e_legs(main, sk, lib, timer, world, dev, sampler, args):
+    """The same metric through the call a user of the reference makes -- skeleton.fk(host arrays) -> host arrays --
+    with every step's H2D and D2H inside the timing (wall clock around the blocking calls, max over ranks)."""
+    import numpy as np
+    import torch
+
+    frames, n_joints, par = main.frames, main.J, main.par
+    steps = max(1, min(args.steps, 5))
+    h_rot = torch.empty((frames, n_joints, 4), dtype=torch.float32, pin_memory=True).copy_(main.rot)
+    h_gpos = torch.empty((frames, 3), dtype=torch.float32, pin_memory=True).copy_(main.gpos)
+    h_off = main.off.cpu()
+    h2d = h_rot.numel() * 4 + h_gpos.numel() * 4 + h_off.numel() * 4
+    d2h_fk = frames * n_joints * 48
+    d2h_fkq = frames * n_joints * 28
+
+    def timed(call):
+        out = call()  # warm-up: allocates the staging workspace / the page-locked result blocks
+        del out
+        timer.barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            out = call()  # returns when the outputs are in host memory
+        w1 = time.perf_counter()
+        sampler.windows.append((w0, w1))
+        return timer.max_over_ranks(w1 - w0) / steps, out
+
+    ceiling = link_ceiling(dev, h2d, d2h_fk, timer)
+    # (1) page-locked host tensors in -> page-locked host tensors out, the reference's signature
+    t_pin, (p_pos, p_rotm) = timed(lambda: sk.fk(h_rot, h_gpos, h_off, par))
+    same = bool(torch.equal(p_pos[:4096], main.pos[:4096].cpu()) and torch.equal(p_rotm[-4096:], main.rotm[-4096:].cpu()))
+    del p_pos, p_rotm
+    # (2) plain pageable NumPy arrays in -> NumPy arrays out (what `import pymotion_b200.ops.skeleton as sk` users pass)
+    n_rot, n_gpos, n_off = np.array(h_rot.numpy()), np.array(h_gpos.numpy()), np.array(h_off.numpy())
+    t_np, (n_pos, n_rotm) = timed(lambda: sk.fk(n_rot, n_gpos, n_off, par))
+    same_np = bool(isinstance(n_pos, np.ndarray) and np.array_equal(n_rotm[-4096:], main.rotm[-4096:].cpu().numpy()))
+    del n_pos, n_rotm
+    # (3) fk_quat: global quaternions back instead of matrices (28 J instead of 48 J bytes per frame over PCIe)
+    t_q, (q_pos, q_rot) = timed(lambda: sk.fk_quat(h_rot, h_gpos, h_off, par))
+    del q_pos, q_rot
+    lib.pmb_release_workspace()
+    chunks = -(-frames // max(1, ((48 << 20) // (64 * n_joints + 12) + 31) // 32 * 32))
+    return {
+        "value": world * frames / t_pin, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_fk, "steps": steps,
+        "api": "pymotion_b200.ops.skeleton.fk(rot, global_pos, offsets, parents) on page-locked CPU tensors -> CPU tensors "
+               "(the reference's signature, ops/skeleton.py:16; chunked pipeline pmb_fk_f32_host underneath)",
+        "ms_per_step": 1e3 * t_pin, "matches_resident_path": same,
+        "frac_of_link_ceiling": ceiling["step_seconds_at_ceiling"] / t_pin,
+        "link_ceiling": ceiling,
+        "pageable_numpy": {"value": world * frames / t_np, "ms_per_step": 1e3 * t_np, "matches_resident_path": same_np,
+                           "api": "skeleton.fk(pageable NumPy arrays) -> NumPy arrays (results in page-locked memory; inputs staged "
+                                  "through the library's pinned ring by host threads)",
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_fk},
+        "fk_quat": {"value": world * frames / t_q, "ms_per_step": 1e3 * t_q, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_fkq,
+                    "api": "skeleton.fk_quat(page-locked CPU tensors): global quaternions instead of rotation matrices"},
+        "gpu_launches": 3 * (steps + 1) * chunks,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fk_1m_x_22", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel-only", action="store_true", help="development: skip the e2e and CPU legs")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (extra records)")
+    ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: cap the frames per step (tests)")
+    ap.add_argument("--kernel-only", action="store_true", help="development: one op, kernel time only")
     ap.add_argument("--op", default="fk", choices=DEV_OPS, help="with --kernel-only: which op of the path to time")
     ap.add_argument("--all-gather", action="store_true",
                     help="with --kernel-only under torchrun: also time the optional all-gather of positions")

@@ -224,10 +224,14 @@ int pmb_build_joint_program(const int64_t *parents_host, int32_t n_joints, uint3
 /* Builds the schedule the fk track kernel executes for `parents_host` with `n_tracks` (1..8)
  * independent joints per step: codes_out[step * n_tracks + track], bits 0-9 joint, bits 10-19
  * parent, bit 20 = the parent is the same track's previous item (kept in registers), bit 21 =
- * no-op.  Every joint appears exactly once, after its parent's step.  Returns the number of
- * steps (> 0) or a negative pmb_status (PMB_ERR_SHAPE if codes_capacity is too small). */
-int pmb_build_track_schedule(const int64_t *parents_host, int32_t n_joints, int32_t n_tracks,
-                             uint32_t *codes_out, int32_t codes_capacity);
+ * no-op.  Every joint appears exactly once, after its parent's step.  `window` = 8: joints are
+ * scheduled box by box (8 consecutive joints, what the kernel holds of the input at a time) and
+ * window_first_out (n_windows + 1 entries, may be NULL) receives the first step of every window
+ * and the total; `window` = 0: the whole skeleton at once (the optimum for n_tracks machines).
+ * Returns the number of steps (> 0) or a negative pmb_status (PMB_ERR_SHAPE if codes_capacity
+ * is too small). */
+int pmb_build_track_schedule(const int64_t *parents_host, int32_t n_joints, int32_t n_tracks, int32_t window,
+                             uint32_t *codes_out, int32_t codes_capacity, int32_t *window_first_out);
 
 /* Kernel-variant knobs (PMB_FK_*, PMB_DQ_*, ...) are honoured only when PMB_EXPERIMENT=1 is in
  * the environment, and are read once; this re-reads them (sweeps and the forced-variant tests

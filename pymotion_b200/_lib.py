@@ -26,7 +26,7 @@ SIGNATURES = {
     "pmb_status_string": [ctypes.c_int],
     "pmb_device_info": [_vp, _vp, _vp, ctypes.c_char_p, ctypes.c_int],
     "pmb_build_joint_program": [_vp, _i32, _vp],
-    "pmb_build_track_schedule": [_vp, _i32, _i32, _vp, _i32],
+    "pmb_build_track_schedule": [_vp, _i32, _i32, _i32, _vp, _i32, _vp],
     "pmb_reload_knobs": [],
     "pmb_fk_f32": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp],
     "pmb_fk_quat_f32": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp],

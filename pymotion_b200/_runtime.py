@@ -65,16 +65,20 @@ class Marshal:
         elif self.out_dtype not in (torch.float32,):
             raise TypeError(f"pymotion_b200 supports float32 (and float64 by rounding) inputs, got {self.out_dtype}")
 
+    @staticmethod
+    def dev_check(a: torch.Tensor) -> None:
+        if a.requires_grad and torch.is_grad_enabled():
+            # the reference's torch twins are differentiable (ops/skeleton_torch.py:60-63 clones for exactly
+            # that); these kernels have no backward, and handing back a tensor without a graph would train
+            # with a silent zero gradient
+            raise RuntimeError(
+                "pymotion_b200 kernels are forward-only: an input has requires_grad=True. Call under "
+                "torch.no_grad() / pass x.detach(), or use the reference's torch twin where gradients are needed")
+
     def dev(self, a) -> torch.Tensor:
         """float32, on the compute device; NOT necessarily contiguous."""
         if isinstance(a, torch.Tensor):
-            if a.requires_grad and torch.is_grad_enabled():
-                # the reference's torch twins are differentiable (ops/skeleton_torch.py:60-63 clones for
-                # exactly that); these kernels have no backward, and handing back a tensor without a graph
-                # would train with a silent zero gradient
-                raise RuntimeError(
-                    "pymotion_b200 kernels are forward-only: an input has requires_grad=True. Call under "
-                    "torch.no_grad() / pass x.detach(), or use the reference's torch twin where gradients are needed")
+            self.dev_check(a)
             return a.to(device=self.device, dtype=torch.float32, non_blocking=True)
         return torch.as_tensor(np.asarray(a), device=self.device).to(torch.float32)
 
@@ -89,6 +93,12 @@ class Marshal:
         if self.kind == "torch_cpu":
             return t.cpu()
         return t
+
+    def out_host(self, t: torch.Tensor):
+        """Result that already lives in host memory (the chunked host pipeline)."""
+        if self.out_dtype != torch.float32:
+            t = t.to(self.out_dtype)
+        return t.numpy() if self.kind == "numpy" else t
 
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -183,24 +183,26 @@ int joint_program(const int64_t *parents_host, int32_t n_joints, bool detach, co
     return PMB_OK;
 }
 
-int track_program(const int64_t *parents_host, int32_t n_joints, int n_tracks, const pmb::TrackProgram *&prog, int &n_steps) {
+int track_program(const int64_t *parents_host, int32_t n_joints, int n_tracks, int window, const pmb::TrackProgram *&prog,
+                  int &n_steps) {
     if (!parents_host) return fail(PMB_ERR_NULL, "parents_host is NULL");
     if (n_joints < 1 || n_joints > PMB_MAX_JOINTS)
         return fail(PMB_ERR_SHAPE, "n_joints = %d outside [1, %d]", n_joints, PMB_MAX_JOINTS);
     thread_local ProgCache<pmb::TrackProgram> cache;
-    if (auto *hit = cache.find(parents_host, n_joints, n_tracks)) {
+    const int variant = n_tracks | (window << 8);
+    if (auto *hit = cache.find(parents_host, n_joints, variant)) {
         prog = &hit->prog, n_steps = hit->extra;
         return PMB_OK;
     }
     auto *slot = cache.victim();
     slot->n_joints = 0, slot->variant = -1;  // invalid while it is being rebuilt
     int bad = -1;
-    const int steps = pmb::build_track_schedule(parents_host, n_joints, n_tracks, slot->prog.code, &bad);
+    const int steps = pmb::build_track_schedule(parents_host, n_joints, n_tracks, slot->prog.code, &bad, window, slot->prog.chunk_first);
     if (steps < 0)
         return fail(PMB_ERR_TOPOLOGY, "parents[%d] = %lld is not in [0, %d): joints must come after their parent (BVH order)", bad,
                     bad >= 0 ? static_cast<long long>(parents_host[bad]) : -1LL, bad);
     slot->parents.assign(parents_host, parents_host + n_joints);
-    slot->n_joints = n_joints, slot->variant = n_tracks, slot->extra = steps;  // steps == 0: does not fit kTrackCap (cached too)
+    slot->n_joints = n_joints, slot->variant = variant, slot->extra = steps;  // steps == 0: does not fit kTrackCap (cached too)
     prog = &slot->prog, n_steps = steps;
     return PMB_OK;
 }
@@ -315,17 +317,22 @@ int pmb_build_joint_program(const int64_t *parents_host, int32_t n_joints, uint3
     return n_slots;
 }
 
-int pmb_build_track_schedule(const int64_t *parents_host, int32_t n_joints, int32_t n_tracks, uint32_t *codes_out,
-                             int32_t codes_capacity) {
+int pmb_build_track_schedule(const int64_t *parents_host, int32_t n_joints, int32_t n_tracks, int32_t window, uint32_t *codes_out,
+                             int32_t codes_capacity, int32_t *window_first_out) {
     if (!codes_out) return fail(PMB_ERR_NULL, "codes_out is NULL");
     if (n_tracks < 1 || n_tracks > 8) return fail(PMB_ERR_SHAPE, "n_tracks = %d outside [1, 8]", n_tracks);
+    if (window != 0 && window != 8) return fail(PMB_ERR_SHAPE, "window = %d: 0 (whole skeleton) or 8 (one box of quaternions)", window);
     const pmb::TrackProgram *prog = nullptr;
     int n_steps = 0;
-    int rc = track_program(parents_host, n_joints, n_tracks, prog, n_steps);
+    int rc = track_program(parents_host, n_joints, n_tracks, window, prog, n_steps);
     if (rc) return rc;
     if (n_steps == 0) return fail(PMB_ERR_SHAPE, "schedule of %d tracks does not fit %d items", n_tracks, pmb::kTrackCap);
     if (n_steps * n_tracks > codes_capacity) return fail(PMB_ERR_SHAPE, "codes_out holds %d items, the schedule has %d", codes_capacity, n_steps * n_tracks);
     memcpy(codes_out, prog->code, sizeof(uint32_t) * static_cast<size_t>(n_steps) * n_tracks);
+    if (window_first_out) {
+        const int n_windows = window ? (n_joints + window - 1) / window : 1;
+        for (int w = 0; w <= n_windows; ++w) window_first_out[w] = prog->chunk_first[w];
+    }
     return n_steps;
 }
 

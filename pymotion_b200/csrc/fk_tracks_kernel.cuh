@@ -1,53 +1,63 @@
 // Forward kinematics, track kernel (ops/skeleton.py:16-61 of the reference).
 //
 // Same mapping as the lane kernel -- a warp owns a tile of FR consecutive frames, lane = 3 f + a walks row a of
-// frame f, G[a][:] = P[a][:] * R(q^), p[a] = P[a][:] . off + p_parent[a] -- but the tree is no longer walked in
-// index order, one joint after the other.  ncu on the lane kernel (profiles/r1_fk_52_ncu_*): 8 warps per SM,
-// every one of them a single dependent chain, issue slots 48 % used, 22 % of the samples on fixed-latency
-// dependencies, 22 % on shared-memory / MUFU results, 16 % waiting for the next TMA box; shared memory (the
-// dense output stage) rules out more warps.  So the parallelism has to come from inside the warp:
+// frame f, G[a][:] = P[a][:] * R(q^), p[a] = P[a][:] . off + p_parent[a]; quaternions arrive as TMA boxes of
+// 8 joints x FR frames -- but inside a box the tree is no longer walked in index order, one joint after the other.
+// ncu on the lane kernel (profiles/r1_fk_52_ncu_*): 8 warps per SM, every one of them a single dependent chain,
+// issue slots 48 % used, 22 % of the samples on fixed-latency dependencies, 22 % on shared-memory / MUFU results;
+// shared memory (the dense output stage) rules out more warps.  So the parallelism has to come from inside the warp:
 //
-//   tracks   the host compiles parents[] into T steps of U independent joints (track_schedule.h, Hu's
-//            highest-level-first list schedule: minimum T for U tracks).  A lane runs the U items of a step
-//            interleaved -- U independent register chains -- so latencies overlap without more warps.  An item
-//            whose parent was the same track's previous item keeps it in registers; every other parent row is
-//            read back from the stage, which already holds every joint processed so far (same lane wrote it).
-//   input    the U quaternions of a step are fetched with plain 16-byte loads, D steps ahead, into a register
-//            ring (the three lanes of a frame share the address).  No shared memory for the input at all: what
-//            the TMA boxes and their mbarriers used now stages output, and registers are plentiful at 6 .. 12
-//            warps per SM.  The next tile's quaternions (FR x 16 J contiguous bytes) are pulled into L2 by one
-//            cp.async.bulk.prefetch a tile ahead, so DRAM sees one burst per tile and the loads hit L2.
-//   output   the dense image of the tile's output (FR x 36 J and FR x 12 J bytes) goes to HBM as two contiguous
-//            TMA bulk stores.  The spans of a tile need not be 16-byte multiples any more (FR = 10 with an odd
-//            joint count): the stage is placed at the same 16-byte phase as the global span, the aligned middle
-//            goes through the TMA engine and the up-to-three head / tail words are stored by single lanes.
-//            The remainder tile of a batch is just a shorter span.
+//   tracks   the host compiles parents[] into steps of U independent joints (track_schedule.h: Hu's
+//            highest-level-first list schedule, window = one box of 8 joints, the part of the input that is resident).
+//            A lane runs the U items of a step interleaved -- U independent register chains -- so latencies overlap
+//            without more warps: 52 joints take 29 steps of two, 65 take 34.  An item whose parent was the same
+//            track's previous item keeps it in registers; every other parent row is read back from the stage, which
+//            already holds every joint processed so far (the same lane wrote it).
+//   input    ring of NB boxes per warp, refilled by lane 0 as soon as the box's last step has read it; an item
+//            reads its quaternion straight from the box (one swizzled LDS.128 per item, the three lanes of a frame
+//            share it) ONE STEP AHEAD of its use, together with its normalisation scale 2 / (|q| + eps)^2 (two MUFU
+//            ops in a ~100-cycle chain that does not depend on the walk): the dependent chain of a step is then
+//            parent row -> two cross products -> store.  The box-relative address of a step's quaternions comes from a
+//            64-bit word per box (4 bits per item), so the prefetch does not wait for the step's table entry.  (Measured and retired, experiments/retired/fk_tracks_ldg_ring_kernel.cuh: a whole-skeleton
+//            schedule fed by per-item 16-byte global loads through a register ring -- half of every 32-byte sector
+//            wasted, the ring too shallow for the latency: 2.95 ms at 4M x 52 against 2.50 for the lane kernel.)
+//   output   the dense image of the tile's output (FR x 36 J and FR x 12 J bytes) goes to HBM as two contiguous TMA
+//            bulk stores.  The spans of a tile need not be 16-byte multiples (FR = 10 with an odd joint count): the
+//            stage is placed at the same 16-byte phase as the global span, the aligned middle goes through the TMA
+//            engine and the up-to-three head / tail words are stored by single lanes.  The remainder tile of a batch
+//            is just a shorter span.
 //
 // Algorithmic HBM traffic 64 J + 12 bytes per pose.
 #pragma once
 #include <cuda.h>
 
 #include "common.cuh"
-#include "fk_rows_kernel.cuh"  // rot_scale
+#include "fk_lanes_kernel.cuh"  // lds128
+#include "fk_rows_kernel.cuh"   // rot_scale
 #include "tma.cuh"
 #include "track_schedule.h"
 
 namespace pmb {
 
 struct FkTracksGeom {
-    int tab_bytes, warp_bytes, block_bytes;
+    int tab_bytes, box_bytes, rst_bytes, warp_bytes, block_bytes;
 };
-// per block: schedule table (32 bytes per item) | per warp: R stage (+16 bytes of phase slack) | P stage (+16)
-__host__ __device__ inline FkTracksGeom fk_tracks_geom(int fr, int warps, int n_joints, int n_items) {
+// per block: schedule table (16 bytes per item) | box table (16 bytes per box) | per warp: NB boxes | R stage (+16 bytes of
+// phase slack) | P stage (+16) | NB mbarriers + fence words
+__host__ __device__ inline FkTracksGeom fk_tracks_geom(int fr, int warps, int n_joints, int n_items, int n_boxes) {
     FkTracksGeom g;
-    g.tab_bytes = (n_items * 32 + 127) & ~127;
-    g.warp_bytes = ((fr * 36 * n_joints + 16 + 15) & ~15) + ((fr * 12 * n_joints + 16 + 15) & ~15);
+    const int n_chunks = (n_joints + kChunk - 1) / kChunk;
+    g.tab_bytes = (((n_items + 2) * 16 + 127) & ~127) + (((n_chunks + 1) * 16 + 127) & ~127);
+    g.box_bytes = fr * 128;  // FR frames x 8 joints x 16 bytes
+    g.rst_bytes = (fr * 36 * n_joints + 16 + 15) & ~15;
+    g.warp_bytes = (n_boxes * g.box_bytes + g.rst_bytes + ((fr * 12 * n_joints + 16 + 15) & ~15) + 32 + 128 + 127) & ~127;
     g.block_bytes = 128 + g.tab_bytes + warps * g.warp_bytes;
     return g;
 }
 
-// The predicates compare the table word with a per-lane threshold: 0 for the lanes that own a (frame, row), INT_MAX for
-// the idle lanes of the warp (which therefore never touch the stage) -- no extra instruction to mask them.
+// Table word of an item: bits 0-9 joint | 10-19 parent | 30 parent kept in registers | 31 no-op.  The predicates compare
+// it (shifted so that the flag is the sign bit) with a per-lane threshold: 0 for the lanes that own a (frame, row),
+// INT_MAX for the idle lanes of the warp (which therefore never touch the stage) -- no extra instruction to mask them.
 __device__ __forceinline__ void track_load_parent_if(uint32_t flag /* taken iff (int)flag >= thr */, int thr, uint32_t raddr, uint32_t paddr,
                                                      float &r0, float &r1, float &r2, float &pp) {
     asm volatile(
@@ -74,51 +84,62 @@ __device__ __forceinline__ void track_store_if(uint32_t flag /* stored iff (int)
         "@p st.shared.f32 [%2], %6;\n"
         "}" ::"r"(flag), "r"(raddr), "r"(paddr), "f"(r0), "f"(r1), "f"(r2), "f"(pp), "r"(thr));
 }
-// Ring refill: volatile, so that it is issued where it is written (right after the step that freed the ring entry) and not
-// sunk towards its use D steps later -- the whole point of the ring is the distance.
-__device__ __forceinline__ float4 track_ldg_q(const void *p) {
-    float4 v;
-    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
 
-// U: tracks per lane (independent chains interleaved).  D: steps of quaternion prefetch (register ring depth).
-template <int U, int D>
+// U: tracks per lane (independent chains interleaved; 1 or 2).  NB: TMA boxes in flight per warp (2 .. 4).
+template <int U, int NB>
 __global__ void __launch_bounds__(256, 1)
-fk_tracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, long long gstride,
+fk_tracks_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                  const float *__restrict__ offsets, float *__restrict__ pos, float *__restrict__ rout,
-                 long long n_frames, int n_joints, int n_steps, int fr, int l2_prefetch,
-                 const __grid_constant__ TrackProgram prog) {
+                 long long n_frames, int n_joints, int n_steps, int fr, const __grid_constant__ TrackProgram prog) {
+    static_assert(U == 1 || U == 2, "the per-box address word holds 16 items");
+    constexpr int C = kChunk;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const int warps = blockDim.x >> 5;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int n_items = n_steps * U;
-    const FkTracksGeom geo = fk_tracks_geom(fr, warps, n_joints, n_items);
+    const int n_chunks = (n_joints + C - 1) / C;
+    const FkTracksGeom geo = fk_tracks_geom(fr, warps, n_joints, n_items, NB);
+    const int BOX = geo.box_bytes;
 
-    // Schedule table, 32 bytes per item:  A = offset (x, y, z) | 16 j      B = 36 j | 12 j | 36 p | 12 p
-    // (byte offsets of the item's quaternion in its frame's input row and of the joint / parent rows in the two
-    // stages).  B.x < 0: no-op item, nothing is stored.  B.z < 0: the parent is in the track's registers.
-    // offsets[0] is ignored by the reference (the root translation is global_pos, skeleton.py:49).
+    // Item table, 16 bytes per item: offset (x, y, z) | word (above).  offsets[0] is ignored by the reference (the root
+    // translation is global_pos, skeleton.py:49).  Box table, 16 bytes per box: 64-bit address word (4 bits per item of
+    // the box's steps: joint mod 8) | first step of the box | unused; one entry past the last box closes the range.
     uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);
+    uint4 *ctab = reinterpret_cast<uint4 *>(smem_raw + (((n_items + 2) * 16 + 127) & ~127));
     for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
         const uint32_t c = prog.code[i];
         const uint32_t j = track_joint(c), p = track_parent(c);
-        uint4 A = make_uint4(0u, 0u, 0u, 0u), B = make_uint4(0x80000000u, 0u, 0x80000000u, 0u);
+        uint4 e = make_uint4(0u, 0u, 0u, 0xC0000000u);
         if (!(c & kTrackNoop)) {
-            if (j > 0) A.x = __float_as_uint(offsets[3 * j]), A.y = __float_as_uint(offsets[3 * j + 1]), A.z = __float_as_uint(offsets[3 * j + 2]);
-            A.w = 16u * j;
-            B.x = 36u * j, B.y = 12u * j;
-            if (!(c & kTrackCarry)) B.z = 36u * p, B.w = 12u * p;
+            if (j > 0) e.x = __float_as_uint(offsets[3 * j]), e.y = __float_as_uint(offsets[3 * j + 1]), e.z = __float_as_uint(offsets[3 * j + 2]);
+            e.w = j | (p << 10) | ((c & kTrackCarry) ? 0x40000000u : 0u);
         }
-        tab[2 * i] = A, tab[2 * i + 1] = B;
+        tab[i] = e;
     }
-    __syncthreads();  // the table; from here on the warps never meet again
+    for (int c = threadIdx.x; c <= n_chunks; c += blockDim.x) {
+        const int first = prog.chunk_first[c], last = c < n_chunks ? prog.chunk_first[c + 1] : first;
+        unsigned long long seq = 0;
+        for (int i = first * U; i < last * U; ++i) {
+            const uint32_t code = prog.code[i];
+            if (!(code & kTrackNoop)) seq |= static_cast<unsigned long long>(track_joint(code) & 7u) << (4 * (i - first * U));
+        }
+        ctab[c] = make_uint4(static_cast<uint32_t>(seq), static_cast<uint32_t>(seq >> 32), static_cast<uint32_t>(first), 0u);
+    }
 
     unsigned char *mine = smem_raw + geo.tab_bytes + warp * geo.warp_bytes;
-    const uint32_t rst0 = smem_u32(mine);
-    const uint32_t pst0 = rst0 + ((fr * 36 * n_joints + 16 + 15) & ~15);
-    const uint32_t tab0 = smem_u32(tab);
+    const uint32_t box0 = smem_u32(mine);
+    const uint32_t rst0 = box0 + NB * BOX;
+    const uint32_t pst0 = rst0 + geo.rst_bytes;
+    const uint32_t bar0 = pst0 + ((fr * 12 * n_joints + 16 + 15) & ~15);  // NB mbarriers (16-byte aligned)
+    const uint32_t fence_word = bar0 + 32 + 4 * lane;
+    const uint32_t tab0 = smem_u32(tab), ctab0 = smem_u32(ctab);
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) mbar_init(bar0 + 8 * b, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();  // the tables; from here on the warps never meet again
 
     const long long n_tiles = (n_frames + fr - 1) / fr;
     const long long tile_stride = static_cast<long long>(gridDim.x) * warps;
@@ -131,32 +152,64 @@ fk_tracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos,
     const int f = active ? lane / 3 : 0, a = active ? lane - 3 * f : 0;
     const int thr = active ? 0 : 0x7FFFFFFF;  // predicate threshold: the idle lanes never pass
     const float id0 = a == 0 ? 1.f : 0.f, id1 = a == 1 ? 1.f : 0.f, id2 = a == 2 ? 1.f : 0.f;
-    const int n_slots = ((n_steps + D - 1) / D) * D;  // steps padded to whole ring turns: the ring phase is the same for every tile
 
-    auto qrow_of = [&](long long t) { return rot + min(t * fr + f, n_frames - 1) * n_joints; };
-    auto q16_of = [&](int step, int u) { return tab[2 * (step * U + u)].w; };
-
-    // quaternion ring: q[d][u] holds the input of the slot that is d slots ahead (mod D)
-    float4 q[D][U];
-    const float4 *qrow = qrow_of(tile);
-    {
+    // TMA producer (lane 0): the warp's boxes in processing order, across its tiles
+    long long la_tile = tile;
+    int la_c0 = 0;
+    auto issue_next = [&](int buf) {
+        if (la_tile < n_tiles) {
+            mbar_arrive_expect_tx(bar0 + 8 * buf, BOX);
+            tma_load_2d(box0 + buf * BOX, &tm_rot, 4 * la_c0, static_cast<int>(la_tile * fr), bar0 + 8 * buf);
+            la_c0 += C;
+            if (la_c0 >= n_joints) la_c0 = 0, la_tile += tile_stride;
+        }
+    };
+    if (lane == 0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d)
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int step = min(d, n_steps - 1);
-                q[d][u] = track_ldg_q(reinterpret_cast<const unsigned char *>(qrow) + q16_of(step, u));
-            }
+        for (int b = 0; b < NB; ++b) issue_next(b);
     }
+
+    // ---- prefetch cursor: runs one step ahead of the walk, across boxes and tiles ------------------------------
+    long long p_tile = tile;     // tile of the step that is fetched next
+    int p_chunk = -1, p_local = 0, p_step = 0, p_end = 0;  // box of that step, its index inside the box, first step of the next box
+    uint32_t p_k = 0, p_row_swz = 0;
+    unsigned long long p_seq = 0;
+    auto fetch = [&](float4 (&q)[U], float (&sc)[U]) {
+        if (p_step == p_end) {  // the step opens a new box (the first of the next tile after the last one)
+            if (++p_chunk == n_chunks) p_chunk = 0, p_step = 0, p_tile += tile_stride;
+            if (p_tile < n_tiles) {
+                const uint32_t buf = p_k % NB;
+                mbar_wait(bar0 + 8 * buf, (p_k / NB) & 1);
+                ++p_k;
+                // the box row of this lane's frame is 128-byte aligned, so 16-byte chunk (jj ^ swz) of it is at
+                // (row | swz << 4) ^ (jj << 4): one XOR per read
+                const uint32_t row = box0 + buf * BOX + f * 128;
+                p_row_swz = row | (((row >> 7) & 7u) << 4);
+            }
+            const float4 ce = lds128_ro(ctab0 + 16 * p_chunk), cn = lds128_ro(ctab0 + 16 * p_chunk + 16);
+            p_seq = static_cast<unsigned long long>(__float_as_uint(ce.x)) | (static_cast<unsigned long long>(__float_as_uint(ce.y)) << 32);
+            p_end = static_cast<int>(__float_as_uint(cn.z));
+            p_local = 0;
+        }
+        const uint32_t fld = static_cast<uint32_t>(p_seq >> (4 * U * p_local));
+        q[0] = lds128(p_row_swz ^ ((fld << 4) & 0x70u));
+        if (U == 2) q[U - 1] = lds128(p_row_swz ^ (fld & 0x70u));
+#pragma unroll
+        for (int u = 0; u < U; ++u) sc[u] = rot_scale(q[u], 1e-8f);
+        ++p_local, ++p_step;
+    };
+
     float gnext = __ldg(gpos + min(tile * fr + f, n_frames - 1) * gstride + a);
-    bool draining = false;  // lane 0: a bulk store of the stage may still be in flight
+    uint32_t k = 0;          // boxes released so far (ring position of the box the walk is in)
+    bool draining = false;   // lane 0: a bulk store of the stage may still be in flight
+
+    float4 qa[U], qb[U];
+    float sa[U], sb[U];
+    fetch(qa, sa);  // step 0 of the first tile
 
     for (; tile < n_tiles; tile += tile_stride) {
         const long long f0 = tile * fr;
         const int nrows = static_cast<int>(min(static_cast<long long>(fr), n_frames - f0));
-        const long long next_tile = tile + tile_stride;
-        const bool has_next = next_tile < n_tiles;
-        const float4 *qrow_next = qrow_of(has_next ? next_tile : tile);
         // the stage sits at the 16-byte phase of the tile's global spans
         const uint32_t rphase = static_cast<uint32_t>((f0 * rpitch) & 15), pphase = static_cast<uint32_t>((f0 * ppitch) & 15);
         const uint32_t rrow = rst0 + rphase + f * rpitch + 12 * a;
@@ -166,58 +219,68 @@ fk_tracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos,
         float r0[U], r1[U], r2[U], pp[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) r0[u] = id0, r1[u] = id1, r2[u] = id2, pp[u] = gnext;
-        if (has_next) {
-            gnext = __ldg(gpos + min(next_tile * fr + f, n_frames - 1) * gstride + a);
-            // the warp's next tile (l2_prefetch = 1) or the one after it (2): its quaternions into L2 as one burst,
-            // well ahead of the ring
-            const long long far_tile = l2_prefetch == 2 ? next_tile + tile_stride : next_tile;
-            if (l2_prefetch && lane == 0 && far_tile < n_tiles - 1)
-                bulk_prefetch_l2(rot + far_tile * fr * n_joints, static_cast<uint32_t>(fr * 16 * n_joints));
+        {
+            const long long next_tile = tile + tile_stride;
+            if (next_tile < n_tiles) gnext = __ldg(gpos + min(next_tile * fr + f, n_frames - 1) * gstride + a);
         }
-        if (lane == 0 && draining) bulk_wait_read0();  // the previous tile has left the stage
-        __syncwarp();
 
-        for (int s0 = 0; s0 < n_slots; s0 += D) {
+        int step = 0, chunk = 0;
+        int e_end = static_cast<int>(__float_as_uint(lds128_ro(ctab0 + 16).z));  // first step of box 1
+        uint32_t acc = 0;
+        // one step of the walk with the quaternions / scales fetched a step ago
+        auto walk = [&](const float4 (&q)[U], const float (&sc)[U]) {
+            float4 e[U];
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const int s = s0 + d;
-                if (s < n_steps) {
-                    uint4 A[U], B[U];
+            for (int u = 0; u < U; ++u) e[u] = lds128_ro(tab0 + (step * U + u) * 16);
+            uint32_t wj[U], wp[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) A[u] = tab[2 * (s * U + u)], B[u] = tab[2 * (s * U + u) + 1];
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        track_load_parent_if(B[u].z, thr, rrow + B[u].z, prow + B[u].w, r0[u], r1[u], r2[u], pp[u]);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const float4 qq = q[d][u];
-                        const float sc = rot_scale(qq, 1e-8f);
-                        const float w = qq.x, x = qq.y, y = qq.z, z = qq.w;
-                        pp[u] = r0[u] * __uint_as_float(A[u].x) + r1[u] * __uint_as_float(A[u].y) + r2[u] * __uint_as_float(A[u].z) + pp[u];
-                        const float cx_ = r1[u] * z - r2[u] * y, cy_ = r2[u] * x - r0[u] * z, cz_ = r0[u] * y - r1[u] * x;
-                        const float ex = w * cx_ + (cy_ * z - cz_ * y);
-                        const float ey = w * cy_ + (cz_ * x - cx_ * z);
-                        const float ez = w * cz_ + (cx_ * y - cy_ * x);
-                        r0[u] = sc * ex + r0[u], r1[u] = sc * ey + r1[u], r2[u] = sc * ez + r2[u];
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        track_store_if(B[u].x, thr, rrow + B[u].x, prow + B[u].y, r0[u], r1[u], r2[u], pp[u]);
-                }
-                // refill ring entry d with the input of the slot D ahead: a later step of this tile, or -- past the
-                // end -- the matching step of the warp's next tile
-                {
-                    const int sn = s + D;
-                    const bool same = sn < n_slots;
-                    const int step = min(same ? sn : sn - n_slots, n_steps - 1);
-                    const unsigned char *base = reinterpret_cast<const unsigned char *>(same ? qrow : qrow_next);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) q[d][u] = track_ldg_q(base + q16_of(step, u));
-                    __syncwarp();  // keeps ptxas from sinking the loads towards their use (it schedules for an occupancy we do not have)
-                }
+            for (int u = 0; u < U; ++u) {
+                const uint32_t w = __float_as_uint(e[u].w);
+                wj[u] = w & 0x3FFu, wp[u] = (w >> 10) & 0x3FFu;
+                track_load_parent_if(w << 1, thr, rrow + 36 * wp[u], prow + 12 * wp[u], r0[u], r1[u], r2[u], pp[u]);
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                acc |= __float_as_uint(q[u].x);
+                const float w = q[u].x, x = q[u].y, y = q[u].z, z = q[u].w;
+                pp[u] = r0[u] * e[u].x + r1[u] * e[u].y + r2[u] * e[u].z + pp[u];
+                const float cx_ = r1[u] * z - r2[u] * y, cy_ = r2[u] * x - r0[u] * z, cz_ = r0[u] * y - r1[u] * x;
+                const float ex = w * cx_ + (cy_ * z - cz_ * y);
+                const float ey = w * cy_ + (cz_ * x - cx_ * z);
+                const float ez = w * cz_ + (cx_ * y - cy_ * x);
+                r0[u] = sc[u] * ex + r0[u], r1[u] = sc[u] * ey + r1[u], r2[u] = sc[u] * ez + r2[u];
+            }
+            if (step == 0) {  // the first stores of the tile: the previous tile must have left the stage
+                if (lane == 0 && draining) bulk_wait_read0();
+                __syncwarp();
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                track_store_if(__float_as_uint(e[u].w), thr, rrow + 36 * wj[u], prow + 12 * wj[u], r0[u], r1[u], r2[u], pp[u]);
+            if (++step == e_end) {
+                // The last step of a box.  Its loads must have LANDED before it is refilled through the async proxy
+                // (see fk_kernel.cuh): a store that depends on every quaternion read from it precedes the refill.
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
+                __syncwarp();
+                if (lane == 0) issue_next(k % NB);  // refill with the box NB ahead (this tile's or the next tile's)
+                ++k, ++chunk, acc = 0;
+                e_end = static_cast<int>(__float_as_uint(lds128_ro(ctab0 + 16 * chunk + 16).z));
+            }
+        };
+        // two steps per turn, ping-pong between the register sets (no copies); an odd step count leaves the first
+        // step of the next tile in set b
+        for (;;) {
+            fetch(qb, sb);
+            walk(qa, sa);
+            if (step == n_steps) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) qa[u] = qb[u], sa[u] = sb[u];
+                break;
+            }
+            fetch(qa, sa);
+            walk(qb, sb);
+            if (step == n_steps) break;
         }
-        qrow = qrow_next;
 
         // ---- the tile's output: two contiguous spans, aligned middle through the TMA engine --------------------
         fence_proxy_async_smem();  // this lane's stage writes -> visible to the async proxy

@@ -36,7 +36,7 @@ inline bool aligned32(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 // inside one process).
 #define PMB_KNOB_LIST(X)                                                                                          \
     X(FK_ROWS) X(FK_LANES) X(FK_TRACKS) X(FK_STAGES) X(FK_FR) X(FK_WARPS) X(FK_GROUP) X(FK_BLOCKS_PER_SM) X(FK_NB) \
-    X(FK_U) X(FK_D) X(FK_WARPS_PER_SM) X(FK_L2_PREFETCH) X(TMA_L2PROMO) X(FKQ_GROUP) X(FKQ_BLOCKS_PER_SM)         \
+    X(FK_U) X(FK_WARPS_PER_SM) X(TMA_L2PROMO) X(FKQ_GROUP) X(FKQ_BLOCKS_PER_SM)         \
     X(FKQ_MATRIX) X(DQ_GROUP) X(DQ_BLOCKS_PER_SM) X(FRDQ_ELEMS) X(FRP_BLOCKS_PER_SM) X(UNROLL_CHUNK_APPLY)        \
     X(VEC3_X4) X(HOST_CHUNK_MB) X(HOST_THREADS)
 enum Knob {
@@ -80,7 +80,9 @@ int kernel_fit(K kernel, const DeviceProps &dp, int threads, int smem, int &per_
 // The returned pointers stay valid until the calling thread's next lookup of the same kind.
 int joint_program(const int64_t *parents_host, int32_t n_joints, bool detach_root_children, const pmb::JointProgram *&prog,
                   int &n_slots);
-int track_program(const int64_t *parents_host, int32_t n_joints, int n_tracks, const pmb::TrackProgram *&prog, int &n_steps);
+// window: joints are scheduled in windows of that many consecutive joints (0 = the whole skeleton at once)
+int track_program(const int64_t *parents_host, int32_t n_joints, int n_tracks, int window, const pmb::TrackProgram *&prog,
+                  int &n_steps);
 
 // ---- TMA descriptor of the quaternion input: rot viewed as [n_frames][4 * n_joints] floats, box = box_frames x
 // `chunk` joints, hardware swizzle matched to the box row.  The last descriptor of a thread is cached.

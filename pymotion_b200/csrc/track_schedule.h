@@ -26,16 +26,22 @@ namespace pmb {
 constexpr int kTrackCap = 1024;  // items (steps x tracks) per program: travels as a 4 KB kernel parameter
 constexpr uint32_t kTrackCarry = 1u << 20, kTrackNoop = 1u << 21;
 
+constexpr int kTrackMaxChunks = PMB_MAX_JOINTS / 8;  // windows of 8 joints (one TMA box of quaternions)
 struct TrackProgram {
     uint32_t code[kTrackCap];
+    uint16_t chunk_first[kTrackMaxChunks + 2];  // first step of every window, then the total step count
 };
 
 __host__ __device__ inline uint32_t track_joint(uint32_t c) { return c & 0x3FFu; }
 __host__ __device__ inline uint32_t track_parent(uint32_t c) { return (c >> 10) & 0x3FFu; }
 
+// `window` > 0: joints are scheduled window by window in index order (a step only holds joints of one window of
+// `window` consecutive joints -- what is resident of the input at any time); chunk_first[w] receives the first step
+// of window w and chunk_first[n_windows] the total.  window = 0: one window, the whole skeleton.
 // Returns the number of steps T (items are code[t * n_tracks + u]), 0 if the schedule does not fit kTrackCap,
 // -1 for a bad parents table (bad_joint set).
-inline int build_track_schedule(const int64_t *parents, int n_joints, int n_tracks, uint32_t *code, int *bad_joint = nullptr) {
+inline int build_track_schedule(const int64_t *parents, int n_joints, int n_tracks, uint32_t *code, int *bad_joint = nullptr,
+                                int window = 0, uint16_t *chunk_first = nullptr) {
     if (n_joints < 1 || n_joints > PMB_MAX_JOINTS || n_tracks < 1) return -1;
     for (int i = 1; i < n_joints; ++i)
         if (parents[i] < 0 || parents[i] >= i) {
@@ -51,6 +57,8 @@ inline int build_track_schedule(const int64_t *parents, int n_joints, int n_trac
     }
     std::vector<int> last(U, -1), pick, ready;  // last[u]: joint track u processed in the previous step
     int done = 0, t = 0;
+    const int W = window > 0 ? window : n_joints;
+    if (chunk_first) chunk_first[0] = 0;
     // step 0: the root, on track 0, carried from the registers the kernel initialises (identity at global_pos)
     {
         if (U > kTrackCap) return 0;
@@ -58,10 +66,17 @@ inline int build_track_schedule(const int64_t *parents, int n_joints, int n_trac
         code[0] = 0u | kTrackCarry;
         step_of[0] = 0, last[0] = 0, done = 1, t = 1;
     }
+    int w_lo = 0, w_done = 1;  // current window [w_lo, w_lo + W), joints of it already scheduled
     while (done < n_joints) {
+        const int w_hi = std::min(n_joints, w_lo + W);
+        if (w_done == w_hi - w_lo) {  // window finished: the next one starts at this step
+            w_lo = w_hi, w_done = 0;
+            if (chunk_first) chunk_first[w_lo / W] = static_cast<uint16_t>(t);
+            continue;
+        }
         if ((t + 1) * U > kTrackCap) return 0;
         ready.clear();
-        for (int i = 1; i < n_joints; ++i) {
+        for (int i = std::max(1, w_lo); i < w_hi; ++i) {
             const int p = static_cast<int>(parents[i]);
             if (step_of[i] < 0 && step_of[p] >= 0 && step_of[p] < t) ready.push_back(i);
         }
@@ -91,13 +106,14 @@ inline int build_track_schedule(const int64_t *parents, int n_joints, int n_trac
             if (slot[u] >= 0) {
                 const int i = slot[u], p = static_cast<int>(parents[i]);
                 c = static_cast<uint32_t>(i) | (static_cast<uint32_t>(p) << 10) | (last[u] == p ? kTrackCarry : 0u);
-                step_of[i] = t, ++done;
+                step_of[i] = t, ++done, ++w_done;
             }
             code[t * U + u] = c;
             last[u] = slot[u];  // a no-op breaks the carry
         }
         ++t;
     }
+    if (chunk_first) chunk_first[(n_joints + W - 1) / W] = static_cast<uint16_t>(t);
     return t;
 }
 

@@ -11,6 +11,8 @@ stream of the tensors' device.  Deliberate, documented differences:
 
 * results are contiguous float32 tensors (input dtype restored on return), not
   float64 views of a 4x4 buffer;
+* large NumPy / CPU-tensor batches of ``fk`` / ``fk_quat`` take the chunked host pipeline (copy in, kernel and
+  copy out overlapped, ``pmb_fk_f32_host``); their results live in page-locked host memory;
 * the joint count is ``shape[-2]`` (the NumPy reference reads ``shape[1]`` in the
   dual-quaternion pair, ops/skeleton.py:188/:228, which is only right for 3-D input);
 * ``parents[i]`` must be in ``[0, i)`` for ``i >= 1`` -> ``ValueError`` otherwise.
@@ -57,6 +59,9 @@ def fk(rot, global_pos, offsets, parents):
     positions : [..., n_joints, 3]
     rotmats : [..., n_joints, 3, 3]   row-major, ``v' = M v``
     """
+    routed = _host_route("fk", rot, global_pos, offsets, parents)
+    if routed is not None:
+        return routed
     m = rt.Marshal(rot, global_pos, offsets)
     q = m.dev(rot)
     if q.dim() < 2 or q.shape[-1] != 4:
@@ -83,6 +88,9 @@ def fk_quat(rot, global_pos, offsets, parents):
     (sign included: it goes through the same branch selection, quat.py:85-156).
     This is what ``mirror`` / ``from_root_positions`` of the reference compute right
     after ``fk`` (ops/skeleton.py:322-323, :134-140); 44 J instead of 64 J bytes per pose."""
+    routed = _host_route("fk_quat", rot, global_pos, offsets, parents)
+    if routed is not None:
+        return routed
     m = rt.Marshal(rot, global_pos, offsets)
     q = m.dev(rot)
     if q.dim() < 2 or q.shape[-1] != 4:
@@ -326,52 +334,102 @@ def mirror(local_rotations, global_translation, parents, offsets, end_sites=None
     return m.out(rots), m.out(gt_mirrored), offsets, end_sites
 
 
-def fk_host(rot, global_pos, offsets, parents, out=None, chunk_frames: int = 0):
-    """End-to-end ``fk`` on HOST buffers (the reference's calling convention: arrays
-    live in host memory).  ``rot`` [F, J, 4] and ``global_pos`` [F, 3] are float32
-    NumPy arrays or CPU tensors -- page-locked for full PCIe rate --, ``offsets`` is
-    [J, 3].  The frame axis is cut into chunks that are copied in, computed and
-    copied out on two streams so H2D, kernel and D2H overlap (pmb_fk_f32_host).
+# ---- host-buffer pipeline (the reference's own calling convention: arrays in host memory) -----------------------
+_HOST_PATH_MIN_BYTES = 8 << 20  # below this a single copy in / kernel / copy out is as fast as the chunked pipeline
 
-    ``out=(positions, rotmats)`` may supply (pinned) CPU tensors to fill; otherwise
-    pinned tensors are allocated.  Returns CPU tensors (NumPy arrays if ``rot`` was one).
-    """
+
+def _is_host(x) -> bool:
+    return isinstance(x, np.ndarray) or (isinstance(x, torch.Tensor) and not x.is_cuda)
+
+
+def _host_f32(x, shape=None) -> torch.Tensor:
+    """Contiguous float32 CPU tensor sharing memory with ``x`` when ``x`` already is one (NumPy or torch)."""
+    t = torch.as_tensor(x)
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        t = torch.broadcast_to(t, tuple(shape))
+    return t.contiguous()
+
+
+def _pinned_empty(shape) -> torch.Tensor:
+    # page-locked, from torch's caching host allocator: the D2H copies land in it by DMA, and the block is
+    # recycled when the caller drops the result
+    return torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
+
+
+def _fk_host_pipeline(kind: str, rot, global_pos, offsets, parents, out=None, chunk_frames: int = 0):
+    """fk / fk_quat on HOST buffers through pmb_fk(_quat)_f32_host: the frame axis is cut into chunks that are
+    copied in, computed and copied out on two streams.  Returns CPU tensors (positions, rotmats | global_rots)."""
     from .. import _lib
 
-    as_numpy = isinstance(rot, np.ndarray)
-    q = torch.as_tensor(rot)
-    gp = torch.as_tensor(global_pos)
-    off = torch.as_tensor(offsets)
-    if q.is_cuda or gp.is_cuda:
-        raise ValueError("fk_host takes host buffers; use fk() for device tensors")
-    if q.dtype != torch.float32 or gp.dtype != torch.float32:
-        raise TypeError("fk_host needs float32 host buffers")
-    if q.dim() != 3 or q.shape[-1] != 4:
-        raise ValueError(f"rot must have shape [n_frames, n_joints, 4], got {tuple(q.shape)}")
-    n_frames, n_joints = int(q.shape[0]), int(q.shape[1])
-    if tuple(gp.shape) != (n_frames, 3) or tuple(off.shape) != (n_joints, 3):
-        raise ValueError("global_pos must be [n_frames, 3] and offsets [n_joints, 3]")
+    q = _host_f32(rot)
+    if q.dim() < 2 or q.shape[-1] != 4:
+        raise ValueError(f"rot must have shape [..., n_joints, 4], got {tuple(q.shape)}")
+    lead, n_joints = tuple(q.shape[:-2]), int(q.shape[-2])
+    n_frames = _lead_frames(lead)
     par = rt.host_parents(parents)
     if par.shape[0] != n_joints:
         raise ValueError(f"parents has {par.shape[0]} entries but rot has {n_joints} joints")
-    q, gp = q.contiguous(), gp.contiguous()
-    off = off.to(torch.float32).contiguous()
+    gp = _host_f32(global_pos, lead + (3,))
+    off = _host_f32(offsets)
+    if tuple(off.shape) != (n_joints, 3):
+        raise ValueError(f"offsets must have shape [{n_joints}, 3] on the host path, got {tuple(off.shape)}")
+    wide = (3, 3) if kind == "fk" else (4,)
     if out is None:
-        pin = torch.cuda.is_available()
-        pos = torch.empty((n_frames, n_joints, 3), dtype=torch.float32, pin_memory=pin)
-        rotm = torch.empty((n_frames, n_joints, 3, 3), dtype=torch.float32, pin_memory=pin)
+        pos, rout = _pinned_empty(lead + (n_joints, 3)), _pinned_empty(lead + (n_joints,) + wide)
     else:
-        pos, rotm = out
-        if tuple(pos.shape) != (n_frames, n_joints, 3) or tuple(rotm.shape) != (n_frames, n_joints, 3, 3):
+        pos, rout = out
+        if tuple(pos.shape) != lead + (n_joints, 3) or tuple(rout.shape) != lead + (n_joints,) + wide:
             raise ValueError("out buffers have the wrong shape")
-        if not (pos.is_contiguous() and rotm.is_contiguous() and pos.dtype == rotm.dtype == torch.float32):
+        if not (pos.is_contiguous() and rout.is_contiguous() and pos.dtype == rout.dtype == torch.float32
+                and not pos.is_cuda and not rout.is_cuda):
             raise ValueError("out buffers must be contiguous float32 CPU tensors")
     device = rt.default_device()
     if n_frames > 0:
+        fn = "pmb_fk_f32_host" if kind == "fk" else "pmb_fk_quat_f32_host"
         with torch.cuda.device(device):
-            _lib.check(_lib.load().pmb_fk_f32_host(q.data_ptr(), gp.data_ptr(), off.data_ptr(), par.ctypes.data,
-                                                   n_frames, n_joints, pos.data_ptr(), rotm.data_ptr(),
-                                                   int(chunk_frames)))
-    if as_numpy and out is None:
+            _lib.check(getattr(_lib.load(), fn)(q.data_ptr(), gp.data_ptr(), off.data_ptr(), par.ctypes.data, n_frames,
+                                                 n_joints, pos.data_ptr(), rout.data_ptr(), int(chunk_frames)))
+    return pos, rout
+
+
+def _host_route(kind: str, rot, global_pos, offsets, parents):
+    """The drop-in call with host arrays: NumPy / CPU tensors in -> NumPy / CPU tensors out, through the chunked
+    pipeline when the batch is large enough to need it.  None = take the single-shot path."""
+    if not (_is_host(rot) and _is_host(global_pos) and _is_host(offsets)):
+        return None
+    shape = tuple(rot.shape)
+    if len(shape) < 2 or shape[-1] != 4 or tuple(np.shape(offsets)) != (shape[-2], 3):
+        return None  # per-frame offsets and malformed inputs: the general path validates / handles them
+    n_frames = _lead_frames(shape[:-2])
+    if n_frames * (64 * shape[-2] + 12) < _HOST_PATH_MIN_BYTES:
+        return None
+    m = rt.Marshal(rot, global_pos, offsets)  # array kind / dtype of the result, float64 warning, grad guard
+    for x in (rot, global_pos, offsets):
+        if isinstance(x, torch.Tensor):
+            m.dev_check(x)
+    pos, rout = _fk_host_pipeline(kind, rot, global_pos, offsets, parents)
+    return m.out_host(pos), m.out_host(rout)
+
+
+def fk_host(rot, global_pos, offsets, parents, out=None, chunk_frames: int = 0):
+    """End-to-end ``fk`` on HOST buffers with explicit control of the output buffers and the chunk size
+    (``fk`` itself takes this route for large NumPy / CPU-tensor inputs).  ``rot`` [F, J, 4] and ``global_pos``
+    [F, 3] are float32 NumPy arrays or CPU tensors -- page-locked buffers are DMA'd directly, pageable ones go
+    through the library's staging ring --, ``offsets`` is [J, 3].  ``out=(positions, rotmats)`` may supply CPU
+    tensors to fill; otherwise page-locked tensors are allocated.  Returns CPU tensors (NumPy arrays if ``rot``
+    was one and ``out`` was not given)."""
+    pos, rotm = _fk_host_pipeline("fk", rot, global_pos, offsets, parents, out=out, chunk_frames=chunk_frames)
+    if isinstance(rot, np.ndarray) and out is None:
         return pos.numpy(), rotm.numpy()
     return pos, rotm
+
+
+def fk_quat_host(rot, global_pos, offsets, parents, out=None, chunk_frames: int = 0):
+    """``fk_host`` returning global quaternions instead of rotation matrices: 28 J instead of 48 J bytes per
+    frame come back over PCIe."""
+    pos, grot = _fk_host_pipeline("fk_quat", rot, global_pos, offsets, parents, out=out, chunk_frames=chunk_frames)
+    if isinstance(rot, np.ndarray) and out is None:
+        return pos.numpy(), grot.numpy()
+    return pos, grot

@@ -141,27 +141,22 @@ def test_product_package_never_imports_the_oracle():
                 assert "oracle" not in text.lower() or f == "_lib.py" and False, f"{f} mentions the oracle"
 
 
-def _track_schedule(lib, parents, n_tracks):
+def _track_schedule(lib, parents, n_tracks, window=0):
     par = np.asarray(parents, dtype=np.int64)
     codes = np.zeros(1024, dtype=np.uint32)
-    steps = lib.pmb_build_track_schedule(par.ctypes.data, len(par), n_tracks, codes.ctypes.data, codes.size)
+    first = np.zeros(70, dtype=np.int32)
+    steps = lib.pmb_build_track_schedule(par.ctypes.data, len(par), n_tracks, window, codes.ctypes.data, codes.size, first.ctypes.data)
     assert steps > 0, _lib.last_error()
-    return steps, codes[: steps * n_tracks].reshape(steps, n_tracks)
+    n_windows = -(-len(par) // window) if window else 1
+    return steps, codes[: steps * n_tracks].reshape(steps, n_tracks), first[: n_windows + 1]
 
 
-@pytest.mark.parametrize("name", ["body22", "smplh52", "deep65", "chain3", "body32"])
-@pytest.mark.parametrize("n_tracks", [1, 2, 3, 4])
-def test_track_schedule_is_a_valid_minimal_tree_schedule(name, n_tracks):
-    """The schedule of the fk track kernel: every joint exactly once, after its parent's step; `carry` only when the
-    parent is the same track's previous item; and the step count is the optimum for unit tasks with tree precedence
-    on `n_tracks` machines (Hu's bound: max over levels l of  l + ceil(#joints deeper than l / n_tracks))."""
-    lib = _lib.load()
-    par = parents_of(name)
-    n = len(par)
-    steps, code = _track_schedule(lib, par, n_tracks)
+def _check_schedule(par, code, n_tracks):
+    """Every joint exactly once, after its parent's step; `carry` only when the parent is the same track's
+    previous item.  Returns step_of."""
     CARRY, NOOP = 1 << 20, 1 << 21
     step_of, track_of = {}, {}
-    for t in range(steps):
+    for t in range(code.shape[0]):
         for u in range(n_tracks):
             c = int(code[t, u])
             if c & NOOP:
@@ -176,7 +171,21 @@ def test_track_schedule_is_a_valid_minimal_tree_schedule(name, n_tracks):
             assert step_of[p] < t, f"joint {j} at step {t} before its parent {p}"
             if c & CARRY:
                 assert step_of[p] == t - 1 and track_of[p] == u
-    assert sorted(step_of) == list(range(n))
+    assert sorted(step_of) == list(range(len(par)))
+    return step_of
+
+
+@pytest.mark.parametrize("name", ["body22", "smplh52", "deep65", "chain3", "body32"])
+@pytest.mark.parametrize("n_tracks", [1, 2, 3, 4])
+def test_track_schedule_is_a_valid_minimal_tree_schedule(name, n_tracks):
+    """The whole-skeleton schedule is the optimum for unit tasks with tree precedence on `n_tracks` machines
+    (Hu's bound: max over levels l of  l + 1 + ceil(#joints deeper than l / n_tracks))."""
+    lib = _lib.load()
+    par = parents_of(name)
+    n = len(par)
+    steps, code, first = _track_schedule(lib, par, n_tracks)
+    _check_schedule(par, code, n_tracks)
+    assert list(first) == [0, steps]
     depth = np.zeros(n, dtype=int)
     for i in range(1, n):
         depth[i] = depth[par[i]] + 1
@@ -184,11 +193,31 @@ def test_track_schedule_is_a_valid_minimal_tree_schedule(name, n_tracks):
     assert steps == max(bound, int(depth.max()) + 1)
 
 
+@pytest.mark.parametrize("name", sorted(TOPOLOGIES))
+@pytest.mark.parametrize("n_tracks", [1, 2, 3])
+def test_track_schedule_by_windows_of_one_box(name, n_tracks):
+    """What the fk track kernel runs: joints scheduled box by box (8 consecutive joints).  Valid as a whole, every
+    step holds joints of ONE window only, windows come in order, and the window table brackets them."""
+    lib = _lib.load()
+    par = parents_of(name)
+    n = len(par)
+    steps, code, first = _track_schedule(lib, par, n_tracks, window=8)
+    step_of = _check_schedule(par, code, n_tracks)
+    assert first[0] == 0 and first[-1] == steps and all(a < b for a, b in zip(first, first[1:]))
+    for j in range(n):
+        w = j // 8
+        assert first[w] <= step_of[j] < first[w + 1], f"joint {j} outside the steps of its window"
+    if n_tracks == 1:
+        assert steps == n
+    assert steps <= n and steps >= -(-n // n_tracks)
+
+
 def test_track_schedule_rejects_bad_tables():
     lib = _lib.load()
     codes = np.zeros(64, dtype=np.uint32)
     bad = np.array([0, 2, 1], dtype=np.int64)
-    assert lib.pmb_build_track_schedule(bad.ctypes.data, 3, 2, codes.ctypes.data, 64) == _lib.PMB_ERR_TOPOLOGY
+    assert lib.pmb_build_track_schedule(bad.ctypes.data, 3, 2, 0, codes.ctypes.data, 64, None) == _lib.PMB_ERR_TOPOLOGY
     ok = np.array([0, 0, 1], dtype=np.int64)
-    assert lib.pmb_build_track_schedule(ok.ctypes.data, 3, 9, codes.ctypes.data, 64) == _lib.PMB_ERR_SHAPE
-    assert lib.pmb_build_track_schedule(ok.ctypes.data, 3, 2, codes.ctypes.data, 2) == _lib.PMB_ERR_SHAPE
+    assert lib.pmb_build_track_schedule(ok.ctypes.data, 3, 9, 0, codes.ctypes.data, 64, None) == _lib.PMB_ERR_SHAPE
+    assert lib.pmb_build_track_schedule(ok.ctypes.data, 3, 2, 0, codes.ctypes.data, 2, None) == _lib.PMB_ERR_SHAPE
+    assert lib.pmb_build_track_schedule(ok.ctypes.data, 3, 2, 5, codes.ctypes.data, 64, None) == _lib.PMB_ERR_SHAPE

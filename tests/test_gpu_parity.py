@@ -611,23 +611,21 @@ def test_fk_lane_kernel(sk, set_knobs, knobs, name, n_frames):
 
 
 @pytest.mark.parametrize("knobs", [
-    {"PMB_FK_TRACKS": "1"},                                                   # two tracks, ring depth 4, tiles of 10 frames
-    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_D": "4"},
-    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_D": "8", "PMB_FK_FR": "8"},
-    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_D": "2"},
-    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_D": "4", "PMB_FK_FR": "8", "PMB_FK_WARPS_PER_SM": "1"},  # many tiles per warp
-    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "3", "PMB_FK_D": "2"},
-    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "3", "PMB_FK_D": "3", "PMB_FK_L2_PREFETCH": "0"},
-    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "4", "PMB_FK_D": "2"},
-    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "4", "PMB_FK_D": "3", "PMB_FK_WARPS_PER_SM": "2"},
+    {"PMB_FK_TRACKS": "1"},                                                   # two tracks, three boxes, tiles of 10 frames
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_NB": "2"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_NB": "3", "PMB_FK_FR": "8"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_NB": "2"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_NB": "4", "PMB_FK_FR": "8", "PMB_FK_WARPS_PER_SM": "1"},  # many tiles per warp
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_NB": "4", "PMB_FK_WARPS_PER_SM": "2"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_NB": "3", "PMB_FK_WARPS_PER_SM": "3"},
 ])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
                                            ("body32", 5_009), ("body22", 7), ("body16", 1), ("deep65", 29)])
 def test_fk_track_kernel(sk, set_knobs, knobs, name, n_frames):
-    """The track kernel (U independent joints per step from the host's level schedule, register ring of quaternions,
-    stage at the 16-byte phase of the global span with head / tail words stored by single lanes): every (U, D) that
+    """The track kernel (U independent joints per step from the host's box-by-box level schedule, ring of TMA boxes,
+    stage at the 16-byte phase of the global span with head / tail words stored by single lanes): every (U, NB) that
     is built, both tile sizes, odd joint counts with 10-frame tiles (unaligned spans), ragged frame counts (remainder
-    tile shorter than the ring), one warp per SM (stage and ring reuse across many tiles)."""
+    tile), one warp per SM (stage and ring reuse across many tiles)."""
     set_knobs(knobs)
     par = parents_of(name)
     rot, gp, off = synth_numpy(n_frames, par, seed=13 * len(par) + n_frames)
@@ -641,7 +639,7 @@ def test_fk_track_kernel(sk, set_knobs, knobs, name, n_frames):
 
 @pytest.mark.parametrize("seed", range(6))
 def test_fk_track_kernel_random_trees(sk, set_knobs, seed):
-    """Random topologies (bushy, deep, up to 200 joints) through the track schedule with 1 .. 4 tracks."""
+    """Random topologies (bushy, deep, up to 200 joints) through the track schedule with 1 and 2 tracks."""
     rng = np.random.default_rng(1000 + seed)
     n_joints = int(rng.integers(2, 200))
     par = np.zeros(n_joints, dtype=np.int64)
@@ -650,8 +648,8 @@ def test_fk_track_kernel_random_trees(sk, set_knobs, seed):
     n_frames = int(rng.integers(1, 3000))
     rot, gp, off = synth_numpy(n_frames, par, seed=seed)
     want_pos, want_rotm = orc.fk(rot, gp, off, par)
-    for u, d in ((1, 4), (2, 4), (3, 3), (4, 2)):
-        set_knobs({"PMB_FK_TRACKS": "1", "PMB_FK_U": str(u), "PMB_FK_D": str(d), "PMB_FK_FR": "8" if n_joints > 150 else "10"})
+    for u, nb in ((1, 2), (2, 3), (2, 4)):
+        set_knobs({"PMB_FK_TRACKS": "1", "PMB_FK_U": str(u), "PMB_FK_NB": str(nb), "PMB_FK_FR": "8" if n_joints > 150 else "10"})
         pos, rotm = sk.fk(rot, gp, off, par)
         assert "fk_tracks_kernel" in _lib.load().pmb_last_variant().decode()
         assert_allclose(pos, want_pos, rtol=2e-5, atol=2e-5)

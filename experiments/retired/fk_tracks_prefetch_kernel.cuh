@@ -15,7 +15,10 @@
 //            already holds every joint processed so far (the same lane wrote it).
 //   input    ring of NB boxes per warp, refilled by lane 0 as soon as the box's last step has read it; an item
 //            reads its quaternion straight from the box (one swizzled LDS.128 per item, the three lanes of a frame
-//            share it).  (Measured and retired, experiments/retired/fk_tracks_ldg_ring_kernel.cuh: a whole-skeleton
+//            share it) ONE STEP AHEAD of its use, together with its normalisation scale 2 / (|q| + eps)^2 (two MUFU
+//            ops in a ~100-cycle chain that does not depend on the walk): the dependent chain of a step is then
+//            parent row -> two cross products -> store.  The box-relative address of a step's quaternions comes from a
+//            64-bit word per box (4 bits per item), so the prefetch does not wait for the step's table entry.  (Measured and retired, experiments/retired/fk_tracks_ldg_ring_kernel.cuh: a whole-skeleton
 //            schedule fed by per-item 16-byte global loads through a register ring -- half of every 32-byte sector
 //            wasted, the ring too shallow for the latency: 2.95 ms at 4M x 52 against 2.50 for the lane kernel.)
 //   output   the dense image of the tile's output (FR x 36 J and FR x 12 J bytes) goes to HBM as two contiguous TMA
@@ -39,15 +42,15 @@ namespace pmb {
 struct FkTracksGeom {
     int tab_bytes, box_bytes, rst_bytes, warp_bytes, block_bytes;
 };
-// per block: schedule table (16 bytes per item) | chunk table | per warp: NB boxes | R stage (+16 bytes of phase slack) |
-// P stage (+16) | NB mbarriers (64 bytes reserved) + fence words
+// per block: schedule table (16 bytes per item) | box table (16 bytes per box) | per warp: NB boxes | R stage (+16 bytes of
+// phase slack) | P stage (+16) | NB mbarriers + fence words
 __host__ __device__ inline FkTracksGeom fk_tracks_geom(int fr, int warps, int n_joints, int n_items, int n_boxes) {
     FkTracksGeom g;
     const int n_chunks = (n_joints + kChunk - 1) / kChunk;
-    g.tab_bytes = ((n_items * 16 + 127) & ~127) + (((n_chunks + 2) * 4 + 127) & ~127);
+    g.tab_bytes = (((n_items + 2) * 16 + 127) & ~127) + (((n_chunks + 1) * 16 + 127) & ~127);
     g.box_bytes = fr * 128;  // FR frames x 8 joints x 16 bytes
     g.rst_bytes = (fr * 36 * n_joints + 16 + 15) & ~15;
-    g.warp_bytes = (n_boxes * g.box_bytes + g.rst_bytes + ((fr * 12 * n_joints + 16 + 15) & ~15) + 64 + 128 + 127) & ~127;
+    g.warp_bytes = (n_boxes * g.box_bytes + g.rst_bytes + ((fr * 12 * n_joints + 16 + 15) & ~15) + 32 + 128 + 127) & ~127;
     g.block_bytes = 128 + g.tab_bytes + warps * g.warp_bytes;
     return g;
 }
@@ -82,34 +85,28 @@ __device__ __forceinline__ void track_store_if(uint32_t flag /* stored iff (int)
         "}" ::"r"(flag), "r"(raddr), "r"(paddr), "f"(r0), "f"(r1), "f"(r2), "f"(pp), "r"(thr));
 }
 
-// U: tracks per lane (independent chains interleaved in the instruction stream).  UL: tracks as LANE GROUPS (1 or 2):
-// with UL = 2 lanes 0 .. 15 walk one joint and lanes 16 .. 31 another one of the same 5 frames -- half the stage per warp,
-// so twice as many warps (dependent chains in flight) for the same shared memory at the same instructions per
-// frame and joint.  The schedule has U * UL tracks; track (t, u) is column t * U + u of a step.  NB: TMA boxes in flight.
-template <int U, int NB, int UL = 1>
-__global__ void __launch_bounds__(512, 1)
+// U: tracks per lane (independent chains interleaved; 1 or 2).  NB: TMA boxes in flight per warp (2 .. 4).
+template <int U, int NB>
+__global__ void __launch_bounds__(256, 1)
 fk_tracks_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__restrict__ gpos, long long gstride,
                  const float *__restrict__ offsets, float *__restrict__ pos, float *__restrict__ rout,
-                 long long n_frames, int n_joints, int n_steps, int fr, const float *__restrict__ rot_l2_prefetch,
-                 const __grid_constant__ TrackProgram prog) {
-    static_assert(UL == 1 || UL == 2, "one or two lane groups");
-    static_assert(NB >= 2 && NB <= 8, "ring depth");
+                 long long n_frames, int n_joints, int n_steps, int fr, const __grid_constant__ TrackProgram prog) {
+    static_assert(U == 1 || U == 2, "the per-box address word holds 16 items");
     constexpr int C = kChunk;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const int warps = blockDim.x >> 5;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    const int n_items = n_steps * U * UL;
+    const int n_items = n_steps * U;
     const int n_chunks = (n_joints + C - 1) / C;
     const FkTracksGeom geo = fk_tracks_geom(fr, warps, n_joints, n_items, NB);
     const int BOX = geo.box_bytes;
 
-    // Schedule table, 16 bytes per item: offset (x, y, z) | word (above).  One shared-memory wavefront per item; the
-    // byte offsets of the joint / parent rows in the two stages and of the quaternion in its box row are multiplies of
-    // the word's fields (issue slots are there, shared-memory bandwidth is what the walk is short of).
-    // offsets[0] is ignored by the reference (the root translation is global_pos, skeleton.py:49).
+    // Item table, 16 bytes per item: offset (x, y, z) | word (above).  offsets[0] is ignored by the reference (the root
+    // translation is global_pos, skeleton.py:49).  Box table, 16 bytes per box: 64-bit address word (4 bits per item of
+    // the box's steps: joint mod 8) | first step of the box | unused; one entry past the last box closes the range.
     uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);
-    int *cfirst = reinterpret_cast<int *>(smem_raw + ((n_items * 16 + 127) & ~127));
+    uint4 *ctab = reinterpret_cast<uint4 *>(smem_raw + (((n_items + 2) * 16 + 127) & ~127));
     for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
         const uint32_t c = prog.code[i];
         const uint32_t j = track_joint(c), p = track_parent(c);
@@ -120,15 +117,23 @@ fk_tracks_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__rest
         }
         tab[i] = e;
     }
-    for (int i = threadIdx.x; i <= n_chunks; i += blockDim.x) cfirst[i] = prog.chunk_first[i];
+    for (int c = threadIdx.x; c <= n_chunks; c += blockDim.x) {
+        const int first = prog.chunk_first[c], last = c < n_chunks ? prog.chunk_first[c + 1] : first;
+        unsigned long long seq = 0;
+        for (int i = first * U; i < last * U; ++i) {
+            const uint32_t code = prog.code[i];
+            if (!(code & kTrackNoop)) seq |= static_cast<unsigned long long>(track_joint(code) & 7u) << (4 * (i - first * U));
+        }
+        ctab[c] = make_uint4(static_cast<uint32_t>(seq), static_cast<uint32_t>(seq >> 32), static_cast<uint32_t>(first), 0u);
+    }
 
     unsigned char *mine = smem_raw + geo.tab_bytes + warp * geo.warp_bytes;
     const uint32_t box0 = smem_u32(mine);
     const uint32_t rst0 = box0 + NB * BOX;
     const uint32_t pst0 = rst0 + geo.rst_bytes;
     const uint32_t bar0 = pst0 + ((fr * 12 * n_joints + 16 + 15) & ~15);  // NB mbarriers (16-byte aligned)
-    const uint32_t fence_word = bar0 + 64 + 4 * lane;
-    const uint32_t tab0 = smem_u32(tab);
+    const uint32_t fence_word = bar0 + 32 + 4 * lane;
+    const uint32_t tab0 = smem_u32(tab), ctab0 = smem_u32(ctab);
     if (lane == 0) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) mbar_init(bar0 + 8 * b, 1);
@@ -142,10 +147,9 @@ fk_tracks_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__rest
     if (tile >= n_tiles) return;
     const int rpitch = 36 * n_joints, ppitch = 12 * n_joints;  // bytes per frame row of the two stages
 
-    // lane -> (lane group, frame, row); lanes past 3 FR of their group shadow its first lane and never touch the stage
-    const int grp = UL == 2 ? lane >> 4 : 0, gl = UL == 2 ? (lane & 15) : lane;
-    const bool active = gl < 3 * fr;
-    const int f = active ? gl / 3 : 0, a = active ? gl - 3 * f : 0;
+    // lane -> (frame, row); lanes past 3 FR shadow lane 0 and never touch the stage
+    const bool active = lane < 3 * fr;
+    const int f = active ? lane / 3 : 0, a = active ? lane - 3 * f : 0;
     const int thr = active ? 0 : 0x7FFFFFFF;  // predicate threshold: the idle lanes never pass
     const float id0 = a == 0 ? 1.f : 0.f, id1 = a == 1 ? 1.f : 0.f, id2 = a == 2 ? 1.f : 0.f;
 
@@ -165,9 +169,43 @@ fk_tracks_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__rest
         for (int b = 0; b < NB; ++b) issue_next(b);
     }
 
+    // ---- prefetch cursor: runs one step ahead of the walk, across boxes and tiles ------------------------------
+    long long p_tile = tile;     // tile of the step that is fetched next
+    int p_chunk = -1, p_local = 0, p_step = 0, p_end = 0;  // box of that step, its index inside the box, first step of the next box
+    uint32_t p_k = 0, p_row_swz = 0;
+    unsigned long long p_seq = 0;
+    auto fetch = [&](float4 (&q)[U], float (&sc)[U]) {
+        if (p_step == p_end) {  // the step opens a new box (the first of the next tile after the last one)
+            if (++p_chunk == n_chunks) p_chunk = 0, p_step = 0, p_tile += tile_stride;
+            if (p_tile < n_tiles) {
+                const uint32_t buf = p_k % NB;
+                mbar_wait(bar0 + 8 * buf, (p_k / NB) & 1);
+                ++p_k;
+                // the box row of this lane's frame is 128-byte aligned, so 16-byte chunk (jj ^ swz) of it is at
+                // (row | swz << 4) ^ (jj << 4): one XOR per read
+                const uint32_t row = box0 + buf * BOX + f * 128;
+                p_row_swz = row | (((row >> 7) & 7u) << 4);
+            }
+            const float4 ce = lds128_ro(ctab0 + 16 * p_chunk), cn = lds128_ro(ctab0 + 16 * p_chunk + 16);
+            p_seq = static_cast<unsigned long long>(__float_as_uint(ce.x)) | (static_cast<unsigned long long>(__float_as_uint(ce.y)) << 32);
+            p_end = static_cast<int>(__float_as_uint(cn.z));
+            p_local = 0;
+        }
+        const uint32_t fld = static_cast<uint32_t>(p_seq >> (4 * U * p_local));
+        q[0] = lds128(p_row_swz ^ ((fld << 4) & 0x70u));
+        if (U == 2) q[U - 1] = lds128(p_row_swz ^ (fld & 0x70u));
+#pragma unroll
+        for (int u = 0; u < U; ++u) sc[u] = rot_scale(q[u], 1e-8f);
+        ++p_local, ++p_step;
+    };
+
     float gnext = __ldg(gpos + min(tile * fr + f, n_frames - 1) * gstride + a);
-    uint32_t k = 0;
-    bool draining = false;  // lane 0: a bulk store of the stage may still be in flight
+    uint32_t k = 0;          // boxes released so far (ring position of the box the walk is in)
+    bool draining = false;   // lane 0: a bulk store of the stage may still be in flight
+
+    float4 qa[U], qb[U];
+    float sa[U], sb[U];
+    fetch(qa, sa);  // step 0 of the first tile
 
     for (; tile < n_tiles; tile += tile_stride) {
         const long long f0 = tile * fr;
@@ -185,63 +223,63 @@ fk_tracks_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__rest
             const long long next_tile = tile + tile_stride;
             if (next_tile < n_tiles) gnext = __ldg(gpos + min(next_tile * fr + f, n_frames - 1) * gstride + a);
         }
-        if (lane == 0) {
-            // the warp's next tile: its quaternions (FR x 16 J contiguous bytes) into L2 as one burst, a tile ahead of the boxes
-            const long long next_tile = tile + tile_stride;
-            if (rot_l2_prefetch && next_tile < n_tiles - 1)
-                bulk_prefetch_l2(rot_l2_prefetch + next_tile * fr * 4 * n_joints, static_cast<uint32_t>(fr * 16 * n_joints));
-            if (draining) bulk_wait_read0();  // the previous tile has left the stage
-        }
-        __syncwarp();
 
-        int step = 0;
-        for (int c = 0; c < n_chunks; ++c) {
-            const uint32_t buf = k % NB;
-            mbar_wait(bar0 + 8 * buf, (k / NB) & 1);
-            ++k;
-            // the box row of this lane's frame is 128-byte aligned, so 16-byte chunk (jj ^ swz) of it is at
-            // (row | swz << 4) ^ (jj << 4): one XOR per read
-            const uint32_t row = box0 + buf * BOX + f * 128;
-            const uint32_t row_swz = row | (((row >> 7) & 7u) << 4);
-            const int step_end = cfirst[c + 1];
-            uint32_t acc = 0;
-            for (; step < step_end; ++step) {
-                const uint32_t t0 = tab0 + (step * UL + grp) * (U * 16);
-                float4 e[U], qq[U];
-                uint32_t wj[U], wp[U];
+        int step = 0, chunk = 0;
+        int e_end = static_cast<int>(__float_as_uint(lds128_ro(ctab0 + 16).z));  // first step of box 1
+        uint32_t acc = 0;
+        // one step of the walk with the quaternions / scales fetched a step ago
+        auto walk = [&](const float4 (&q)[U], const float (&sc)[U]) {
+            float4 e[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) e[u] = lds128_ro(t0 + u * 16);
+            for (int u = 0; u < U; ++u) e[u] = lds128_ro(tab0 + (step * U + u) * 16);
+            uint32_t wj[U], wp[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t w = __float_as_uint(e[u].w);
-                    qq[u] = lds128(row_swz ^ ((w & 7u) << 4));
-                    wj[u] = w & 0x3FFu, wp[u] = (w >> 10) & 0x3FFu;
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    track_load_parent_if(__float_as_uint(e[u].w) << 1, thr, rrow + 36 * wp[u], prow + 12 * wp[u], r0[u], r1[u], r2[u], pp[u]);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    acc |= __float_as_uint(qq[u].x);
-                    const float sc = rot_scale(qq[u], 1e-8f);
-                    const float w = qq[u].x, x = qq[u].y, y = qq[u].z, z = qq[u].w;
-                    pp[u] = r0[u] * e[u].x + r1[u] * e[u].y + r2[u] * e[u].z + pp[u];
-                    const float cx_ = r1[u] * z - r2[u] * y, cy_ = r2[u] * x - r0[u] * z, cz_ = r0[u] * y - r1[u] * x;
-                    const float ex = w * cx_ + (cy_ * z - cz_ * y);
-                    const float ey = w * cy_ + (cz_ * x - cx_ * z);
-                    const float ez = w * cz_ + (cx_ * y - cy_ * x);
-                    r0[u] = sc * ex + r0[u], r1[u] = sc * ey + r1[u], r2[u] = sc * ez + r2[u];
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    track_store_if(__float_as_uint(e[u].w), thr, rrow + 36 * wj[u], prow + 12 * wj[u], r0[u], r1[u], r2[u], pp[u]);
-                if (UL > 1) __syncwarp();  // a parent row may have been stored by the other lane group
+            for (int u = 0; u < U; ++u) {
+                const uint32_t w = __float_as_uint(e[u].w);
+                wj[u] = w & 0x3FFu, wp[u] = (w >> 10) & 0x3FFu;
+                track_load_parent_if(w << 1, thr, rrow + 36 * wp[u], prow + 12 * wp[u], r0[u], r1[u], r2[u], pp[u]);
             }
-            // the box's loads must have LANDED before it is refilled through the async proxy (see fk_kernel.cuh): a
-            // store that depends on every loaded quaternion precedes the refill
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
-            __syncwarp();
-            if (lane == 0) issue_next(buf);  // refill with the box NB ahead (this tile's or the next tile's)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                acc |= __float_as_uint(q[u].x);
+                const float w = q[u].x, x = q[u].y, y = q[u].z, z = q[u].w;
+                pp[u] = r0[u] * e[u].x + r1[u] * e[u].y + r2[u] * e[u].z + pp[u];
+                const float cx_ = r1[u] * z - r2[u] * y, cy_ = r2[u] * x - r0[u] * z, cz_ = r0[u] * y - r1[u] * x;
+                const float ex = w * cx_ + (cy_ * z - cz_ * y);
+                const float ey = w * cy_ + (cz_ * x - cx_ * z);
+                const float ez = w * cz_ + (cx_ * y - cy_ * x);
+                r0[u] = sc[u] * ex + r0[u], r1[u] = sc[u] * ey + r1[u], r2[u] = sc[u] * ez + r2[u];
+            }
+            if (step == 0) {  // the first stores of the tile: the previous tile must have left the stage
+                if (lane == 0 && draining) bulk_wait_read0();
+                __syncwarp();
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                track_store_if(__float_as_uint(e[u].w), thr, rrow + 36 * wj[u], prow + 12 * wj[u], r0[u], r1[u], r2[u], pp[u]);
+            if (++step == e_end) {
+                // The last step of a box.  Its loads must have LANDED before it is refilled through the async proxy
+                // (see fk_kernel.cuh): a store that depends on every quaternion read from it precedes the refill.
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
+                __syncwarp();
+                if (lane == 0) issue_next(k % NB);  // refill with the box NB ahead (this tile's or the next tile's)
+                ++k, ++chunk, acc = 0;
+                e_end = static_cast<int>(__float_as_uint(lds128_ro(ctab0 + 16 * chunk + 16).z));
+            }
+        };
+        // two steps per turn, ping-pong between the register sets (no copies); an odd step count leaves the first
+        // step of the next tile in set b
+        for (;;) {
+            fetch(qb, sb);
+            walk(qa, sa);
+            if (step == n_steps) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) qa[u] = qb[u], sa[u] = sb[u];
+                break;
+            }
+            fetch(qa, sa);
+            walk(qb, sb);
+            if (step == n_steps) break;
         }
 
         // ---- the tile's output: two contiguous spans, aligned middle through the TMA engine --------------------

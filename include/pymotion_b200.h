@@ -212,6 +212,20 @@ int pmb_interpolate_positions_f32(const double *sample_times, const double *orig
 /* ops/vector.py:4  v / (|v| + eps) over rows of length k. */
 int pmb_vec_normalize_f32(const float *v, float eps, float *out, int64_t n, int32_t k, void *stream);
 
+/* ---- the numeric part of BVH.get_data (io/bvh.py:332-365) ----------------- */
+
+/* rots = quat.normalize(quat.unroll(quat.from_euler(np.radians(rotations), rot_order tiled over
+ * the frames), axis=0))  (io/bvh.py:352-359) as ONE fused three-pass scan: the un-unrolled
+ * quaternions are never stored.
+ *   euler_deg    [n_frames][n_joints][3]   Euler angles in DEGREES, as read from the file
+ *   order_codes  [n_joints]                one byte per joint, o0 + 3*o1 + 9*o2 with 0|1|2 = 'x'|'y'|'z'
+ *   out          [n_frames][n_joints][4]   unit quaternions, sign-continuous along the frame axis
+ *   workspace    pmb_unroll_workspace_bytes(n_frames, n_joints) bytes of device memory
+ * BVH text parsing stays on the host (out of scope). */
+int pmb_bvh_rotations_to_quat_f32(const float *euler_deg, const uint8_t *order_codes, int64_t n_frames,
+                                  int64_t n_joints, float *out, void *workspace, int64_t workspace_bytes,
+                                  void *stream);
+
 /* ---- introspection of the host-side joint program (tests) ---- */
 
 /* Builds the per-joint program the chain kernels execute for `parents_host`:

@@ -425,9 +425,47 @@ def gen_misc():
     return d
 
 
+def gen_bvh():
+    """the numeric chain of BVH.get_data (io/bvh.py:332-365) run through the REAL BVH class on a
+    synthetic, in-memory `data` dictionary (no file is parsed: text I/O is out of scope).  Euler angles in degrees
+    with large frame-to-frame jumps so that the unroll has covers to fix, mixed per-joint channel orders."""
+    import pymotion.io.bvh as ref_bvh
+
+    d = {}
+    rng = np.random.default_rng(77)
+    orders = [list(o) for o in ("zyx", "xyz", "yzx", "zxy", "xzy", "yxz")]
+    for tag, n_frames, n_joints in (("small", 7, 3), ("body22", 300, 22), ("long", 1000, 5)):
+        # a smooth motion plus jumps of whole turns: the same rotations, the other quaternion cover
+        base = np.cumsum(rng.normal(0, 6.0, (n_frames, n_joints, 3)), axis=0) + rng.uniform(-180, 180, (1, n_joints, 3))
+        turns = 360.0 * rng.integers(-1, 2, (n_frames, n_joints, 3)) * (rng.uniform(size=(n_frames, n_joints, 3)) < 0.15)
+        rotations = base + turns
+        rot_order = np.array([orders[k % len(orders)] for k in range(n_joints)])
+        bvh = ref_bvh.BVH()
+        bvh.data = {
+            "names": np.array([f"j{k}" for k in range(n_joints)]),
+            "offsets": rng.normal(0, 0.15, (n_joints, 3)),
+            "end_sites": np.zeros((0, 3)),
+            "end_sites_parents": np.zeros((0,), dtype=int),
+            "parents": np.array([0] + [max(0, k - 1) for k in range(1, n_joints)]),
+            "rot_order": rot_order,
+            "positions": np.zeros((n_frames, n_joints, 3)),
+            "rotations": rotations,
+            "frame_time": 1.0 / 60.0,
+        }
+        rots, pos, parents, offsets, end_sites, end_sites_parents = bvh.get_data()
+        d[f"{tag}/rotations_deg"] = rotations
+        d[f"{tag}/rot_order"] = rot_order
+        d[f"{tag}/rots"] = rots
+    np.savez_compressed(os.path.join(OUT, "bvh.npz"), **d)
+    return d
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    for fn in (gen_fk, gen_dq, gen_quat, gen_quat_ext, gen_ik, gen_misc):
+    only = sys.argv[1:]
+    for fn in (gen_fk, gen_dq, gen_quat, gen_quat_ext, gen_ik, gen_misc, gen_bvh):
+        if only and fn.__name__ not in only:
+            continue
         out = fn()
         print(fn.__name__, len(out), "arrays")
     sizes = {f: os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)}

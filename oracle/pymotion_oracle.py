@@ -599,3 +599,14 @@ def interpolate_positions(sample_times, original_times, positions, axis, method=
     out = (1 - wb) * lo
     out += wb * hi
     return out
+
+
+# ----------------------------------------------------------------------------
+# io/bvh.py: the numeric part of BVH.get_data
+# ----------------------------------------------------------------------------
+def bvh_get_data_rotations(rotations_deg, rot_order):
+    """io/bvh.py:352-359: rots = normalize(unroll(from_euler(np.radians(rotations), order tiled over the frames),
+    axis=0)).  rotations_deg [n_frames, n_joints, 3] in degrees, rot_order [n_joints, 3] of 'x' | 'y' | 'z'."""
+    order = np.tile(rot_order, (rotations_deg.shape[0], 1, 1))
+    rots = quat_unroll(quat_from_euler(np.radians(rotations_deg), order), axis=0)
+    return quat_normalize(rots)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "pmb_quat_from_to_axis_f32": [_vp, _vp, _vp, _i32, _vp, _i64, _vp],
     "pmb_unroll_workspace_bytes": [_i64, _i64],
     "pmb_unroll_f32": [_vp, _i32, _i64, _i64, _vp, _vp, _i64, _vp],
+    "pmb_bvh_rotations_to_quat_f32": [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp],
     "pmb_dq_is_unit_f32": [_vp, _f32, _i64, _vp, _vp],
     "pmb_dq_normalize_f32": [_vp, _vp, _i64, _vp, _vp],
     "pmb_from_root_positions_f32": [_vp, _vp, _vp, _i64, _i32, _vp, _vp],

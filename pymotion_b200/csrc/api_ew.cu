@@ -209,6 +209,36 @@ int pmb_unroll_f32(const float *x, int32_t width, int64_t n_steps, int64_t n_col
     return PMB_OK;
 }
 
+// io/bvh.py:352-359: the numeric part of BVH.get_data, one fused three-pass scan (rotations_ext.cuh)
+int pmb_bvh_rotations_to_quat_f32(const float *euler_deg, const uint8_t *order_codes, int64_t n_frames, int64_t n_joints, float *out,
+                                  void *workspace, int64_t workspace_bytes, void *stream) {
+    if (n_frames < 0 || n_joints < 0) return fail(PMB_ERR_SHAPE, "%s: negative size", __func__);
+    if (n_frames == 0 || n_joints == 0) return PMB_OK;
+    if (!euler_deg || !order_codes || !out || !workspace) return fail(PMB_ERR_NULL, "%s: NULL array pointer", __func__);
+    PMB_NEED16(out);
+    if (workspace_bytes < pmb_unroll_workspace_bytes(n_frames, n_joints))
+        return fail(PMB_ERR_SHAPE, "%s: workspace too small (%lld < %lld bytes)", __func__, static_cast<long long>(workspace_bytes),
+                    static_cast<long long>(pmb_unroll_workspace_bytes(n_frames, n_joints)));
+    DeviceProps dp;
+    int rc = device_props(dp);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t chunks = (n_frames + pmb::kUnrollChunk - 1) / pmb::kUnrollChunk;
+    if (n_joints > 0x7FFFFFFFLL || (chunks * n_joints + 127) / 128 > 0x7FFFFFFFLL)
+        return fail(PMB_ERR_SHAPE, "%s: array too large for one launch", __func__);
+    uint8_t *local = static_cast<uint8_t *>(workspace), *agg = local + n_frames * n_joints;
+    const long long local_threads = chunks * n_joints;
+    pmb::bvh_local_kernel<<<static_cast<unsigned>((local_threads + 127) / 128), 128, 0, st>>>(euler_deg, order_codes, n_frames, n_joints,
+                                                                                              chunks, local, agg);
+    PMB_CUDA(cudaGetLastError());
+    pmb::unroll_chunks_kernel<<<static_cast<unsigned>(n_joints), 256, 0, st>>>(agg, chunks, n_joints);
+    PMB_CUDA(cudaGetLastError());
+    pmb::bvh_apply_kernel<<<ew_grid(n_frames * n_joints, 256, dp), 256, 0, st>>>(euler_deg, order_codes, n_frames, n_joints, local, agg,
+                                                                                reinterpret_cast<float4 *>(out));
+    PMB_CUDA(cudaGetLastError());
+    return PMB_OK;
+}
+
 int pmb_dq_is_unit_f32(const float *dq, float atol, int64_t n, int32_t *flags3, void *stream) {
     if (!flags3) return fail(PMB_ERR_NULL, "%s: flags3 is NULL", __func__);
     PMB_CUDA(cudaMemsetAsync(flags3, 0, 3 * sizeof(int32_t), static_cast<cudaStream_t>(stream)));

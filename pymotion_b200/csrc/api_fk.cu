@@ -185,7 +185,7 @@ struct FkTracksShape {
 inline FkTracksShape fk_tracks_shape(int fr, int n_joints, int n_items, int n_boxes, int warps_cap, const DeviceProps &dp) {
     FkTracksShape best;
     for (int blocks = 1; blocks <= 4; ++blocks)
-        for (int warps = 8; warps >= 1; --warps) {
+        for (int warps = 16; warps >= 1; --warps) {
             const int smem = pmb::fk_tracks_geom(fr, warps, n_joints, n_items, n_boxes).block_bytes;
             if (smem > dp.smem_optin || blocks * (smem + 1024) > dp.smem_sm) continue;
             if (blocks * warps > warps_cap) continue;
@@ -195,9 +195,9 @@ inline FkTracksShape fk_tracks_shape(int fr, int n_joints, int n_items, int n_bo
     return best;
 }
 
-template <int U, int NB>
+template <int U, int NB, int UL>
 int launch_fk_tracks_cfg(const FkArgs &a, const DeviceProps &dp, const FkTracksShape &sh, const pmb::TrackProgram &tp, int n_steps) {
-    auto kernel = pmb::fk_tracks_kernel<U, NB>;
+    auto kernel = pmb::fk_tracks_kernel<U, NB, UL>;
     int per_sm = 0, rc = kernel_fit(kernel, dp, sh.warps * 32, sh.smem, per_sm);
     if (rc) return rc;
     if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk track kernel does not fit on an SM (%d bytes of shared memory)", sh.smem);
@@ -206,10 +206,11 @@ int launch_fk_tracks_cfg(const FkArgs &a, const DeviceProps &dp, const FkTracksS
     if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk, sh.fr))) return rc;
     const long long tiles = (a.n_frames + sh.fr - 1) / sh.fr;
     const long long blocks = std::min<long long>((tiles + sh.warps - 1) / sh.warps, static_cast<long long>(per_sm) * dp.sm_count);
-    note_variant("fk_tracks_kernel<U=%d,NB=%d> FR=%d steps=%d grid=%lld x %d warps (%d warps/SM) smem=%d", U, NB, sh.fr, n_steps, blocks,
-                 sh.warps, per_sm * sh.warps, sh.smem);
+    note_variant("fk_tracks_kernel<U=%d,NB=%d,UL=%d> FR=%d steps=%d grid=%lld x %d warps (%d warps/SM) smem=%d", U, NB, UL, sh.fr,
+                 n_steps, blocks, sh.warps, per_sm * sh.warps, sh.smem);
     kernel<<<static_cast<unsigned>(blocks), sh.warps * 32, sh.smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos, a.rout, a.n_frames,
-                                                                              a.n_joints, n_steps, sh.fr, tp);
+                                                                              a.n_joints, n_steps, sh.fr,
+                                                                              knob(K_FK_L2_PREFETCH, 0) ? a.rot : nullptr, tp);
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;
 }
@@ -220,19 +221,23 @@ bool try_fk_tracks(const FkArgs &a, const DeviceProps &dp, int &rc) {
     const int force = knob(K_FK_TRACKS, -1);
     if (force == 0) return false;
     if (force != 1) return false;  // not part of the default policy yet
-    const int U = knob(K_FK_U, 2), NB = knob(K_FK_NB, 3);
+    const int U = knob(K_FK_U, 2), NB = knob(K_FK_NB, 3), UL = knob(K_FK_UL, 1);
+    if (UL != 1 && UL != 2) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_UL must be 1 or 2"); return true; }
     const pmb::TrackProgram *tp = nullptr;
     int n_steps = 0;
-    if ((rc = track_program(a.parents_host, a.n_joints, U, pmb::kChunk, tp, n_steps))) return true;
-    if (n_steps == 0) { rc = fail(PMB_ERR_SHAPE, "track schedule with %d tracks does not fit", U); return true; }
-    const int fr = knob(K_FK_FR, 10);
-    const FkTracksShape sh = fk_tracks_shape(fr, a.n_joints, n_steps * U, NB, knob(K_FK_WARPS_PER_SM, 16), dp);
+    if ((rc = track_program(a.parents_host, a.n_joints, U * UL, pmb::kChunk, tp, n_steps))) return true;
+    if (n_steps == 0) { rc = fail(PMB_ERR_SHAPE, "track schedule with %d tracks does not fit", U * UL); return true; }
+    const int fr = knob(K_FK_FR, UL == 2 ? 5 : 10);
+    if (fr < 1 || 3 * fr * UL > 32) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_FR=%d does not fit %d lane group(s)", fr, UL); return true; }
+    const FkTracksShape sh = fk_tracks_shape(fr, a.n_joints, n_steps * U * UL, NB, knob(K_FK_WARPS_PER_SM, 16), dp);
     if (sh.fr == 0) { rc = fail(PMB_ERR_SHAPE, "fk track kernel: %d joints do not fit in shared memory", a.n_joints); return true; }
-#define PMB_TRACKS_CASE(u, nb) \
-    if (U == u && NB == nb) { rc = launch_fk_tracks_cfg<u, nb>(a, dp, sh, *tp, n_steps); return true; }
-    PMB_TRACKS_CASE(1, 2) PMB_TRACKS_CASE(1, 3) PMB_TRACKS_CASE(1, 4) PMB_TRACKS_CASE(2, 2) PMB_TRACKS_CASE(2, 3) PMB_TRACKS_CASE(2, 4)
+#define PMB_TRACKS_CASE(u, nb, ul) \
+    if (U == u && NB == nb && UL == ul) { rc = launch_fk_tracks_cfg<u, nb, ul>(a, dp, sh, *tp, n_steps); return true; }
+    PMB_TRACKS_CASE(1, 2, 1) PMB_TRACKS_CASE(1, 3, 1) PMB_TRACKS_CASE(2, 2, 1) PMB_TRACKS_CASE(2, 3, 1) PMB_TRACKS_CASE(2, 4, 1)
+    PMB_TRACKS_CASE(1, 2, 2) PMB_TRACKS_CASE(1, 3, 2) PMB_TRACKS_CASE(1, 4, 2) PMB_TRACKS_CASE(1, 5, 2) PMB_TRACKS_CASE(1, 6, 2)
+    PMB_TRACKS_CASE(2, 4, 2)
 #undef PMB_TRACKS_CASE
-    rc = fail(PMB_ERR_SHAPE, "PMB_FK_U=%d / PMB_FK_NB=%d select no available variant", U, NB);
+    rc = fail(PMB_ERR_SHAPE, "PMB_FK_U=%d / PMB_FK_NB=%d / PMB_FK_UL=%d select no available variant", U, NB, UL);
     return true;
 }
 

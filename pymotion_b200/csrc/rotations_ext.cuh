@@ -346,4 +346,57 @@ unroll_apply_chunk_kernel(const float4 *__restrict__ x, int w4, long long n_step
     }
 }
 
+// ---- BVH.get_data producer chain, fused (io/bvh.py:352-359) -----------------------------------------------------
+// rots = quat.normalize(quat.unroll(quat.from_euler(np.radians(rotations), order tiled over the frames), axis=0))
+// as the same chunked scan as `unroll`, with the quaternion of an entry COMPUTED from its Euler angles where it is
+// needed (never stored un-unrolled) and the final normalisation applied by the pass that writes:
+//   bvh_local   per (chunk of kUnrollChunk frames, joint): quaternions from Euler angles on the fly, running sign state
+//               -> local[T][J], state of the chunk -> agg[chunks][J]
+//   unroll_chunks (above) exclusive scan of agg over the chunks
+//   bvh_apply   per (frame, joint): quaternion again, sign from combine(agg, local), q / (|q| + 1e-8), store
+// 12 + 12 bytes of angles read, 16 written, 2 of state per entry: 42 bytes against 110 for the three separate ops
+// (from_euler 28, unroll 50, normalize 32); 28 is the algorithmic minimum.
+__device__ __forceinline__ Quat<float> q_from_euler_deg(const float *euler_deg, long long i, int o0, int o1, int o2) {
+    constexpr float kRad = 0.017453292519943295f;  // np.radians: x * pi / 180
+    const Vec3<float> e = ldv(euler_deg, i);
+    return q_mul(q_about_axis(e.x * kRad, o0), q_mul(q_about_axis(e.y * kRad, o1), q_about_axis(e.z * kRad, o2)));
+}
+__global__ void bvh_local_kernel(const float *__restrict__ euler_deg, const uint8_t *__restrict__ order, long long n_steps,
+                                 long long n_cols, long long n_chunks, uint8_t *__restrict__ local, uint8_t *__restrict__ agg) {
+    const long long id = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (id >= n_chunks * n_cols) return;
+    const long long c = id / n_cols, m = id - c * n_cols, t0 = c * kUnrollChunk;
+    const long long t1 = min(t0 + kUnrollChunk, n_steps);
+    int o0, o1, o2;
+    order_unpack(order[m], o0, o1, o2);
+    Quat<float> prev = t0 > 0 ? q_from_euler_deg(euler_deg, (t0 - 1) * n_cols + m, o0, o1, o2) : Quat<float>{0.f, 0.f, 0.f, 0.f};
+    uint8_t state = 0;
+    for (long long t = t0; t < t1; ++t) {
+        const Quat<float> cur = q_from_euler_deg(euler_deg, t * n_cols + m, o0, o1, o2);
+        uint8_t el = 2;  // the first entry keeps its cover
+        if (t > 0) {
+            const float d = dot4_np(cur, prev);  // np.sum(r[i] * r[i - 1], axis=-1): separate roundings
+            el = d < 0.f ? 1 : (d > 0.f ? 0 : 2);
+        }
+        state = unroll_combine(state, el);
+        local[t * n_cols + m] = state;
+        prev = cur;
+    }
+    agg[c * n_cols + m] = state;
+}
+__global__ void bvh_apply_kernel(const float *__restrict__ euler_deg, const uint8_t *__restrict__ order, long long n_steps,
+                                 long long n_cols, const uint8_t *__restrict__ local, const uint8_t *__restrict__ agg,
+                                 float4 *__restrict__ o) {
+    const long long n = n_steps * n_cols;
+    PMB_GRID_STRIDE(i, n) {
+        const long long t = i / n_cols, m = i - t * n_cols;
+        int o0, o1, o2;
+        order_unpack(order[m], o0, o1, o2);
+        const uint8_t s = unroll_combine(agg[(t / kUnrollChunk) * n_cols + m], local[i]);
+        Quat<float> q = q_from_euler_deg(euler_deg, i, o0, o1, o2);
+        if (s & 1) q = {-q.w, -q.x, -q.y, -q.z};
+        stq(o, i, q_normalize(q, 1e-8f));
+    }
+}
+
 }  // namespace pmb

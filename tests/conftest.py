@@ -45,6 +45,11 @@ def golden_misc():
     return dict(np.load(os.path.join(GOLDEN, "misc.npz")))
 
 
+@pytest.fixture(scope="session")
+def golden_bvh():
+    return dict(np.load(os.path.join(GOLDEN, "bvh.npz")))
+
+
 @pytest.fixture
 def set_knobs(monkeypatch):
     """Force kernel variants for one test: the library honours its PMB_* experiment knobs only under

@@ -109,3 +109,41 @@ def test_vector_normalize_vec3_paths(mods, set_knobs, n):
     shifted = vec.normalize(t[1:])  # data pointer 12 bytes past a 16-byte boundary: generic kernel
     assert isinstance(shifted, torch.Tensor)
     assert_array_equal(shifted.cpu().numpy(), fast[1:])
+
+
+@pytest.mark.parametrize("tag", ["small", "body22", "long"])
+def test_bvh_get_data_fused(golden_bvh, tag):
+    """io.bvh.rotations_to_quat / get_data: the fused from_euler -> unroll -> normalize scan against the output of the
+    real BVH.get_data (fixtures) -- same rotations everywhere, and the SAME cover (sign) wherever the unroll decision
+    of the float64 reference is not within fp32 rounding of a tie (consecutive frames more than ~90 degrees apart in
+    quaternion space)."""
+    import pymotion_b200.io.bvh as bvh
+    import pymotion_b200.rotations.quat as quat
+
+    g = golden_bvh
+    rot_deg, order, want = g[f"{tag}/rotations_deg"].astype(np.float32), g[f"{tag}/rot_order"], g[f"{tag}/rots"]
+    got = bvh.rotations_to_quat(rot_deg, order)
+    assert isinstance(got, np.ndarray) and got.dtype == np.float32 and got.shape == want.shape
+    assert_allclose(np.linalg.norm(got, axis=-1), 1.0, atol=1e-6)
+    dots = np.sum(got * want, axis=-1)
+    # degrees up to a few turns in fp32: the angle itself carries ~1e-5 rad of rounding before any arithmetic
+    assert_allclose(np.abs(dots), 1.0, atol=2e-6)
+    # the reference's own decisions: |dot| of consecutive reference frames below 1e-3 is a coin toss in fp32
+    margin = np.abs(np.sum(want[1:] * want[:-1], axis=-1))
+    decided = np.concatenate([np.ones((1,) + margin.shape[1:], bool), np.minimum.accumulate(margin > 1e-3, axis=0)])
+    assert (dots[decided] > 0).all()
+    assert decided.mean() > 0.9
+    # sign-continuous along the frame axis, like the reference's output
+    assert (np.sum(got[1:] * got[:-1], axis=-1) >= -1e-6).all()
+    # the same chain as three separate ops of this package (from_euler -> unroll -> normalize) agrees bit for bit on
+    # the cover and to rounding on the values
+    sep = quat.normalize(quat.unroll(quat.from_euler(np.radians(rot_deg).astype(np.float32), np.tile(order, (rot_deg.shape[0], 1, 1))), 0))
+    assert_allclose(got, sep, rtol=0, atol=2e-6)
+    # drop-in for BVH.get_data given the reference's data dictionary
+    data = {"rotations": rot_deg, "rot_order": order, "positions": np.zeros(rot_deg.shape, np.float32), "parents": np.arange(3),
+            "offsets": np.zeros((3, 3)), "end_sites": np.zeros((0, 3)), "end_sites_parents": np.zeros(0, int)}
+    rots, pos, parents, offsets, end_sites, end_sites_parents = bvh.get_data(data)
+    assert_array_equal(rots, got)
+    assert pos is data["positions"] and parents is data["parents"]
+    t = bvh.rotations_to_quat(torch.from_numpy(rot_deg).cuda(), order)
+    assert t.is_cuda and torch.equal(t.cpu(), torch.from_numpy(got))

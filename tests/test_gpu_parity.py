@@ -616,8 +616,11 @@ def test_fk_lane_kernel(sk, set_knobs, knobs, name, n_frames):
     {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_NB": "3", "PMB_FK_FR": "8"},
     {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_NB": "2"},
     {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_NB": "4", "PMB_FK_FR": "8", "PMB_FK_WARPS_PER_SM": "1"},  # many tiles per warp
-    {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_NB": "4", "PMB_FK_WARPS_PER_SM": "2"},
     {"PMB_FK_TRACKS": "1", "PMB_FK_U": "2", "PMB_FK_NB": "3", "PMB_FK_WARPS_PER_SM": "3"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "1", "PMB_FK_NB": "3"},   # two lane groups, tiles of 5 frames
+    {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "1", "PMB_FK_NB": "2", "PMB_FK_WARPS_PER_SM": "1"},
+    {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "2", "PMB_FK_NB": "4"},   # four tracks
+    {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "1", "PMB_FK_NB": "4", "PMB_FK_FR": "4"},
 ])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
                                            ("body32", 5_009), ("body22", 7), ("body16", 1), ("deep65", 29)])
@@ -648,8 +651,9 @@ def test_fk_track_kernel_random_trees(sk, set_knobs, seed):
     n_frames = int(rng.integers(1, 3000))
     rot, gp, off = synth_numpy(n_frames, par, seed=seed)
     want_pos, want_rotm = orc.fk(rot, gp, off, par)
-    for u, nb in ((1, 2), (2, 3), (2, 4)):
-        set_knobs({"PMB_FK_TRACKS": "1", "PMB_FK_U": str(u), "PMB_FK_NB": str(nb), "PMB_FK_FR": "8" if n_joints > 150 else "10"})
+    for u, nb, ul in ((1, 2, 1), (2, 3, 1), (1, 3, 2), (2, 4, 2)):
+        set_knobs({"PMB_FK_TRACKS": "1", "PMB_FK_U": str(u), "PMB_FK_NB": str(nb), "PMB_FK_UL": str(ul),
+                   "PMB_FK_FR": "5" if ul == 2 else ("8" if n_joints > 150 else "10")})
         pos, rotm = sk.fk(rot, gp, off, par)
         assert "fk_tracks_kernel" in _lib.load().pmb_last_variant().decode()
         assert_allclose(pos, want_pos, rtol=2e-5, atol=2e-5)

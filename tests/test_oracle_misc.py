@@ -56,3 +56,14 @@ def test_vector_normalize(golden_misc, tag):
     same(orc.vec_normalize(g[f"{tag}/vec"]), g[f"{tag}/vec_normalize"])
     same(orc.vec_normalize(g[f"{tag}/vec"], eps=1e-3), g[f"{tag}/vec_normalize_eps"])
     same(orc.vec_normalize(g[f"{tag}/vec5"]), g[f"{tag}/vec5_normalize"])
+
+
+@pytest.mark.parametrize("tag", ["small", "body22", "long"])
+def test_bvh_get_data_rotations(golden_bvh, tag):
+    """The numeric chain of BVH.get_data (io/bvh.py:352-359) restated, against outputs of the REAL BVH class on an
+    in-memory data dictionary (gen_golden.py::gen_bvh): bit-exact, unit length, sign-continuous along the frames."""
+    g = golden_bvh
+    got = orc.bvh_get_data_rotations(g[f"{tag}/rotations_deg"], g[f"{tag}/rot_order"])
+    same(got, g[f"{tag}/rots"])
+    assert_allclose(np.linalg.norm(got, axis=-1), 1.0, atol=1e-7)
+    assert (np.sum(got[1:] * got[:-1], axis=-1) >= 0).all()

@@ -215,13 +215,32 @@ int launch_fk_tracks_cfg(const FkArgs &a, const DeviceProps &dp, const FkTracksS
     return PMB_OK;
 }
 
-// PMB_FK_TRACKS = 0 / 1 forces; PMB_FK_U = 1 | 2 tracks, PMB_FK_NB = 2 .. 4 boxes in flight, PMB_FK_FR = 8 | 10,
-// PMB_FK_WARPS_PER_SM caps the resident warps.
-bool try_fk_tracks(const FkArgs &a, const DeviceProps &dp, int &rc) {
+// Worst-case number of lanes of one lane group whose stage stores fall into the same shared-memory bank: the frames of a
+// tile are 9J words apart (same rule as fk_lanes_bank_degree, for the FR frames of a group).
+inline int fk_tracks_bank_degree(int fr, int n_joints) {
+    int count[32] = {0}, worst = 0;
+    for (int f = 0; f < fr; ++f) worst = std::max(worst, ++count[(f * 9 * n_joints) & 31]);
+    return worst;
+}
+
+// Default policy (measured on B200, profiles/r2_sweep_tracks_*.jsonl): skeletons too large for four row teams per SM take
+// the track kernel with two lane groups (tiles of 5 frames, one track per lane) --
+//     2M x 40: 0.880 ms against 0.907 lanes;  4M x 52: 2.331 against 2.504;  4M x 65: 3.090 against 3.442
+// -- unless the frames of a group collide in 3 or more banks (J = 32, 48, 64, ...), which stay with the padded stage of
+// the thread-per-frame kernel.  Four boxes in flight from 48 joints up (52: 2.360 -> 2.331, 65: 3.220 -> 3.090 against
+// three), three below (40: 0.880 against 0.892).
+// PMB_FK_TRACKS = 0 / 1 forces; PMB_FK_U = 1 | 2 tracks per lane, PMB_FK_UL = 1 | 2 lane groups, PMB_FK_NB = 2 .. 6 boxes in
+// flight, PMB_FK_FR frames per tile, PMB_FK_WARPS_PER_SM caps the resident warps.
+bool try_fk_tracks(const FkArgs &a, const DeviceProps &dp, int &rc, bool rows_preferred) {
     const int force = knob(K_FK_TRACKS, -1);
     if (force == 0) return false;
-    if (force != 1) return false;  // not part of the default policy yet
-    const int U = knob(K_FK_U, 2), NB = knob(K_FK_NB, 3), UL = knob(K_FK_UL, 1);
+    if (force != 1) {
+        if (knob_set(K_FK_GROUP) || knob_set(K_FK_ROWS) || knob_set(K_FK_LANES) || knob_set(K_FK_WARPS)) return false;  // another kernel is forced
+        if (rows_preferred || a.n_joints <= 30) return false;
+        if (fk_tracks_bank_degree(5, a.n_joints) >= 3) return false;
+    }
+    const int U = knob(K_FK_U, force == 1 ? 2 : 1), UL = knob(K_FK_UL, force == 1 ? 1 : 2);
+    const int NB = knob(K_FK_NB, force == 1 ? 3 : (a.n_joints >= 48 ? 4 : 3));
     if (UL != 1 && UL != 2) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_UL must be 1 or 2"); return true; }
     const pmb::TrackProgram *tp = nullptr;
     int n_steps = 0;
@@ -230,7 +249,11 @@ bool try_fk_tracks(const FkArgs &a, const DeviceProps &dp, int &rc) {
     const int fr = knob(K_FK_FR, UL == 2 ? 5 : 10);
     if (fr < 1 || 3 * fr * UL > 32) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_FR=%d does not fit %d lane group(s)", fr, UL); return true; }
     const FkTracksShape sh = fk_tracks_shape(fr, a.n_joints, n_steps * U * UL, NB, knob(K_FK_WARPS_PER_SM, 16), dp);
-    if (sh.fr == 0) { rc = fail(PMB_ERR_SHAPE, "fk track kernel: %d joints do not fit in shared memory", a.n_joints); return true; }
+    if (sh.fr == 0) {
+        if (force != 1) return false;  // too many joints for a tile of 5 frames: the older kernels decide
+        rc = fail(PMB_ERR_SHAPE, "fk track kernel: %d joints do not fit in shared memory", a.n_joints);
+        return true;
+    }
 #define PMB_TRACKS_CASE(u, nb, ul) \
     if (U == u && NB == nb && UL == ul) { rc = launch_fk_tracks_cfg<u, nb, ul>(a, dp, sh, *tp, n_steps); return true; }
     PMB_TRACKS_CASE(1, 2, 1) PMB_TRACKS_CASE(1, 3, 1) PMB_TRACKS_CASE(2, 2, 1) PMB_TRACKS_CASE(2, 3, 1) PMB_TRACKS_CASE(2, 4, 1)
@@ -244,8 +267,8 @@ bool try_fk_tracks(const FkArgs &a, const DeviceProps &dp, int &rc) {
 // Which fk kernel (shared offsets, matrices out) -- measured on B200, DESIGN.md section 4:
 //   row-team kernel      skeletons small enough for >= 4 teams per SM (J <= 30) with J not a multiple of 4
 //                        (1M x 22: 0.2316 ms against 0.2415 ms thread-per-frame, 0.2326 ms lanes);
-//   lane kernel          everything larger (2M x 40: 5.6 TB/s against 5.15; 4M x 52: 5.0 against 4.76; 4M x 65:
-//                        4.4, as the row kernel, against 3.9), unless
+//   track kernel         larger skeletons (try_fk_tracks above);
+//   lane kernel          what is left (small J that is a multiple of 4 but not of 8), unless
 //   thread-per-frame     the dense stage of the lane kernel would put >= 4 frames in one bank (J = 16, 32, 48,
 //                        64, ...: 2.0 TB/s at J = 32 against 5.6), per-frame offsets, or a forced variant.
 // Bank conflicts of the row-team kernel (lane = frame, 32 lanes 9J words apart): J odd: none; J = 2 (mod 4):
@@ -392,8 +415,8 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
              static_cast<cudaStream_t>(stream)};
     if (ostride == 0 && !quat_out) {
         int rrc = PMB_OK;
-        if (try_fk_tracks(a, dp, rrc)) return rrc;
         const bool rows_first = fk_rows_preferred(a, dp) && knob(K_FK_ROWS, -1) != 0;
+        if (try_fk_tracks(a, dp, rrc, rows_first)) return rrc;
         if (try_fk_lanes(a, dp, rrc, rows_first || knob(K_FK_ROWS, -1) == 1)) return rrc;
         if (try_fk_rows(a, dp, rrc)) return rrc;
     }

@@ -27,9 +27,12 @@ struct ChildTable {
 //       roll = from_to_axis(off_g, G_j^-1 (P_g - P_j), G_j^-1 normalize(P_c - P_j));   rot_j = rot_j (x) roll
 // Joints without children keep the identity.  Global rotations are composed from NORMALISED local rotations,
 // as the reference's fk does (from_to / from_to_axis results are unit only up to their eps terms).
-// Conditioning: the roll corrections amplify rounding by up to ~1e3 on joints with several children (the
-// reference's own float32 torch twin differs from its NumPy path by 1e-4 .. 2e-3 there, 1e-7 in the median);
-// the parity tests for this op use matching tolerances.
+// Conditioning: the further children of a joint are almost aligned once the first one is, so the roll corrections
+// are SMALL angles: the half-angle sine comes from |a x b| / (2 w) (q_from_to_axis_stable), not from the reference's
+// sqrt((1 - dot) / 2), which cancels in fp32.  What remains against the float64 reference are its np.isclose snaps to
+// the identity (|angle| < 4.5e-3: a frame on the other side of the threshold differs by up to 2.2e-3) and the sign of
+// a roll whose axis is perpendicular to the correction; the reference's own float32 torch twin differs from its
+// NumPy path by up to 2.3e-3 for the same reasons.
 // ---------------------------------------------------------------------------------------------------
 // (A tile-staged variant -- one warp per block, positions and rotations through shared memory with coalesced
 // 16-byte accesses -- was measured SLOWER: 0.54 ms against 0.36 ms at 1M x 22.  The op is bound by the IEEE
@@ -40,10 +43,13 @@ from_root_positions_kernel(const float *__restrict__ pos, const float *__restric
                            long long n_frames, int n_joints, int n_slots, const __grid_constant__ JointProgram prog,
                            const __grid_constant__ ChildTable kids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *tab = reinterpret_cast<float4 *>(smem_raw);                 // [J] offsets
+    float4 *tab = reinterpret_cast<float4 *>(smem_raw);                 // [J] rest directions: offsets / (|offsets| + 1e-8)
     float4 *slots = tab + n_joints;                                      // [n_slots][THREADS] global quaternions
-    for (int j = threadIdx.x; j < n_joints; j += THREADS)
-        tab[j] = make_float4(offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2], 0.f);
+    for (int j = threadIdx.x; j < n_joints; j += THREADS) {
+        // from_to / from_to_axis normalise their first argument (quat.py:541, :616): the same value for every frame
+        const Vec3<float> d = v_normalize(Vec3<float>{offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2]}, 1e-8f);
+        tab[j] = make_float4(d.x, d.y, d.z, 0.f);
+    }
     __syncthreads();
     const long long f = blockIdx.x * static_cast<long long>(THREADS) + threadIdx.x;
     if (f >= n_frames) return;
@@ -72,7 +78,7 @@ from_root_positions_kernel(const float *__restrict__ pos, const float *__restric
             const Vec3<float> pc = point(c);
             const Vec3<float> to_c{pc.x - pj.x, pc.y - pj.y, pc.z - pj.z};
             const float4 oc = tab[c];
-            rot = q_from_to(Vec3<float>{oc.x, oc.y, oc.z}, q_rotate(q_conj(G), to_c), true);
+            rot = q_from_to_stable(Vec3<float>{oc.x, oc.y, oc.z}, q_rotate(q_conj(G), to_c));
             for (int k = k0 + 1; k < k1; ++k) {
                 const int g = kids.child[k];
                 const Quat<float> inv = q_conj(q_mul(G, q_normalize(rot, 1e-8f)));  // fk normalises local rotations (quat.py:411)
@@ -80,7 +86,7 @@ from_root_positions_kernel(const float *__restrict__ pos, const float *__restric
                 const float4 og = tab[g];
                 const Vec3<float> pred = q_rotate(inv, Vec3<float>{pg.x - pj.x, pg.y - pj.y, pg.z - pj.z});
                 const Vec3<float> axis = q_rotate(inv, v_normalize(to_c, 1e-8f));
-                rot = q_mul(rot, q_from_to_axis(Vec3<float>{og.x, og.y, og.z}, pred, axis, true));
+                rot = q_mul(rot, q_from_to_axis_stable(Vec3<float>{og.x, og.y, og.z}, pred, axis));
             }
         }
         R[j] = make_float4(rot.w, rot.x, rot.y, rot.z);

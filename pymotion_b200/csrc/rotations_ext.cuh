@@ -171,6 +171,51 @@ __device__ __forceinline__ Quat<float> q_from_to_axis(Vec3<float> a, Vec3<float>
     if (np_isclose(dot, -1.f)) r = {0.f, u.x, u.y, u.z};
     return r;
 }
+// The same two rotations for from_root_positions (ik_kernels.cuh), where the angle is usually SMALL (a rigid skeleton's
+// further children are almost aligned once the first one is) and the result feeds a chain of products: the reference's
+// float64 sqrt((1 - dot) / 2) loses everything to cancellation in fp32 there (1 - dot ~ 1e-6 carries 6 % of rounding).
+// sin(theta) = |a x b| = 2 s w gives the small one of (w, s) from the well-conditioned one: same values as the
+// reference's formulas, conditioned for fp32.  `a` is already normalised (a rest offset, normalised once per block).
+__device__ __forceinline__ void half_angle_stable(float dot, float ncr, float &w, float &s) {
+    if (dot >= 0.f) {
+        w = sqrtf((1.f + dot) * 0.5f);
+        s = ncr / (w + w);
+    } else {
+        s = sqrtf((1.f - dot) * 0.5f);
+        w = ncr / (s + s);
+    }
+}
+__device__ __forceinline__ Quat<float> q_from_to_stable(const Vec3<float> &a, Vec3<float> b) {
+    b = v_normalize(b, 1e-8f);
+    const Vec3<float> cr = cross3(a, b);
+    const float dot = dot3_np(a, b);
+    const float ncr = sqrtf(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z);
+    float w, s;
+    half_angle_stable(dot, ncr, w, s);
+    const float k = s / (ncr + 1e-8f);  // normalize(cross) * s
+    Quat<float> r{w, cr.x * k, cr.y * k, cr.z * k};
+    if (np_isclose(dot, 1.f)) r = {1.f, 0.f, 0.f, 0.f};
+    if (np_isclose(dot, -1.f)) {
+        const Vec3<float> e = np_isclose(fabsf(a.x), 1.f) ? Vec3<float>{0.f, 1.f, 0.f} : Vec3<float>{1.f, 0.f, 0.f};
+        const Vec3<float> h = v_normalize(cross3(a, e), 1e-8f);
+        r = {0.f, h.x, h.y, h.z};
+    }
+    return r;
+}
+__device__ __forceinline__ Quat<float> q_from_to_axis_stable(const Vec3<float> &a, Vec3<float> b, const Vec3<float> &u) {
+    b = v_normalize(b, 1e-8f);
+    const Vec3<float> cr = cross3(a, b);
+    const float dot = dot3_np(a, b);
+    const float ncr = sqrtf(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z);
+    float w, s;
+    half_angle_stable(dot, ncr, w, s);
+    const float side = dot3_np(cr, u);
+    s *= side > 0.f ? 1.f : (side < 0.f ? -1.f : side);  // np.sign (keeps 0 and nan)
+    Quat<float> r{w, u.x * s, u.y * s, u.z * s};
+    if (np_isclose(dot, 1.f)) r = {1.f, 0.f, 0.f, 0.f};
+    if (np_isclose(dot, -1.f)) r = {0.f, u.x, u.y, u.z};
+    return r;
+}
 __global__ void quat_from_to_kernel(const float *v1, const float *v2, const float *axis, int normalize_input, float4 *o,
                                     long long n) {
     PMB_GRID_STRIDE(i, n) {

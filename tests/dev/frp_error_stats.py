@@ -20,8 +20,9 @@ from oracle import pymotion_oracle as orc  # noqa: E402
 from pymotion_b200.ops import skeleton as sk  # noqa: E402
 from pymotion_b200.topologies import parents_of, synth_numpy  # noqa: E402
 
-sizes = [int(x) for x in sys.argv[1:4]] or [20000, 6000, 4000]
-for name, n in zip(("body22", "smplh52", "deep65"), sizes):
+sizes = [int(x) for x in sys.argv[1:]] or [20000, 6000, 4000]
+names = ("body22", "smplh52", "deep65") * (len(sizes) // 3)
+for name, n in zip(names, sizes):
     par = parents_of(name)
     rot, gp, off = synth_numpy(n, par, seed=n)
     pos, _ = orc.fk(rot, gp, off, par)

@@ -49,6 +49,21 @@ def main():
                "c_abi_us_sync": round(timeit(c_call, n, True), 2), "c_abi_us_pipelined": round(timeit(c_call, n, False), 2),
                "python_us_sync": round(timeit(lambda: sk.fk(rot, gp, off, par), n, True), 2),
                "python_us_pipelined": round(timeit(lambda: sk.fk(rot, gp, off, par), n, False), 2)}
+        if frames == 1000:  # the other two ops of the path and a large skeleton (track kernel: schedule cache, TMA map cache)
+            dq = torch.empty((frames, 22, 8), device=dev)
+            rots = torch.empty((frames, 22, 4), device=dev)
+            off0 = np.zeros(3, dtype=np.float32)
+            out["to_dq_c_abi_us_pipelined"] = round(timeit(lambda: lib.pmb_to_root_dual_quat_f32(
+                rot.data_ptr(), gp.data_ptr(), 3, par.ctypes.data, off.data_ptr(), off0.ctypes.data, frames, 22, dq.data_ptr(), st), n, False), 2)
+            out["from_dq_c_abi_us_pipelined"] = round(timeit(lambda: lib.pmb_from_root_dual_quat_f32(
+                dq.data_ptr(), par.ctypes.data, frames, 22, pos.data_ptr(), rots.data_ptr(), st), n, False), 2)
+            par65 = parents_of("deep65")
+            rot65, gp65, off65 = synth_torch(frames, par65, dev, seed=2)
+            pos65 = torch.empty((frames, 65, 3), device=dev)
+            rotm65 = torch.empty((frames, 65, 3, 3), device=dev)
+            out["fk65_c_abi_us_pipelined"] = round(timeit(lambda: lib.pmb_fk_f32(
+                rot65.data_ptr(), gp65.data_ptr(), 3, off65.data_ptr(), 0, par65.ctypes.data, frames, 65, pos65.data_ptr(),
+                rotm65.data_ptr(), st), n, False), 2)
         if frames <= 1000:
             r, g, o = rot.cpu().numpy(), gp.cpu().numpy(), off.cpu().numpy()
             t0 = time.perf_counter()

@@ -20,7 +20,20 @@ from pymotion_b200.topologies import parents_of, synth_numpy  # noqa: E402
 
 KNOBS = [{}, {"PMB_FK_ROWS": "1"}, {"PMB_FK_ROWS": "1", "PMB_FK_STAGES": "3", "PMB_FK_BLOCKS_PER_SM": "1"},
          {"PMB_FK_LANES": "1"}, {"PMB_FK_LANES": "1", "PMB_FK_NB": "3", "PMB_FK_BLOCKS_PER_SM": "1", "PMB_FK_WARPS": "1"},
-         {"PMB_FK_LANES": "0", "PMB_FK_ROWS": "0"}, {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "4"}]
+         {"PMB_FK_LANES": "0", "PMB_FK_ROWS": "0", "PMB_FK_TRACKS": "0"}, {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "4"},
+         {"PMB_FK_TRACKS": "1"}, {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "1", "PMB_FK_NB": "4", "PMB_FK_WARPS_PER_SM": "2"},
+         {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "2", "PMB_FK_NB": "4"}]
+
+
+def set_knobs(knobs):
+    from pymotion_b200 import _lib
+
+    for k in [k for k in os.environ if k.startswith("PMB_")]:
+        os.environ.pop(k)
+    os.environ.update(knobs)
+    if knobs:
+        os.environ["PMB_EXPERIMENT"] = "1"
+    _lib.load().pmb_reload_knobs()
 
 
 def main():
@@ -39,9 +52,7 @@ def main():
         want_pos, want_rotm = orc.fk(rot, gp, off, par)
         scale = max(1.0, float(np.abs(want_pos).max()))  # deep chains accumulate rounding
         for knobs in KNOBS:
-            for k in [k for k in os.environ if k.startswith("PMB_")]:
-                os.environ.pop(k)
-            os.environ.update(knobs)
+            set_knobs(knobs)
             try:
                 pos, rotm = sk.fk(rot, gp, off, par)
             except Exception as e:  # a FORCED variant may not fit the largest skeletons; the default policy must
@@ -51,8 +62,7 @@ def main():
             np.testing.assert_allclose(pos, want_pos, rtol=1e-5, atol=1e-5 * scale)
             np.testing.assert_allclose(rotm, want_rotm, rtol=1e-5, atol=5e-5)
             n_checked += 1
-        for k in [k for k in os.environ if k.startswith("PMB_")]:
-            os.environ.pop(k)
+        set_knobs({})
         p2, gq = sk.fk_quat(rot, gp, off, par)
         np.testing.assert_allclose(p2, want_pos, rtol=1e-5, atol=1e-5 * scale)
         d = sk.to_root_dual_quat(rot, gp, par, off)
@@ -70,6 +80,17 @@ def main():
         dq.is_unit(d)
         quat.to_matrix(rot)
         quat.slerp(rot, rot[::-1].copy(), 0.3)
+        if len(par) <= 65:
+            import pymotion_b200.io.bvh as bvh
+
+            order = np.array([list("zyx")] * len(par))
+            bvh.rotations_to_quat(np.degrees(rot[..., 1:]).astype(np.float32), order)
+            # large host batches take the chunked pipeline; force it on this small one through fk_host
+            hp, hr = sk.fk_host(rot, gp, off, par, chunk_frames=64)
+            np.testing.assert_allclose(hp, want_pos, rtol=1e-5, atol=1e-5 * scale)
+            hp, hq = sk.fk_quat_host(rot, gp, off, par, chunk_frames=64)
+            np.testing.assert_allclose(hp, want_pos, rtol=1e-5, atol=1e-5 * scale)
+            n_checked += 3
         n_checked += 12
     print(f"sanitize_run ok: {n_checked} kernel-family launches checked")
 

@@ -3,13 +3,19 @@ reference and against the oracle.  Needs a B200: -m gpu.
 
 Tolerances.  mirror 'all' / 'symmetry' are fk + element-wise work: 1e-5 like the hot path (compared up to the
 sign of each quaternion: the sign comes out of quat.from_matrix's branch selection, which a rounding error
-can flip for matrices on a branch boundary -- the rotation is the same).  from_root_positions is
-ill-conditioned on joints with several children (roll corrections): the reference's OWN float32 torch twin
-differs from its NumPy path by up to 1e-4 (22 joints) .. 2.3e-3 (65 joints) with a median of 1e-7 (measured,
-DESIGN.md); the bars below are median <= 1e-6, 99th percentile <= 5e-5, maximum <= 5e-2 (1.3e-2 seen on a
-517-frame 65-joint batch), and the pose rebuilt
-from the rotations must agree with the pose rebuilt from the reference's rotations to 5e-3 (0.04 % of the
-coordinates of a 52-joint batch were off by more than 1e-3, at most 1.6e-3: the same ill-conditioned joints)."""
+can flip for matrices on a branch boundary -- the rotation is the same).  from_root_positions is ill-conditioned BY
+CONSTRUCTION: np.isclose snaps small alignments to the identity (a frame on the other side of the threshold differs by
+up to 2.2e-3 and drags its descendants along), and the roll of a joint with several children has an arbitrary sign when
+its axis is perpendicular to the correction.  "Close enough" is therefore defined by the reference itself: its own
+float32 torch twin against its float64 NumPy path on the SAME batches (tests/golden/ik_twin_envelope.json, written by
+oracle/gen_ik_envelope.py from the real reference).  The kernel must stay inside a small multiple of that envelope at
+every quantile -- median 3x, 99th percentile 2.5x, 99.9th percentile 5x, maximum 8x (single rare events) -- and the pose
+rebuilt from its rotations must match the pose rebuilt from the reference's rotations to 5x the twin's figure.  Measured (B200,
+profiles/r2_frp_error_stats.jsonl): 3001 x 22 median 2e-7 / p99 4.2e-6 / max 1.2e-3 (twin 1.4e-7 / 2.4e-6 / 2.5e-4),
+1000 x 52 5e-7 / 2.4e-5 / 7.5e-3 (twin 2.8e-7 / 1.9e-5 / 7.6e-3), 517 x 65 3.4e-7 / 2.3e-5 / 1.3e-2 (twin 2.3e-7 /
+1.5e-5 / 1.0e-2); the same frames are the outliers of both."""
+import json
+import os
 import warnings
 
 import numpy as np
@@ -47,14 +53,28 @@ def quat_close_up_to_sign(got, want, atol=1e-5, max_flipped=0.02):
     assert (d_flip < d_same).mean() <= max_flipped  # the sign convention is the reference's almost everywhere
 
 
-def check_ik(got, want, positions, par, off):
-    got = np.asarray(got, dtype=np.float64)
-    d = np.abs(got - want)
-    assert np.median(d) <= 1e-6 and np.quantile(d, 0.99) <= 5e-5 and d.max() <= 5e-2, (np.median(d), np.quantile(d, 0.99), d.max())
+ENVELOPE = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ik_twin_envelope.json")))
+
+
+def ik_stats(got, want, par, off):
+    d = np.abs(np.asarray(got, dtype=np.float64) - want).max(axis=-1)
     zero = np.zeros((1, 3))
-    p_got, _ = orc.fk(got, zero, off, par)
-    p_want, _ = orc.fk(want, zero, off, par)
-    assert_allclose(p_got, p_want, atol=5e-3)
+    p_got, _ = orc.fk(np.asarray(got, dtype=np.float64), zero, off.astype(np.float64), par)
+    p_want, _ = orc.fk(want, zero, off.astype(np.float64), par)
+    return {"median": float(np.median(d)), "p99": float(np.quantile(d, 0.99)), "p999": float(np.quantile(d, 0.999)),
+            "max": float(d.max()), "pose_rebuild_max": float(np.abs(p_got - p_want).max())}
+
+
+def check_ik(got, want, positions, par, off, envelope=None):
+    """Small fixtures: absolute bars (median / p99 of a few hundred entries).  Batches with a recorded twin envelope: a
+    small multiple of the reference's own float32 error at every quantile."""
+    st = ik_stats(got, want, par, off)
+    if envelope is None:
+        assert st["median"] <= 1e-6 and st["p99"] <= 5e-5 and st["max"] <= 2e-2 and st["pose_rebuild_max"] <= 3e-3, st
+        return
+    factor = {"median": 3.0, "p99": 2.5, "p999": 5.0, "max": 8.0, "pose_rebuild_max": 5.0}
+    for key, mult in factor.items():
+        assert st[key] <= mult * envelope[key] + 1e-7, (key, st, envelope)
 
 
 @pytest.mark.parametrize("name", SKELS)
@@ -77,7 +97,8 @@ def test_from_root_positions_vs_oracle(sk, name, n_frames):
     rot, gp, off = synth_numpy(n_frames, par, seed=n_frames)
     pos, _ = orc.fk(rot, gp, off, par)
     centred = (pos - pos[:, 0:1]).astype(np.float32)
-    check_ik(sk.from_root_positions(centred, par, off), orc.from_root_positions(centred, par, off), centred, par, off)
+    want = orc.from_root_positions(centred.astype(np.float64), par, off.astype(np.float64))
+    check_ik(sk.from_root_positions(centred, par, off), want, centred, par, off, ENVELOPE[f"{name}/{n_frames}"])
 
 
 @pytest.mark.parametrize("name", SKELS)

@@ -209,6 +209,20 @@ def test_fk_4m_invariants_and_slabs(sk, name):
         assert_allclose(rotm[sl].cpu().numpy(), want_rotm, **TOL)
 
 
+def assert_sign_convention(grot, want_q, rotm):
+    """fk_quat returns the quaternion quat.from_matrix(fk rotmats) returns, SIGN INCLUDED (the cover feeds unroll /
+    interpolation downstream).  The only entries allowed to differ are those where a branch test of from_matrix
+    (quat.py:111-155: m22 < 0, m00 > m11, m00 < -m11) is within float32 rounding of a tie -- measured on B200: 4 of
+    22 M entries at 1M x 22, 4 of 20.8 M at 400k x 52, 0 of 19.5 M at 300k x 65, every one with a tie margin below 1.4e-6
+    (profiles/r2_fkq_sign_stats.jsonl)."""
+    m = np.asarray(rotm, dtype=np.float64)
+    flipped = np.sum(np.asarray(grot, dtype=np.float64) * want_q, axis=-1) < 0
+    m22, m00, m11 = m[..., 2, 2], m[..., 0, 0], m[..., 1, 1]
+    margin = np.minimum(np.abs(m22), np.where(m22 < 0, np.abs(m00 - m11), np.abs(m00 + m11)))
+    assert flipped.mean() <= 1e-4, flipped.mean()
+    assert (margin[flipped] < 1e-5).all(), margin[flipped].max()
+
+
 def test_fk_quat_matches_from_matrix_of_fk(sk, quat, golden_fk):
     g = golden_fk
     for name in SKELS:
@@ -219,8 +233,7 @@ def test_fk_quat_matches_from_matrix_of_fk(sk, quat, golden_fk):
         # same rotation; sign may flip only where the branch test of from_matrix is within rounding of a tie
         dots = np.abs(np.sum(grot * want, axis=-1))
         assert_allclose(dots, 1.0, atol=1e-5)
-        same_sign = np.sum(grot * want, axis=-1) > 0
-        assert same_sign.mean() > 0.99
+        assert_sign_convention(grot, want, g[f"{name}/rotm"])
 
 
 def test_fk_on_side_stream(sk, golden_fk):
@@ -582,7 +595,7 @@ def test_fk_quat_every_variant(sk, set_knobs, knobs, name, n_frames):
     assert_allclose(pos, want_pos, **TOL)
     dots = np.sum(grot * want_q, axis=-1)
     assert_allclose(np.abs(dots), 1.0, atol=1e-5)
-    assert (dots > 0).mean() > 0.999
+    assert_sign_convention(grot, want_q, want_rotm)
     assert_allclose(np.linalg.norm(grot, axis=-1), 1.0, atol=1e-5)
 
 

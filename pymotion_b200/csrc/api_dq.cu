@@ -7,6 +7,7 @@
 
 #include "dq_kernels.cuh"
 #include "host_common.h"
+#include "qtracks_host.h"
 
 using namespace pmbh;
 
@@ -29,6 +30,15 @@ int pmb_to_root_dual_quat_f32(const float *rotations, const float *global_pos, i
     DeviceProps dp;
     if ((rc = device_props(dp))) return rc;
     if (n_frames > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames must be below 2^31 per call");
+    // The quaternion track kernel (qtracks_kernel.cuh) unless it does not apply; PMB_DQ_TRACKS = 0 / 1 forces, and forcing
+    // a flush group of the chain kernel (PMB_DQ_GROUP / PMB_DQ_BLOCKS_PER_SM) selects the chain kernel.
+    const int tracks = knob(K_DQ_TRACKS, (knob_set(K_DQ_GROUP) || knob_set(K_DQ_BLOCKS_PER_SM)) ? 0 : -1);
+    if (tracks != 0) {
+        int trc = PMB_OK;
+        if (launch_qtracks<pmb::kQtDq>(rotations, global_pos, gpos_frame_stride, offsets, parents_host, n_frames, n_joints, dq, nullptr,
+                                       static_cast<cudaStream_t>(stream), dp, tracks == 1, trc))
+            return trc;
+    }
     // Joints per flush.  Dual quaternions are whole 32-byte sectors, so partial flushes cost DRAM little and
     // occupancy matters more than for fk (measured, 1M x 22: whole rows / 4 warps per SM 0.239 ms, 8 joints /
     // 12 warps 0.214 ms, 16 joints / 8 warps 0.186 ms): take the largest group that still lets TWO 4-warp

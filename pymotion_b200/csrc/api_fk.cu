@@ -12,6 +12,7 @@
 #include "fk_rows_kernel.cuh"
 #include "fk_tracks_kernel.cuh"
 #include "host_common.h"
+#include "qtracks_host.h"
 
 using namespace pmbh;
 
@@ -419,6 +420,17 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
         if (try_fk_tracks(a, dp, rrc, rows_first)) return rrc;
         if (try_fk_lanes(a, dp, rrc, rows_first || knob(K_FK_ROWS, -1) == 1)) return rrc;
         if (try_fk_rows(a, dp, rrc)) return rrc;
+    }
+    // fk_quat: the quaternion track kernel (qtracks_kernel.cuh) unless it does not apply; PMB_FKQ_TRACKS = 0 / 1 forces,
+    // and forcing a variant of the chain kernels (PMB_FKQ_GROUP / _BLOCKS_PER_SM / _MATRIX) selects those.
+    const int qtracks = knob(K_FKQ_TRACKS, (knob_set(K_FKQ_GROUP) || knob_set(K_FKQ_BLOCKS_PER_SM) || knob_set(K_FKQ_MATRIX)) ? 0 : -1);
+    if (ostride == 0 && quat_out && qtracks != 0) {
+        int trc = PMB_OK;
+        const bool f = qtracks == 1;
+        const bool took = rotations_only
+                              ? launch_qtracks<pmb::kQtFkQuatRot>(rot, gpos, gstride, offsets, parents_host, n_frames, n_joints, rout, nullptr, a.stream, dp, f, trc)
+                              : launch_qtracks<pmb::kQtFkQuat>(rot, gpos, gstride, offsets, parents_host, n_frames, n_joints, rout, pos, a.stream, dp, f, trc);
+        if (took) return trc;
     }
     if (ostride == 0 && quat_out && (rotations_only || knob(K_FKQ_MATRIX, 0) == 0)) return launch_fk_quat_chain(a, dp);
     if (ostride == 0) return quat_out ? launch_fk<false, true>(a, dp) : launch_fk<false, false>(a, dp);

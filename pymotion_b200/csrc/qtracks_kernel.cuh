@@ -40,7 +40,7 @@ __host__ __device__ inline QtGeom qt_geom(int mode, int warps, int n_joints, int
     g.q_pitch = mode == kQtDq ? 32 * (n_joints + 1) + 16 : 16 * ((n_joints + 1) | 1);  // + the identity record (dq) / padding
     g.q_bytes = kQtFrames * g.q_pitch;
     g.p_bytes = mode == kQtFkQuat ? ((kQtFrames * 12 * n_joints + 16 + 15) & ~15) : 0;  // dense, + 16 bytes of phase slack
-    g.tab_bytes = (n_items * 16 + 127) & ~127;
+    g.tab_bytes = (((n_items + kQtTracks) * 16 + 127) & ~127) + 128;  // + one step of no-ops (prefetch overrun) + the tile counter
     g.warp_bytes = (2 * g.in_bytes + g.q_bytes + g.p_bytes + 16 + 128 + 127) & ~127;  // + 2 mbarriers + fence words
     g.block_bytes = 128 + g.tab_bytes + warps * g.warp_bytes;
     return g;
@@ -94,15 +94,15 @@ __device__ __forceinline__ Quat<float> qt_from_matrix_sign(const Quat<float> &q)
     return pivot < 0.f ? Quat<float>{-q.w, -q.x, -q.y, -q.z} : q;
 }
 
-template <int MODE>
+template <int MODE, bool PIPE>
 __global__ void __launch_bounds__(512, 1)
 qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, long long gstride, const float *__restrict__ offsets,
                float4 *__restrict__ out_q, float *__restrict__ out_p, long long n_frames, int n_joints, int n_steps,
-               const __grid_constant__ TrackProgram prog) {
+               int dynamic_claims, const __grid_constant__ TrackProgram prog) {
     constexpr int FQ = kQtFrames, NT = kQtTracks;
     constexpr bool POS = MODE == kQtFkQuat;
-    extern __shared__ __align__(128) unsigned char smem_dyn[];
-    unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    extern __shared__ __align__(128) unsigned char smem_qt[];
+    unsigned char *smem_raw = smem_qt + ((128u - (smem_u32(smem_qt) & 127u)) & 127u);
     const int warps = blockDim.x >> 5;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int n_items = n_steps * NT;
@@ -111,8 +111,10 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
     // Item table, 16 bytes per item: offset (x, y, z) | word: bits 0-9 joint, 10-19 parent, 30 = parent in the track's
     // registers, 31 + 30 = no-op.  to_root_dual_quat: the children of the root get the identity record (joint index J).
     uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);
-    for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
-        const uint32_t c = prog.code[i];
+    uint32_t *tile_counter = reinterpret_cast<uint32_t *>(smem_raw + geo.tab_bytes - 128);
+    if (threadIdx.x == 0) *tile_counter = 0u;
+    for (int i = threadIdx.x; i < n_items + NT; i += blockDim.x) {
+        const uint32_t c = i < n_items ? prog.code[i] : kTrackNoop;
         const uint32_t j = track_joint(c);
         uint32_t p = track_parent(c);
         uint4 e = make_uint4(0u, 0u, 0u, 0xC0000000u);
@@ -142,9 +144,23 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
     }
     __syncthreads();  // table, barriers, identity records; from here on the warps never meet again
 
+    // Tiles: block b owns tiles b, b + grid, b + 2 grid, ...; its warps CLAIM them from a shared-memory counter.  (With a
+    // static round robin the warps of an SM whose count is not a multiple of four -- 6 or 7 at 65 joints, 9 at 52 -- finish
+    // at the pace of the sub-partition that holds one warp more: measured 1.67 ms with 9 warps against 1.52 ms with 8 at
+    // 4M x 52.)  A warp holds two claims: the tile it walks and the one whose quaternions are on their way.
     const long long n_tiles = (n_frames + FQ - 1) / FQ;
-    const long long tile_stride = static_cast<long long>(gridDim.x) * warps;
-    long long tile = static_cast<long long>(blockIdx.x) * warps + warp;
+    uint32_t static_n = warp;
+    auto claim = [&]() -> long long {
+        uint32_t n = 0;
+        if (dynamic_claims) {
+            if (lane == 0) n = atomicAdd(tile_counter, 1u);
+            n = __shfl_sync(0xffffffffu, n, 0);
+            return static_cast<long long>(n) * gridDim.x + blockIdx.x;
+        }
+        n = static_n, static_n += warps;
+        return (static_cast<long long>(n / warps) * gridDim.x + blockIdx.x) * warps + (n % warps);
+    };
+    long long tile = claim(), tile_next = claim();
     if (tile >= n_tiles) return;
     const int row_bytes = 16 * n_joints;
     const uint32_t in_row0 = in0 + f * geo.in_pitch, q_row = qst + f * geo.q_pitch;
@@ -160,7 +176,7 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
         }
     };
     issue_tile(tile, 0);
-    issue_tile(tile + tile_stride, 1);
+    issue_tile(tile_next, 1);
 
     float gn0, gn1, gn2;  // root position of this lane's frame in the NEXT tile, fetched a tile early
     {
@@ -170,7 +186,7 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
     uint32_t k = 0;
     bool draining = false;
 
-    for (; tile < n_tiles; tile += tile_stride, ++k) {
+    for (; tile < n_tiles; ++k) {
         const long long f0 = tile * FQ;
         const int nrows = static_cast<int>(min(static_cast<long long>(FQ), n_frames - f0));
         const int buf = k & 1;
@@ -181,34 +197,73 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
         Quat<float> R{1.f, 0.f, 0.f, 0.f};
         float4 D = make_float4(0.f, 0.f, 0.f, 0.f);
         float t0 = gn0, t1 = gn1, t2 = gn2;
-        if (tile + tile_stride < n_tiles) {
-            const float *g = gpos + min((tile + tile_stride) * FQ + f, n_frames - 1) * gstride;
+        if (tile_next < n_tiles) {
+            const float *g = gpos + min(tile_next * FQ + f, n_frames - 1) * gstride;
             gn0 = __ldg(g), gn1 = __ldg(g + 1), gn2 = __ldg(g + 2);
         }
         mbar_wait(bar0 + 8 * buf, (k >> 1) & 1);
         if (draining) bulk_wait_read0();  // (lanes that stored) the previous tile has left the stage
         __syncwarp();
 
+        // The walk, software pipelined: the table entry and the local quaternion of step s + 1 (for fk_quat already
+        // normalised) are fetched while step s computes, so what is left on the step-to-step critical path is parent
+        // read -> products -> store -> __syncwarp.  The table ends with one step of no-ops for the last prefetch.
         uint32_t acc = 0;
+        uint32_t tab_addr = tab0 + trk * 16;
+        float4 e = lds128_ro(tab_addr);
+        float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PIPE) {
+            qv = lds128(in_row + 16 * (__float_as_uint(e.w) & 0x3FFu));
+            acc |= __float_as_uint(qv.x);
+            if (MODE != kQtDq) {
+                Quat<float> r = q_normalize_fast(Quat<float>{qv.x, qv.y, qv.z, qv.w}, 1e-8f);
+                qv = make_float4(r.w, r.x, r.y, r.z);
+            }
+        }
         for (int step = 0; step < n_steps; ++step) {
-            const float4 e = lds128_ro(tab0 + (step * NT + trk) * 16);
+            tab_addr += NT * 16;
+            float4 e_next = e, qv_next = qv;
+            if (!PIPE) {
+                qv = lds128(in_row + 16 * (__float_as_uint(e.w) & 0x3FFu));
+                acc |= __float_as_uint(qv.x);
+                if (MODE != kQtDq) {
+                    Quat<float> r = q_normalize_fast(Quat<float>{qv.x, qv.y, qv.z, qv.w}, 1e-8f);
+                    qv = make_float4(r.w, r.x, r.y, r.z);
+                }
+            }
+            // Issued AFTER the parent reads of this step (shared-memory instructions keep their order): the address of the
+            // quaternion depends on the table entry, and an in-order warp would otherwise sit on that dependency with the
+            // parent reads -- the critical path -- queued behind it.
+            auto prefetch = [&]() {
+                if (PIPE) {
+                    e_next = lds128_ro(tab_addr);
+                    qv_next = lds128(in_row + 16 * (__float_as_uint(e_next.w) & 0x3FFu));
+                    acc |= __float_as_uint(qv_next.x);
+                    if (MODE != kQtDq) {
+                        // the reference turns q / (|q| + eps) into a MATRIX: the zero quaternion becomes the identity (below)
+                        Quat<float> r = q_normalize_fast(Quat<float>{qv_next.x, qv_next.y, qv_next.z, qv_next.w}, 1e-8f);
+                        qv_next = make_float4(r.w, r.x, r.y, r.z);
+                    }
+                }
+            };
             const uint32_t w = __float_as_uint(e.w);
             const uint32_t j = w & 0x3FFu, p = (w >> 10) & 0x3FFu;
-            const float4 qv = lds128(in_row + 16 * j);
-            acc |= __float_as_uint(qv.x);
             if (MODE == kQtDq) {
                 // parent (rotation, dual part): registers, or the stage (a joint stored earlier, or the identity record)
                 float4 a = make_float4(R.w, R.x, R.y, R.z), b = D;
                 qt_lds128_if(w << 1, q_row + 32 * p, a);
                 qt_lds128_if(w << 1, q_row + 32 * p + 16, b);
-                if (static_cast<int>(w << 1) >= 0) {
+                prefetch();
+                {
                     // translation back from the dual part: t = 2 (d (x) conj(r)) / |r|^2 (dual_quat.py:62-83; rotations are
-                    // not normalised on this path)
+                    // not normalised on this path).  Branch free: the tracks of a warp disagree about where the parent is.
                     const float n2 = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-                    const float s = 2.f / n2;
-                    t0 = s * (-b.x * a.y + b.y * a.x - b.z * a.w + b.w * a.z);
-                    t1 = s * (-b.x * a.z + b.y * a.w + b.z * a.x - b.w * a.y);
-                    t2 = s * (-b.x * a.w - b.y * a.z + b.z * a.y + b.w * a.x);
+                    const float s = __fdividef(2.f, n2);
+                    const float u0 = s * (-b.x * a.y + b.y * a.x - b.z * a.w + b.w * a.z);
+                    const float u1 = s * (-b.x * a.z + b.y * a.w + b.z * a.x - b.w * a.y);
+                    const float u2 = s * (-b.x * a.w - b.y * a.z + b.z * a.y + b.w * a.x);
+                    const bool from_stage = static_cast<int>(w << 1) >= 0;
+                    t0 = from_stage ? u0 : t0, t1 = from_stage ? u1 : t1, t2 = from_stage ? u2 : t2;
                 }
                 const Quat<float> Rp{a.x, a.y, a.z, a.w};
                 const Vec3<float> v = q_rotate(Rp, Vec3<float>{e.x, e.y, e.z});   // skeleton.py:238-240
@@ -222,8 +277,8 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
                 float4 a = make_float4(R.w, R.x, R.y, R.z);
                 qt_lds128_if(w << 1, q_row + 16 * p, a);
                 if (POS) qt_lds3_if(w << 1, p_row + 12 * p, t0, t1, t2);
-                // the reference turns q / (|q| + eps) into a MATRIX: the zero quaternion becomes the identity
-                Quat<float> r = q_normalize_fast(Quat<float>{qv.x, qv.y, qv.z, qv.w}, 1e-8f);
+                prefetch();
+                Quat<float> r{qv.x, qv.y, qv.z, qv.w};
                 if (r.w == 0.f && r.x == 0.f && r.y == 0.f && r.z == 0.f) r.w = 1.f;
                 const Quat<float> Qp{a.x, a.y, a.z, a.w};
                 if (POS) {
@@ -235,12 +290,16 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
                 if (POS) qt_sts3_if(w, p_row + 12 * j, t0, t1, t2);
             }
             __syncwarp();  // a parent may have been stored by another track
+            if (PIPE) e = e_next, qv = qv_next;
+            else e = lds128_ro(tab_addr);
         }
         // the tile's quaternions have been READ (a store that depends on all of them precedes the refill through the async
         // proxy, see fk_kernel.cuh); fetch the tile after the next one into this buffer
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(fence_word), "r"(acc) : "memory");
         __syncwarp();
-        issue_tile(tile + 2 * tile_stride, buf);
+        tile = tile_next;
+        tile_next = claim();
+        issue_tile(tile_next, buf);
 
         // ---- output: one bulk store per frame row; positions as one dense span ---------------------------------
         fence_proxy_async_smem();

@@ -62,11 +62,24 @@ def main():
             np.testing.assert_allclose(pos, want_pos, rtol=1e-5, atol=1e-5 * scale)
             np.testing.assert_allclose(rotm, want_rotm, rtol=1e-5, atol=5e-5)
             n_checked += 1
-        set_knobs({})
-        p2, gq = sk.fk_quat(rot, gp, off, par)
-        np.testing.assert_allclose(p2, want_pos, rtol=1e-5, atol=1e-5 * scale)
-        d = sk.to_root_dual_quat(rot, gp, par, off)
-        np.testing.assert_allclose(d, orc.to_root_dual_quat(rot, gp, par, off), rtol=1e-5, atol=5e-5 * scale)
+        want_dq = orc.to_root_dual_quat(rot, gp, par, off)
+        # the quaternion track kernel (forced, both tile-claim modes, with and without the one-step-ahead fetch) and the
+        # thread-per-frame chain kernels it replaces by default
+        for knobs in ({"PMB_DQ_TRACKS": "1", "PMB_FKQ_TRACKS": "1"},
+                      {"PMB_DQ_TRACKS": "1", "PMB_FKQ_TRACKS": "1", "PMB_QT_DYNAMIC": "0", "PMB_QT_PIPE": "1", "PMB_QT_WARPS_PER_SM": "2"},
+                      {"PMB_DQ_TRACKS": "1", "PMB_FKQ_TRACKS": "1", "PMB_QT_PIPE": "0", "PMB_QT_WARPS_PER_SM": "1"},
+                      {"PMB_DQ_TRACKS": "0", "PMB_FKQ_TRACKS": "0"}, {}):
+            set_knobs(knobs)
+            try:
+                p2, gq = sk.fk_quat(rot, gp, off, par)
+                d = sk.to_root_dual_quat(rot, gp, par, off)
+            except Exception as e:
+                if knobs and ("fit" in str(e) or "variant" in str(e)):
+                    continue
+                raise
+            np.testing.assert_allclose(p2, want_pos, rtol=1e-5, atol=1e-5 * scale)
+            np.testing.assert_allclose(d, want_dq, rtol=1e-5, atol=5e-5 * scale)
+            n_checked += 2
         t, r = sk.from_root_dual_quat(d, par)
         np.testing.assert_allclose(r, rot, rtol=1e-5, atol=5e-5)
         sk.from_global_rotations(gq, par)

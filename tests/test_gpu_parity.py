@@ -577,8 +577,11 @@ def test_fk_row_team_kernel(sk, set_knobs, knobs, name, n_frames):
         assert_allclose(rotm, want_rotm, **TOL)
 
 
-@pytest.mark.parametrize("knobs", [{}, {"PMB_FKQ_GROUP": "8"}, {"PMB_FKQ_GROUP": "16"}, {"PMB_FKQ_GROUP": "24"},
-                                   {"PMB_FKQ_BLOCKS_PER_SM": "1"}, {"PMB_FKQ_MATRIX": "1"}])
+@pytest.mark.parametrize("knobs", [{}, {"PMB_FKQ_TRACKS": "0"}, {"PMB_FKQ_GROUP": "8"}, {"PMB_FKQ_GROUP": "16"}, {"PMB_FKQ_GROUP": "24"},
+                                   {"PMB_FKQ_BLOCKS_PER_SM": "1"}, {"PMB_FKQ_MATRIX": "1"},
+                                   {"PMB_FKQ_TRACKS": "1"}, {"PMB_FKQ_TRACKS": "1", "PMB_QT_WARPS_PER_SM": "1"},
+                                   {"PMB_FKQ_TRACKS": "1", "PMB_QT_PIPE": "0", "PMB_QT_DYNAMIC": "0"},
+                                   {"PMB_FKQ_TRACKS": "1", "PMB_QT_PIPE": "1", "PMB_QT_WARPS_PER_SM": "3"}])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 6_050), ("deep65", 5_031), ("chain3", 777),
                                            ("body40", 2_049)])
 def test_fk_quat_every_variant(sk, set_knobs, knobs, name, n_frames):
@@ -703,6 +706,46 @@ def test_to_root_dual_quat_every_group(sk, set_knobs, group, name, n_frames):
     rot, gp, off = synth_numpy(n_frames, par, seed=7 * len(par) + n_frames)
     dq = sk.to_root_dual_quat(rot, gp, par, off)
     assert_allclose(dq, orc.to_root_dual_quat(rot, gp, par, off), **TOL)
+
+
+@pytest.mark.parametrize("knobs", [{"PMB_DQ_TRACKS": "1"}, {"PMB_DQ_TRACKS": "1", "PMB_QT_WARPS_PER_SM": "1"},
+                                   {"PMB_DQ_TRACKS": "1", "PMB_QT_DYNAMIC": "0", "PMB_QT_WARPS_PER_SM": "3"}, {"PMB_DQ_TRACKS": "0"}])
+@pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
+                                           ("body32", 5_009), ("body22", 7), ("body16", 1), ("deep65", 29)])
+def test_to_root_dual_quat_track_kernel(sk, set_knobs, knobs, name, n_frames):
+    """to_root_dual_quat through the quaternion track kernel (lanes = 4 tracks x 8 frames, whole-skeleton level schedule,
+    dense output stage doubling as the parent store), forced on and off: ragged frame counts (remainder tile), one warp
+    per SM (stage and input double buffer reused across many tiles), single-tile batches."""
+    set_knobs(knobs)
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=17 * len(par) + n_frames)
+    want = orc.to_root_dual_quat(rot, gp, par, off)
+    for _ in range(2):
+        dq = sk.to_root_dual_quat(rot, gp, par, off)
+        assert ("qtracks_kernel" in _lib.load().pmb_last_variant().decode()) == (knobs["PMB_DQ_TRACKS"] == "1")
+        assert_allclose(dq, want, **TOL)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_quaternion_track_kernel_random_trees(sk, set_knobs, seed):
+    """Random topologies (bushy, deep, up to 200 joints) through the four-track whole-skeleton schedule: dual quaternions and
+    fk_quat (positions at the hot-path tolerance, rotations as the same rotation with the reference's sign rule)."""
+    rng = np.random.default_rng(2000 + seed)
+    n_joints = int(rng.integers(2, 200))
+    par = np.zeros(n_joints, dtype=np.int64)
+    for i in range(1, n_joints):
+        par[i] = rng.integers(max(0, i - 1 - int(rng.integers(0, 12))), i)
+    n_frames = int(rng.integers(1, 3000))
+    rot, gp, off = synth_numpy(n_frames, par, seed=seed)
+    set_knobs({"PMB_DQ_TRACKS": "1", "PMB_FKQ_TRACKS": "1"})
+    dq = sk.to_root_dual_quat(rot, gp, par, off)
+    assert "qtracks_kernel" in _lib.load().pmb_last_variant().decode()
+    assert_allclose(dq, orc.to_root_dual_quat(rot, gp, par, off), rtol=2e-5, atol=2e-5)
+    want_pos, want_rotm = orc.fk(rot, gp, off, par)
+    pos, grot = sk.fk_quat(rot, gp, off, par)
+    assert "qtracks_kernel" in _lib.load().pmb_last_variant().decode()
+    assert_allclose(pos, want_pos, rtol=2e-5, atol=2e-5)
+    assert_allclose(np.abs(np.sum(grot * orc.quat_from_matrix(want_rotm), axis=-1)), 1.0, atol=2e-5)
 
 
 def test_frame_shards_on_two_devices(sk):

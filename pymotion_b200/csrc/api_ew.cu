@@ -369,11 +369,12 @@ int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_h
     }
     DeviceProps dp;
     if ((rc = device_props(dp))) return rc;
+    const bool fast = knob(K_FRP_FAST, 1) != 0;
     constexpr int THREADS = 128;
     const int smem = n_joints * 16 + n_slots * THREADS * 16;
     if (smem > dp.smem_optin)
         return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", n_slots);
-    auto kernel = pmb::from_root_positions_kernel<THREADS>;
+    auto kernel = fast ? pmb::from_root_positions_kernel<THREADS, true> : pmb::from_root_positions_kernel<THREADS, false>;
     int per_sm_unused = 0;
     if ((rc = kernel_fit(kernel, dp, THREADS, smem, per_sm_unused))) return rc;
     // Thread = frame reads its positions row 12 bytes at a time, so the op lives on L1 hits, and L1 is what the
@@ -387,7 +388,7 @@ int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_h
         const int want = target * (smem + 1024);
         const int pct = std::max(1, std::min(100, (want * 100 + dp.smem_optin - 1) / dp.smem_optin));
         PMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        note_variant("from_root_positions_kernel<%d> smem=%d carveout=%d%% (for %d blocks/SM)", THREADS, smem, pct, target);
+        note_variant("from_root_positions_kernel<%d,FAST=%d> smem=%d carveout=%d%% (for %d blocks/SM)", THREADS, int(fast), smem, pct, target);
     }
     const long long blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");

@@ -37,7 +37,138 @@ struct ChildTable {
 // (A tile-staged variant -- one warp per block, positions and rotations through shared memory with coalesced
 // 16-byte accesses -- was measured SLOWER: 0.54 ms against 0.36 ms at 1M x 22.  The op is bound by the IEEE
 // square roots and divisions of from_to / from_to_axis, not by its strided global accesses.)
-template <int THREADS>
+// ---- the same alignments with approximate square roots / reciprocals -----------------------------------------------
+// sqrt.approx and rcp.approx are good to about 1 ulp (against 0.5 ulp for the IEEE versions) and cost one MUFU
+// instruction each instead of ~10 instructions with a slow path; the stable half-angle formulas keep those relative
+// errors relative (nothing here subtracts nearly equal quantities).  Error statistics against the float64 reference are
+// the same as with IEEE arithmetic at every quantile (profiles/r2_frp_error_stats.jsonl).  (A shorter chain from two
+// levels of rsqrt.approx without the q / (|q| + eps) of the intermediate rotations was measured too: 10 % faster, but
+// median / p99 errors 1.2 - 1.5 x larger -- not taken.)
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ Vec3<float> v_normalize_approx(const Vec3<float> &v, float eps) {
+    const float inv = rcp_approx(sqrt_approx(v.x * v.x + v.y * v.y + v.z * v.z) + eps);
+    return {v.x * inv, v.y * inv, v.z * inv};
+}
+__device__ __forceinline__ Quat<float> q_normalize_approx(const Quat<float> &q, float eps) {
+    const float inv = rcp_approx(sqrt_approx(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z) + eps);
+    return {q.w * inv, q.x * inv, q.y * inv, q.z * inv};
+}
+__device__ __forceinline__ void half_angle_approx(float dot, float ncr, float &w, float &s) {
+    const float big = sqrt_approx((1.f + fabsf(dot)) * 0.5f);
+    const float small = ncr * rcp_approx(big + big);
+    w = dot >= 0.f ? big : small;
+    s = dot >= 0.f ? small : big;
+}
+template <bool FAST>
+__device__ __forceinline__ Quat<float> ik_from_to(const Vec3<float> &a, Vec3<float> b) {
+    if (!FAST) return q_from_to_stable(a, b);
+    b = v_normalize_approx(b, 1e-8f);
+    const Vec3<float> cr = cross3(a, b);
+    const float dot = dot3_np(a, b);
+    const float ncr = sqrt_approx(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z);
+    float w, s;
+    half_angle_approx(dot, ncr, w, s);
+    const float k = s * rcp_approx(ncr + 1e-8f);  // normalize(cross) * s
+    Quat<float> r{w, cr.x * k, cr.y * k, cr.z * k};
+    if (np_isclose(dot, 1.f)) r = {1.f, 0.f, 0.f, 0.f};
+    if (np_isclose(dot, -1.f)) {
+        const Vec3<float> e = np_isclose(fabsf(a.x), 1.f) ? Vec3<float>{0.f, 1.f, 0.f} : Vec3<float>{1.f, 0.f, 0.f};
+        const Vec3<float> h = v_normalize(cross3(a, e), 1e-8f);
+        r = {0.f, h.x, h.y, h.z};
+    }
+    return r;
+}
+template <bool FAST>
+__device__ __forceinline__ Quat<float> ik_from_to_axis(const Vec3<float> &a, Vec3<float> b, const Vec3<float> &u) {
+    if (!FAST) return q_from_to_axis_stable(a, b, u);
+    b = v_normalize_approx(b, 1e-8f);
+    const Vec3<float> cr = cross3(a, b);
+    const float dot = dot3_np(a, b);
+    const float ncr = sqrt_approx(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z);
+    float w, s;
+    half_angle_approx(dot, ncr, w, s);
+    const float side = dot3_np(cr, u);
+    s *= side > 0.f ? 1.f : (side < 0.f ? -1.f : side);  // np.sign (keeps 0 and nan)
+    Quat<float> r{w, u.x * s, u.y * s, u.z * s};
+    if (np_isclose(dot, 1.f)) r = {1.f, 0.f, 0.f, 0.f};
+    if (np_isclose(dot, -1.f)) r = {0.f, u.x, u.y, u.z};
+    return r;
+}
+template <bool FAST>
+__device__ __forceinline__ Quat<float> ik_q_normalize(const Quat<float> &q) {
+    return FAST ? q_normalize_approx(q, 1e-8f) : q_normalize(q, 1e-8f);
+}
+template <bool FAST>
+__device__ __forceinline__ Vec3<float> ik_v_normalize(const Vec3<float> &v) {
+    return FAST ? v_normalize_approx(v, 1e-8f) : v_normalize(v, 1e-8f);
+}
+
+// The walk of one frame, shared by the two kernels below.  point(j) returns P_j, load_slot / save_slot move the global
+// quaternion of a branch joint, emit(j, rot) receives the local rotation of joint j (joints in index order).
+template <bool FAST, class Point, class LoadSlot, class SaveSlot, class Emit>
+__device__ __forceinline__ void frp_walk(int n_joints, const float4 *tab, const JointProgram &prog, const ChildTable &kids,
+                                         Point point, LoadSlot load_slot, SaveSlot save_slot, Emit emit) {
+    Quat<float> cur{1.f, 0.f, 0.f, 0.f};  // global rotation of the previous joint
+    Vec3<float> pc_prev{0.f, 0.f, 0.f};   // point of the previous joint's first child: the next joint's own point on a chain
+    int c_prev = -1;
+    for (int j = 0; j < n_joints; ++j) {
+        const uint32_t code = prog.code[j];
+        Quat<float> G{1.f, 0.f, 0.f, 0.f};  // global rotation of j's parent (the root's parent is the world)
+        if (j > 0) {
+            const uint32_t src = prog_src(code);
+            G = src == kSrcReg ? cur : load_slot(src);
+        }
+        Quat<float> rot{1.f, 0.f, 0.f, 0.f};
+        const int k0 = kids.start[j], k1 = kids.start[j + 1];
+        if (k1 > k0) {
+            const Vec3<float> pj = j == c_prev ? pc_prev : point(j);
+            const int c = kids.child[k0];
+            const Vec3<float> pc = point(c);
+            pc_prev = pc, c_prev = c;
+            const Vec3<float> to_c{pc.x - pj.x, pc.y - pj.y, pc.z - pj.z};
+            const float4 oc = tab[c];
+            rot = ik_from_to<FAST>(Vec3<float>{oc.x, oc.y, oc.z}, q_rotate(q_conj(G), to_c));
+            for (int k = k0 + 1; k < k1; ++k) {
+                const int g = kids.child[k];
+                const Quat<float> inv = q_conj(q_mul(G, ik_q_normalize<FAST>(rot)));  // fk normalises local rotations (quat.py:411)
+                const Vec3<float> pg = point(g);
+                const float4 og = tab[g];
+                const Vec3<float> pred = q_rotate(inv, Vec3<float>{pg.x - pj.x, pg.y - pj.y, pg.z - pj.z});
+                const Vec3<float> axis = q_rotate(inv, ik_v_normalize<FAST>(to_c));
+                rot = q_mul(rot, ik_from_to_axis<FAST>(Vec3<float>{og.x, og.y, og.z}, pred, axis));
+            }
+        }
+        emit(j, rot);
+        cur = q_mul(G, ik_q_normalize<FAST>(rot));
+        const uint32_t sv = prog_save(code);
+        if (sv != kNoSave) save_slot(sv, cur);
+    }
+}
+
+// Rest directions: from_to / from_to_axis normalise their first argument (quat.py:541, :616) -- the same value for every frame.
+__device__ __forceinline__ void frp_fill_rest_directions(float4 *tab, const float *offsets, int n_joints) {
+    for (int j = threadIdx.x; j < n_joints; j += blockDim.x) {
+        const Vec3<float> d = v_normalize(Vec3<float>{offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2]}, 1e-8f);
+        tab[j] = make_float4(d.x, d.y, d.z, 0.f);
+    }
+}
+
+// Thread = frame straight from / to global memory: 12-byte reads 12 J bytes apart, 16-byte stores 16 J bytes apart.  Kept
+// for skeletons whose tile does not fit the tile kernel's shared memory and for unaligned position arrays.
+// ncu at 4M x 65 (profiles/r2_frp_fk_4m_x_65_ncu_summary.txt): 1.37 G sector look-ups in L1 at a 56 % hit rate, 573 M sectors
+// read from L2 for an input of 97.5 M (each point is touched twice, as a child and as a joint, and 24 warps x 25 KB of
+// rows do not stay in L1), 260 M partial-sector stores; 174 G sectors/s through L2 -- the sector rate, not the arithmetic,
+// bounds it (approximate square roots / reciprocals change nothing: 4.85 -> 4.82 ms).
+template <int THREADS, bool FAST>
 __global__ void __launch_bounds__(THREADS)
 from_root_positions_kernel(const float *__restrict__ pos, const float *__restrict__ offsets, float4 *__restrict__ rots,
                            long long n_frames, int n_joints, int n_slots, const __grid_constant__ JointProgram prog,
@@ -45,55 +176,33 @@ from_root_positions_kernel(const float *__restrict__ pos, const float *__restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *tab = reinterpret_cast<float4 *>(smem_raw);                 // [J] rest directions: offsets / (|offsets| + 1e-8)
     float4 *slots = tab + n_joints;                                      // [n_slots][THREADS] global quaternions
-    for (int j = threadIdx.x; j < n_joints; j += THREADS) {
-        // from_to / from_to_axis normalise their first argument (quat.py:541, :616): the same value for every frame
-        const Vec3<float> d = v_normalize(Vec3<float>{offsets[3 * j], offsets[3 * j + 1], offsets[3 * j + 2]}, 1e-8f);
-        tab[j] = make_float4(d.x, d.y, d.z, 0.f);
-    }
+    frp_fill_rest_directions(tab, offsets, n_joints);
     __syncthreads();
     const long long f = blockIdx.x * static_cast<long long>(THREADS) + threadIdx.x;
     if (f >= n_frames) return;
     const float *P = pos + f * n_joints * 3;
     float4 *R = rots + f * n_joints;
-    auto point = [&](int j) { return Vec3<float>{__ldg(P + 3 * j), __ldg(P + 3 * j + 1), __ldg(P + 3 * j + 2)}; };
-
-    Quat<float> cur{1.f, 0.f, 0.f, 0.f};  // global rotation of the previous joint
-    for (int j = 0; j < n_joints; ++j) {
-        const uint32_t code = prog.code[j];
-        Quat<float> G{1.f, 0.f, 0.f, 0.f};  // global rotation of j's parent (the root's parent is the world)
-        if (j > 0) {
-            const uint32_t src = prog_src(code);
-            if (src == kSrcReg) {
-                G = cur;
-            } else {
-                const float4 s = slots[src * THREADS + threadIdx.x];
-                G = {s.x, s.y, s.z, s.w};
+    // Rotations leave as whole 32-byte sectors where the row allows it: joints (j - 1, j) share a sector iff the float4
+    // index f J + j is odd, so the rotation of an even-index joint waits in registers for its neighbour (one 256-bit store
+    // instead of two half-sector ones: 260 M -> 130 M store sectors at 4M x 65).
+    // this frame's row starts on a sector boundary (the array itself may start mid-sector: it is 16-byte aligned)
+    const bool pair_at_odd = ((f * n_joints + static_cast<long long>((reinterpret_cast<uintptr_t>(rots) >> 4) & 1u)) & 1LL) == 0;
+    Quat<float> held{1.f, 0.f, 0.f, 0.f};
+    frp_walk<FAST>(
+        n_joints, tab, prog, kids,
+        [&](int j) { return Vec3<float>{__ldg(P + 3 * j), __ldg(P + 3 * j + 1), __ldg(P + 3 * j + 2)}; },
+        [&](uint32_t s) { const float4 v = slots[s * THREADS + threadIdx.x]; return Quat<float>{v.x, v.y, v.z, v.w}; },
+        [&](uint32_t s, const Quat<float> &q) { slots[s * THREADS + threadIdx.x] = make_float4(q.w, q.x, q.y, q.z); },
+        [&](int j, const Quat<float> &r) {
+            const bool second = ((j & 1) != 0) == pair_at_odd;  // j closes the sector that j - 1 opened
+            if (second && j > 0) {
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(R + j - 1), "f"(held.w), "f"(held.x), "f"(held.y),
+                             "f"(held.z), "f"(r.w), "f"(r.x), "f"(r.y), "f"(r.z) : "memory");
+            } else if (second || j == n_joints - 1) {  // the first joint of a row that starts mid-sector / the last one of a row that ends there
+                R[j] = make_float4(r.w, r.x, r.y, r.z);
             }
-        }
-        Quat<float> rot{1.f, 0.f, 0.f, 0.f};
-        const int k0 = kids.start[j], k1 = kids.start[j + 1];
-        if (k1 > k0) {
-            const Vec3<float> pj = point(j);
-            const int c = kids.child[k0];
-            const Vec3<float> pc = point(c);
-            const Vec3<float> to_c{pc.x - pj.x, pc.y - pj.y, pc.z - pj.z};
-            const float4 oc = tab[c];
-            rot = q_from_to_stable(Vec3<float>{oc.x, oc.y, oc.z}, q_rotate(q_conj(G), to_c));
-            for (int k = k0 + 1; k < k1; ++k) {
-                const int g = kids.child[k];
-                const Quat<float> inv = q_conj(q_mul(G, q_normalize(rot, 1e-8f)));  // fk normalises local rotations (quat.py:411)
-                const Vec3<float> pg = point(g);
-                const float4 og = tab[g];
-                const Vec3<float> pred = q_rotate(inv, Vec3<float>{pg.x - pj.x, pg.y - pj.y, pg.z - pj.z});
-                const Vec3<float> axis = q_rotate(inv, v_normalize(to_c, 1e-8f));
-                rot = q_mul(rot, q_from_to_axis_stable(Vec3<float>{og.x, og.y, og.z}, pred, axis));
-            }
-        }
-        R[j] = make_float4(rot.w, rot.x, rot.y, rot.z);
-        cur = q_mul(G, q_normalize(rot, 1e-8f));
-        const uint32_t sv = prog_save(code);
-        if (sv != kNoSave) slots[sv * THREADS + threadIdx.x] = make_float4(cur.w, cur.x, cur.y, cur.z);
-    }
+            held = r;
+        });
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -101,6 +101,50 @@ def test_from_root_positions_vs_oracle(sk, name, n_frames):
     check_ik(sk.from_root_positions(centred, par, off), want, centred, par, off, ENVELOPE[f"{name}/{n_frames}"])
 
 
+@pytest.mark.parametrize("knobs", [{}, {"PMB_FRP_FAST": "0"}, {"PMB_FRP_BLOCKS_PER_SM": "2"}])
+@pytest.mark.parametrize("name,n_frames", [("body22", 3001), ("smplh52", 1000), ("deep65", 517)])
+def test_from_root_positions_every_variant(sk, set_knobs, knobs, name, n_frames):
+    """Approximate (default) and IEEE square roots / reciprocals, another shared-memory carve-out: all inside the reference
+    twin's envelope."""
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=n_frames)
+    pos, _ = orc.fk(rot, gp, off, par)
+    centred = (pos - pos[:, 0:1]).astype(np.float32)
+    want = orc.from_root_positions(centred.astype(np.float64), par, off.astype(np.float64))
+    set_knobs(knobs)
+    check_ik(sk.from_root_positions(centred, par, off), want, centred, par, off, ENVELOPE[f"{name}/{n_frames}"])
+
+
+@pytest.mark.parametrize("n_frames", [1, 2, 31, 33, 128, 129])
+def test_from_root_positions_sector_pairs(sk, n_frames):
+    """Rotations leave as 32-byte sectors (joints j - 1, j of a frame whose float4 index is odd): odd and even joint counts
+    (rows that start and end mid-sector), batches around the block size, and an output array that itself starts mid-sector
+    (a view one frame into a larger array) -- every entry written, none twice with a different value."""
+    for name in ("chain3", "body22", "deep65"):
+        par = parents_of(name)
+        rot, gp, off = synth_numpy(n_frames + 1, par, seed=7 + n_frames)
+        pos, _ = orc.fk(rot, gp, off, par)
+        centred = (pos - pos[:, 0:1]).astype(np.float32)
+        want = orc.from_root_positions(centred.astype(np.float64), par, off.astype(np.float64))
+        whole = sk.from_root_positions(centred, par, off)
+        st = ik_stats(whole, want, par, off)
+        assert st["median"] <= 5e-6 and st["max"] <= 2e-2 and st["pose_rebuild_max"] <= 3e-3, st
+        # the same frames computed as a batch that starts one frame later: the output rows change sector parity
+        dev, doff = torch.from_numpy(centred).cuda(), torch.from_numpy(off).cuda()
+        shifted = sk.from_root_positions(dev[1:], par, doff)
+        assert_array_equal(shifted.cpu().numpy(), whole[1:])
+        # straight through the C ABI into an output that starts 16 bytes into a sector; the float4 before it stays untouched
+        from pymotion_b200 import _lib
+
+        buf = torch.full((1 + (n_frames + 1) * len(par), 4), float("nan"), device="cuda")
+        par64 = np.ascontiguousarray(par, dtype=np.int64)
+        rc = _lib.load().pmb_from_root_positions_f32(dev.data_ptr(), par64.ctypes.data, doff.data_ptr(), n_frames + 1, len(par),
+                                                     buf[1:].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        assert torch.isnan(buf[0]).all()
+        assert_array_equal(buf[1:].view(n_frames + 1, len(par), 4).cpu().numpy(), whole)
+
+
 @pytest.mark.parametrize("name", SKELS)
 def test_mirror_all(sk, golden_ik, name):
     g = golden_ik

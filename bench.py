@@ -560,6 +560,11 @@ def run_ours(args):
             b = Batch(name)
             b.alloc("rotm")
             record(name, cfg, b, "fk", b.fk, 1)
+            if name == "fk_4m_x_65":  # the other two walks at the deep hierarchy (quaternion track kernel), same inputs
+                del b.rotm
+                b.alloc("dq", "rots")
+                record("to_root_dual_quat_4m_x_65", "configs[3] shape, to_root_dual_quat", b, "to_dq", b.to_dq, 1)
+                record("fk_quat_4m_x_65", "configs[3] shape, fk emitting global quaternions (SURVEY 8f rank 1)", b, "fk_quat", b.fk_quat, 1)
             if name == "fk_4m_x_52" and world > 1:
                 extra.append({"name": "all_gather_positions_4m_x_52", "baseline_config": "configs[4], OPTIONAL exchange, never part of poses/s",
                               **all_gather_leg(b, timer, world, rank, dev, stream)})

@@ -102,6 +102,7 @@ int pmb_from_root_dual_quat_f32(const float *dq, const int64_t *parents_host, in
     const long long blocks = (n_frames + fb - 1) / fb;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");
     const uint32_t magic = magic_small(n_joints);
+    note_variant("from_root_dq_kernel<%d> tile=%d frames grid=%lld smem=%d", THREADS, fb, blocks, smem);
     kernel<<<static_cast<unsigned>(blocks), THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4 *>(dq), translations, reinterpret_cast<float4 *>(rotations), n_frames, n_joints,
         fb, magic, *prog_p);

@@ -253,16 +253,16 @@ int pmb_dq_normalize_f32(const float *dq, float *out, int64_t n, int32_t *flags3
     PMB_CUDA(cudaMemsetAsync(flags3, 0, 3 * sizeof(int32_t), static_cast<cudaStream_t>(stream)));
     PMB_EW_PROLOGUE(n, dq, out);
     PMB_NEED16(dq); PMB_NEED16(out);
-    // pass 1 reads the array and reduces the reference's whole-array is_unit verdict into flags3; pass 2 reads it
-    // again and writes every result once (96 bytes of traffic per element instead of the 128 of scale-then-fix)
+    // pass 1: one read, scaled values written, whole-array is_unit verdict reduced into flags3; pass 2 returns at once when
+    // the verdict is "unit", else projects the output in place (rotations_ext.cuh)
     if (aligned32(dq) && aligned32(out)) {
-        pmb::dq_normalize_flags_kernel<true><<<grid_, 256, 0, st_>>>((const float4 *)dq, flags3, n);
+        pmb::dq_normalize_scale_kernel<true><<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
         PMB_CUDA(cudaGetLastError());
-        pmb::dq_normalize_write_kernel<true><<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
+        pmb::dq_normalize_project_kernel<true><<<grid_, 256, 0, st_>>>((float4 *)out, flags3, n);
     } else {
-        pmb::dq_normalize_flags_kernel<false><<<grid_, 256, 0, st_>>>((const float4 *)dq, flags3, n);
+        pmb::dq_normalize_scale_kernel<false><<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
         PMB_CUDA(cudaGetLastError());
-        pmb::dq_normalize_write_kernel<false><<<grid_, 256, 0, st_>>>((const float4 *)dq, (float4 *)out, flags3, n);
+        pmb::dq_normalize_project_kernel<false><<<grid_, 256, 0, st_>>>((float4 *)out, flags3, n);
     }
     PMB_CUDA(cudaGetLastError());
     return PMB_OK;

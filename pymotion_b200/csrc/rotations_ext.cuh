@@ -239,13 +239,17 @@ __device__ __forceinline__ void unit_flags(const Quat<float> &r, const Quat<floa
 __global__ void dq_is_unit_kernel(const float4 *dq, float atol, int *flags, long long n) {
     PMB_GRID_STRIDE(i, n) unit_flags(ldq(dq, 2 * i), ldq(dq, 2 * i + 1), atol, flags);
 }
-// dual_quat.normalize (dual_quat.py:86-115) in two passes over the input.
-// Pass 1 reduces the reference's whole-array verdict `is_unit(scaled array)` (atol 1e-3) WITHOUT forming the scaled
-// values: for r / |r| the squared norm is 1 to rounding unless |r|^2 is 0 / inf / nan (so "all real parts ~ 0" can
-// never hold and flags[0] is always raised), and real.dual of the scaled pair is (r . d) / |r|^2.  (Measured:
-// forming the eight quotients in this pass too made the op compute bound, 0.81 ms for 22 M elements.)
+// dual_quat.normalize (dual_quat.py:86-115).  The reference scales both parts by 1 / |real|, asks whether the scaled ARRAY
+// AS A WHOLE is unit (is_unit, atol 1e-3) and only if it is not removes the real direction from every dual part.
+// Pass 1 reads the input once, writes the scaled values (one square root and one division per element, within an ulp of
+// the reference's quotients) and reduces the whole-array verdict on the way: for r / |r| the squared norm is 1 to rounding
+// unless |r|^2 is 0 / inf / nan (so "all real parts ~ 0" can never hold and flags[0] is always raised), and real . dual of
+// the scaled pair is (r . d) / |r|^2.  Pass 2 is launched behind it, reads the three flags and returns at once when the
+// verdict is "unit" -- the case of dual quaternions that were built from rotations and translations -- so that case
+// costs the algorithmic 64 bytes per element; otherwise it projects IN PLACE on the output (k = rn . dn equals
+// (r . d) / |r|^2), 128 bytes per element in total.  (Round 1 read the input twice, 96 bytes per element in both cases.)
 template <bool A32>
-__global__ void dq_normalize_flags_kernel(const float4 *dq, int *flags, long long n) {
+__global__ void dq_normalize_scale_kernel(const float4 *dq, float4 *o, int *flags, long long n) {
     PMB_GRID_STRIDE(i, n) {
         const F8 x = ld_dq<A32>(dq, i);
         const Quat<float> r{x.lo.x, x.lo.y, x.lo.z, x.lo.w}, d{x.hi.x, x.hi.y, x.hi.z, x.hi.w};
@@ -255,25 +259,18 @@ __global__ void dq_normalize_flags_kernel(const float4 *dq, int *flags, long lon
         if (i == 0) atomicOr(flags + 0, 1);
         if (__any_sync(__activemask(), f1) && f1) atomicOr(flags + 1, 1);
         if (__any_sync(__activemask(), f2) && f2) atomicOr(flags + 2, 1);
+        const float inv = 1.f / sqrtf(r.w * r.w + r.x * r.x + r.y * r.y + r.z * r.z);
+        st_dq<A32>(o, i, make_float4(r.w * inv, r.x * inv, r.y * inv, r.z * inv), make_float4(d.w * inv, d.x * inv, d.y * inv, d.z * inv));
     }
 }
-// Pass 2 (:98-113): both parts times 1 / |real| (one division per element; within an ulp of the reference's
-// quotients), and only if the scaled array as a whole is not unit the real direction is removed from the dual part.
 template <bool A32>
-__global__ void dq_normalize_write_kernel(const float4 *dq, float4 *o, const int *flags, long long n) {
-    const bool unit = flags[0] == 0 || (flags[1] == 0 && flags[2] == 0);
+__global__ void dq_normalize_project_kernel(float4 *o, const int *flags, long long n) {
+    if (flags[0] == 0 || (flags[1] == 0 && flags[2] == 0)) return;  // the scaled array is unit: nothing to do
     PMB_GRID_STRIDE(i, n) {
-        const F8 x = ld_dq<A32>(dq, i);
-        const Quat<float> r{x.lo.x, x.lo.y, x.lo.z, x.lo.w}, d{x.hi.x, x.hi.y, x.hi.z, x.hi.w};
-        const float n2 = r.w * r.w + r.x * r.x + r.y * r.y + r.z * r.z;
-        const float inv = 1.f / sqrtf(n2);
-        const Quat<float> rn{r.w * inv, r.x * inv, r.y * inv, r.z * inv};
-        Quat<float> dn{d.w * inv, d.x * inv, d.y * inv, d.z * inv};
-        if (!unit) {
-            const float k = dot4_np(r, d) / n2;
-            dn = {dn.w - rn.w * k, dn.x - rn.x * k, dn.y - rn.y * k, dn.z - rn.z * k};
-        }
-        st_dq<A32>(o, i, make_float4(rn.w, rn.x, rn.y, rn.z), make_float4(dn.w, dn.x, dn.y, dn.z));
+        const F8 x = ld_dq<A32>(o, i);
+        const Quat<float> rn{x.lo.x, x.lo.y, x.lo.z, x.lo.w}, dn{x.hi.x, x.hi.y, x.hi.z, x.hi.w};
+        const float k = dot4_np(rn, dn);
+        st_dq<A32>(o, i, x.lo, make_float4(dn.w - rn.w * k, dn.x - rn.x * k, dn.y - rn.y * k, dn.z - rn.z * k));
     }
 }
 

@@ -70,8 +70,7 @@ def fk_bytes_per_pose(n_joints: int) -> int:
 def op_bytes_per_pose(op: str, n_joints: int) -> int:
     return {"fk": 64 * n_joints + 12, "to_dq": 48 * n_joints + 12, "from_dq": 60 * n_joints,
             "round_trip": 108 * n_joints + 12, "fk_quat": 44 * n_joints + 12,
-            # 8f rank 2 ops: positions in, rotations out; mirror = rotations in, rotations out (its two kernels
-            # move 76 J + 12: the fk_quat positions and the global quaternions in between are not algorithmic)
+            # 8f rank 2 ops: positions in, rotations out; mirror = rotations in, rotations out
             "from_root_positions": 28 * n_joints, "mirror_all": 32 * n_joints}[op]
 
 
@@ -474,11 +473,9 @@ def run_ours(args):
             _lib.check(lib.pmb_from_root_positions_f32(self.pos.data_ptr(), self.par.ctypes.data, self.off.data_ptr(), self.frames,
                                                        self.J, self.rots.data_ptr(), st))
 
-        def mirror_all(self):  # device part of mirror(mode="all"): fk_quat (rotations only) -> flip -> local
-            _lib.check(lib.pmb_fk_quat_f32(self.rot.data_ptr(), self.gpos.data_ptr(), 0, self.off.data_ptr(), 0, self.par.ctypes.data,
-                                           self.frames, self.J, None, self.rots.data_ptr(), st))
-            _lib.check(lib.pmb_mirror_to_local_f32(self.rots.data_ptr(), self.par.ctypes.data, None, 0, self.frames, self.J,
-                                                   self.dq.data_ptr(), st))
+        def mirror_all(self):  # device part of mirror(mode="all"): fk (rotations only) -> flip -> local, one fused launch
+            _lib.check(lib.pmb_mirror_local_f32(self.rot.data_ptr(), self.par.ctypes.data, None, 0, self.frames, self.J,
+                                                self.rots.data_ptr(), self.dq.data_ptr(), st))
 
     # ------------------------------------------------------------------ development mode: one op, kernel only
     if args.kernel_only:

@@ -188,6 +188,17 @@ int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_h
  * (0 = X, 1 = Y, 2 = Z) negated, then back to local space as from_global_rotations does. */
 int pmb_mirror_to_local_f32(const float *global_quats, const int64_t *parents_host, const int64_t *joints_mapping_host,
                             int32_t mirror_axis, int64_t n_frames, int32_t n_joints, float *local_quats, void *stream);
+
+/* The whole device side of mirror's rotation step in ONE call: fk (rotations only, root at the origin) -> sign convention of
+ * quat.from_matrix -> re-index by joints_mapping (NULL = identity), flip two vector components -> back to local space
+ * (ops/skeleton.py:322-331 `mirror`, :410-416 `_true_mirror`).  Equivalent to pmb_fk_quat_f32 (positions = NULL) followed by
+ * pmb_mirror_to_local_f32, but where the quaternion track kernel applies the global quaternions never leave the SM (32 J
+ * instead of 64 J bytes per pose).  global_quats_scratch [n_frames][n_joints][4] is only used by skeletons that take the
+ * two-kernel path (pmb_mirror_local_needs_scratch returns 1: sparse level schedules, very large skeletons) and may be NULL
+ * otherwise.  local_quats is not modified. */
+int pmb_mirror_local_needs_scratch(const int64_t *parents_host, int32_t n_joints);
+int pmb_mirror_local_f32(const float *local_quats, const int64_t *parents_host, const int64_t *joints_mapping_host, int32_t mirror_axis,
+                         int64_t n_frames, int32_t n_joints, float *global_quats_scratch, float *mirrored_local_quats, void *stream);
 /* out = v with component `axis` negated, v [n][3] (translations / offsets / end sites, skeleton.py:405-408). */
 int pmb_vec_mirror_f32(const float *v, int32_t axis, float *out, int64_t n, void *stream);
 /* out[f][j] = positions[f][j] - positions[f][0] (mirror mode 'positions', skeleton.py:338). */

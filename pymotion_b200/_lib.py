@@ -61,6 +61,8 @@ SIGNATURES = {
     "pmb_dq_is_unit_f32": [_vp, _f32, _i64, _vp, _vp],
     "pmb_dq_normalize_f32": [_vp, _vp, _i64, _vp, _vp],
     "pmb_from_root_positions_f32": [_vp, _vp, _vp, _i64, _i32, _vp, _vp],
+    "pmb_mirror_local_needs_scratch": [_vp, _i32],
+    "pmb_mirror_local_f32": [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp],
     "pmb_mirror_to_local_f32": [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp],
     "pmb_vec_mirror_f32": [_vp, _i32, _vp, _i64, _vp],
     "pmb_root_center_f32": [_vp, _vp, _i64, _i32, _vp],

@@ -455,4 +455,67 @@ int pmb_fk_quat_f32(const float *rot, const float *global_pos, int64_t gpos_fram
                      global_rots, true, stream);
 }
 
+// fk (rotations only) -> sign of quat.from_matrix -> mirror flip / re-index -> local rotations (ops/skeleton.py:322-331,
+// :410-416), as ONE kernel where the quaternion track kernel applies; else the two-kernel path through the caller's scratch.
+namespace {
+bool mirror_fused_applies(const int64_t *parents_host, int32_t n_joints, const DeviceProps &dp) {
+    if (knob(K_MIRROR_FUSED, 1) == 0) return false;
+    const pmb::TrackProgram *tp = nullptr;
+    int n_steps = 0;
+    if (track_program(parents_host, n_joints, pmb::kQtTracks, 0, tp, n_steps) || n_steps == 0) return false;
+    const QtShape sh = qt_shape(pmb::kQtMirror, n_joints, n_steps * pmb::kQtTracks, knob(K_QT_WARPS_PER_SM, 32), dp);
+    return sh.warps * sh.blocks >= 4 && 2 * n_joints >= n_steps * pmb::kQtTracks;
+}
+}  // namespace
+
+int pmb_mirror_local_needs_scratch(const int64_t *parents_host, int32_t n_joints) {
+    if (!parents_host) return fail(PMB_ERR_NULL, "parents_host is NULL");
+    if (n_joints < 1 || n_joints > PMB_MAX_JOINTS) return fail(PMB_ERR_SHAPE, "n_joints = %d outside [1, %d]", n_joints, PMB_MAX_JOINTS);
+    DeviceProps dp;
+    int rc = device_props(dp);
+    if (rc) return rc;
+    return mirror_fused_applies(parents_host, n_joints, dp) ? 0 : 1;
+}
+
+int pmb_mirror_local_f32(const float *local_quats, const int64_t *parents_host, const int64_t *joints_mapping_host, int32_t mirror_axis,
+                         int64_t n_frames, int32_t n_joints, float *global_quats_scratch, float *mirrored_local_quats, void *stream) {
+    if (!local_quats || !mirrored_local_quats) return fail(PMB_ERR_NULL, "mirror_local: NULL array pointer");
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames = %lld < 0", static_cast<long long>(n_frames));
+    if (n_frames > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames must be below 2^31 per call");
+    if (mirror_axis < 0 || mirror_axis > 2) return fail(PMB_ERR_SHAPE, "mirror_axis must be 0 (X), 1 (Y) or 2 (Z)");
+    if (!aligned16(local_quats) || !aligned16(mirrored_local_quats)) return fail(PMB_ERR_ALIGN, "quaternion arrays must be 16-byte aligned");
+    const pmb::JointProgram *prog = nullptr;
+    int n_slots = 0;
+    int rc = joint_program(parents_host, n_joints, false, prog, n_slots);  // validates parents[]
+    if (rc) return rc;
+    static thread_local pmb::QtMirrorTable mt;
+    for (int j = 0; j < n_joints; ++j) {
+        const int64_t mj = joints_mapping_host ? joints_mapping_host[j] : j;
+        const int64_t pj = j > 0 ? parents_host[j] : 0;
+        const int64_t mp = joints_mapping_host ? joints_mapping_host[pj] : pj;
+        if (mj < 0 || mj >= n_joints || mp < 0 || mp >= n_joints)
+            return fail(PMB_ERR_SHAPE, "joints_mapping[%d] outside [0, %d)", j, n_joints);
+        mt.word[j] = static_cast<uint32_t>(mj) | (static_cast<uint32_t>(mp) << 16);
+    }
+    // the two vector components that change sign (skeleton.py:307-315): X -> (y, z), Y -> (x, z), Z -> (x, y)
+    mt.fx = mirror_axis == 0 ? 1.f : -1.f, mt.fy = mirror_axis == 1 ? 1.f : -1.f, mt.fz = mirror_axis == 2 ? 1.f : -1.f;
+    if (n_frames == 0) return PMB_OK;
+    DeviceProps dp;
+    if ((rc = device_props(dp))) return rc;
+    if (mirror_fused_applies(parents_host, n_joints, dp)) {
+        int trc = PMB_OK;
+        // root at the origin, offsets unused: the walk is rotations only (the pointers only have to be readable)
+        if (launch_qtracks<pmb::kQtMirror>(local_quats, local_quats, 0, local_quats, parents_host, n_frames, n_joints, mirrored_local_quats,
+                                           nullptr, static_cast<cudaStream_t>(stream), dp, true, trc, mt))
+            return trc;
+    }
+    if (!global_quats_scratch)
+        return fail(PMB_ERR_NULL, "mirror_local: this skeleton takes the two-kernel path and needs global_quats_scratch "
+                                  "(pmb_mirror_local_needs_scratch)");
+    if ((rc = pmb_fk_quat_f32(local_quats, local_quats, 0, local_quats, 0, parents_host, n_frames, n_joints, nullptr, global_quats_scratch, stream)))
+        return rc;
+    return pmb_mirror_to_local_f32(global_quats_scratch, parents_host, joints_mapping_host, mirror_axis, n_frames, n_joints,
+                                   mirrored_local_quats, stream);
+}
+
 }  // extern "C"

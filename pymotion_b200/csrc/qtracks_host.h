@@ -39,7 +39,7 @@ inline QtShape qt_shape(int mode, int n_joints, int n_items, int warps_cap, cons
 template <int MODE>
 bool launch_qtracks(const float *rot, const float *gpos, long long gstride, const float *offsets, const int64_t *parents_host,
                     long long n_frames, int n_joints, float *out_q, float *out_p, cudaStream_t stream, const DeviceProps &dp,
-                    bool forced, int &rc) {
+                    bool forced, int &rc, const typename pmb::QtMirrorArg<MODE>::type &mir = typename pmb::QtMirrorArg<MODE>::type()) {
     const pmb::TrackProgram *tp = nullptr;
     int n_steps = 0;
     if ((rc = track_program(parents_host, n_joints, pmb::kQtTracks, 0, tp, n_steps))) return true;
@@ -60,7 +60,7 @@ bool launch_qtracks(const float *rot, const float *gpos, long long gstride, cons
                  per_sm * sh.warps, sh.smem);
     kernel<<<static_cast<unsigned>(blocks), sh.warps * 32, sh.smem, stream>>>(reinterpret_cast<const float4 *>(rot), gpos, gstride, offsets,
                                                                             reinterpret_cast<float4 *>(out_q), out_p, n_frames, n_joints,
-                                                                            n_steps, knob(K_QT_DYNAMIC, 1), *tp);
+                                                                            n_steps, knob(K_QT_DYNAMIC, 1), *tp, mir);
     rc = PMB_OK;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = cuda_fail(e, "qtracks_kernel launch");

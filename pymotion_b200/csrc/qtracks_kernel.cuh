@@ -28,10 +28,23 @@
 namespace pmb {
 
 constexpr int kQtDq = 0, kQtFkQuat = 1, kQtFkQuatRot = 2;  // dual quaternions | global quaternions + positions | quaternions only
+constexpr int kQtMirror = 3;  // mirrored LOCAL rotations: the quaternion walk followed, per tile, by the second half of mirror
+                              // (ops/skeleton.py:324-331, :410-416): re-index the global quaternions by the joints mapping,
+                              // flip two components, back to local space -- without the global quaternions ever leaving
+                              // the SM (the two-kernel path moves 64 J bytes per pose for 32 J of input and output)
+// joint j of the mirrored result reads the global quaternions of joints (word & 0xFFFF) and, for j > 0, (word >> 16):
+// joints_mapping[j] and joints_mapping[parents[j]]; (fx, fy, fz) are the signs of the vector part under the mirror axis
+struct QtMirrorTable {
+    uint32_t word[PMB_MAX_JOINTS];
+    float fx, fy, fz;
+};
+struct QtNoMirror {};
+template <int MODE> struct QtMirrorArg { using type = QtNoMirror; };
+template <> struct QtMirrorArg<kQtMirror> { using type = QtMirrorTable; };
 constexpr int kQtFrames = 8, kQtTracks = 4;
 
 struct QtGeom {
-    int in_pitch, in_bytes, q_pitch, q_bytes, p_bytes, tab_bytes, warp_bytes, block_bytes;
+    int in_pitch, in_bytes, q_pitch, q_bytes, p_bytes, o_bytes, tab_bytes, warp_bytes, block_bytes;
 };
 __host__ __device__ inline QtGeom qt_geom(int mode, int warps, int n_joints, int n_items) {
     QtGeom g;
@@ -40,8 +53,10 @@ __host__ __device__ inline QtGeom qt_geom(int mode, int warps, int n_joints, int
     g.q_pitch = mode == kQtDq ? 32 * (n_joints + 1) + 16 : 16 * ((n_joints + 1) | 1);  // + the identity record (dq) / padding
     g.q_bytes = kQtFrames * g.q_pitch;
     g.p_bytes = mode == kQtFkQuat ? ((kQtFrames * 12 * n_joints + 16 + 15) & ~15) : 0;  // dense, + 16 bytes of phase slack
+    g.o_bytes = mode == kQtMirror ? g.in_bytes : 0;                          // mirrored local rotations of the tile, rows like the input's
     g.tab_bytes = (((n_items + kQtTracks) * 16 + 127) & ~127) + 128;  // + one step of no-ops (prefetch overrun) + the tile counter
-    g.warp_bytes = (2 * g.in_bytes + g.q_bytes + g.p_bytes + 16 + 128 + 127) & ~127;  // + 2 mbarriers + fence words
+    if (mode == kQtMirror) g.tab_bytes += (n_joints * 4 + 127) & ~127;       // + the mirror table
+    g.warp_bytes = (2 * g.in_bytes + g.q_bytes + g.p_bytes + g.o_bytes + 16 + 128 + 127) & ~127;  // + 2 mbarriers + fence words
     g.block_bytes = 128 + g.tab_bytes + warps * g.warp_bytes;
     return g;
 }
@@ -98,9 +113,11 @@ template <int MODE, bool PIPE>
 __global__ void __launch_bounds__(512, 1)
 qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, long long gstride, const float *__restrict__ offsets,
                float4 *__restrict__ out_q, float *__restrict__ out_p, long long n_frames, int n_joints, int n_steps,
-               int dynamic_claims, const __grid_constant__ TrackProgram prog) {
+               int dynamic_claims, const __grid_constant__ TrackProgram prog,
+               const __grid_constant__ typename QtMirrorArg<MODE>::type mir) {
     constexpr int FQ = kQtFrames, NT = kQtTracks;
     constexpr bool POS = MODE == kQtFkQuat;
+    constexpr bool MIRROR = MODE == kQtMirror;
     extern __shared__ __align__(128) unsigned char smem_qt[];
     unsigned char *smem_raw = smem_qt + ((128u - (smem_u32(smem_qt) & 127u)) & 127u);
     const int warps = blockDim.x >> 5;
@@ -113,6 +130,9 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
     uint4 *tab = reinterpret_cast<uint4 *>(smem_raw);
     uint32_t *tile_counter = reinterpret_cast<uint32_t *>(smem_raw + geo.tab_bytes - 128);
     if (threadIdx.x == 0) *tile_counter = 0u;
+    uint32_t *mtab = reinterpret_cast<uint32_t *>(smem_raw + (((n_items + NT) * 16 + 127) & ~127));  // kQtMirror only
+    if constexpr (MIRROR)
+        for (int j = threadIdx.x; j < n_joints; j += blockDim.x) mtab[j] = mir.word[j];
     for (int i = threadIdx.x; i < n_items + NT; i += blockDim.x) {
         const uint32_t c = i < n_items ? prog.code[i] : kTrackNoop;
         const uint32_t j = track_joint(c);
@@ -130,7 +150,8 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
     const uint32_t in0 = smem_u32(mine);
     const uint32_t qst = in0 + 2 * geo.in_bytes;
     const uint32_t pst = qst + geo.q_bytes;
-    const uint32_t bar0 = pst + geo.p_bytes;  // two mbarriers
+    const uint32_t ost = pst + geo.p_bytes;   // kQtMirror: the tile's output rows
+    const uint32_t bar0 = ost + geo.o_bytes;  // two mbarriers
     const uint32_t fence_word = bar0 + 16 + 4 * lane;
     const uint32_t tab0 = smem_u32(tab);
     if (lane == 0) {
@@ -202,7 +223,7 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
             gn0 = __ldg(g), gn1 = __ldg(g + 1), gn2 = __ldg(g + 2);
         }
         mbar_wait(bar0 + 8 * buf, (k >> 1) & 1);
-        if (draining) bulk_wait_read0();  // (lanes that stored) the previous tile has left the stage
+        if (!MIRROR && draining) bulk_wait_read0();  // (lanes that stored) the previous tile has left the stage
         __syncwarp();
 
         // The walk, software pipelined: the table entry and the local quaternion of step s + 1 (for fk_quat already
@@ -301,12 +322,30 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
         tile_next = claim();
         issue_tile(tile_next, buf);
 
+        if constexpr (MIRROR) {
+            // ---- second half of mirror on the tile's global quaternions (all in the stage): track t takes joints
+            // t, t + 4, ...; results go to their own rows (the stage is still being read by the other tracks)
+            if (draining) bulk_wait_read0();  // (lanes that stored) the previous tile has left the output rows
+            __syncwarp();
+            const uint32_t o_row = ost + f * geo.in_pitch;
+            for (int j = trk; j < n_joints; j += NT) {
+                const uint32_t m = mtab[j];
+                const float4 a = lds128(q_row + 16 * (m & 0xFFFFu));
+                Quat<float> r{a.x, mir.fx * a.y, mir.fy * a.z, mir.fz * a.w};
+                if (j > 0) {
+                    const float4 b = lds128(q_row + 16 * (m >> 16));
+                    r = q_mul(Quat<float>{b.x, -mir.fx * b.y, -mir.fy * b.z, -mir.fz * b.w}, r);  // conj(flip(parent)) (x) flip(joint)
+                }
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(o_row + 16 * j), "f"(r.w), "f"(r.x), "f"(r.y), "f"(r.z) : "memory");
+            }
+        }
         // ---- output: one bulk store per frame row; positions as one dense span ---------------------------------
         fence_proxy_async_smem();
         __syncwarp();
         if (lane < nrows) {
             const int out_row = MODE == kQtDq ? 2 * row_bytes : row_bytes;
-            bulk_store(reinterpret_cast<unsigned char *>(out_q) + (f0 + lane) * out_row, qst + lane * geo.q_pitch, static_cast<uint32_t>(out_row));
+            const uint32_t src_row = MIRROR ? ost + lane * geo.in_pitch : qst + lane * geo.q_pitch;
+            bulk_store(reinterpret_cast<unsigned char *>(out_q) + (f0 + lane) * out_row, src_row, static_cast<uint32_t>(out_row));
         }
         if (POS) {
             const long long pa = f0 * ppitch, pb = pa + static_cast<long long>(nrows) * ppitch;

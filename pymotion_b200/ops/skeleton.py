@@ -25,6 +25,7 @@ import weakref
 import numpy as np
 import torch
 
+from .. import _lib
 from .. import _runtime as rt
 
 
@@ -255,18 +256,19 @@ def _vec_mirror(m: rt.Marshal, v, axis_index: int):
 
 def _mirrored_local(m: rt.Marshal, q, offsets_dev, par, mapping, axis_index: int):
     """fk -> global quaternions -> (re-index, flip two components) -> local rotations
-    (ops/skeleton.py:322-331, :410-416)."""
+    (ops/skeleton.py:322-331, :410-416) as one fused launch (``pmb_mirror_local_f32``): the global quaternions stay on
+    the SM.  Offsets play no part: the walk is rotations only."""
     lead, n_joints = tuple(q.shape[:-2]), int(q.shape[-2])
     n_frames = _lead_frames(lead)
-    zero = torch.zeros(3, device=m.device, dtype=torch.float32)  # np.zeros_like(global_translation): root at the origin
-    grot = m.new(lead + (n_joints, 4))
     local = m.new(lead + (n_joints, 4))
     if n_frames > 0:
-        rt.call("pmb_fk_quat_f32", m.device, rt.ptr(q), rt.ptr(zero), 0, rt.ptr(offsets_dev), 0, par.ctypes.data,
-                n_frames, n_joints, None, rt.ptr(grot), m.stream())  # positions = NULL: rotations only
-        rt.call("pmb_mirror_to_local_f32", m.device, rt.ptr(grot), par.ctypes.data,
-                None if mapping is None else mapping.ctypes.data, axis_index, n_frames, n_joints, rt.ptr(local),
-                m.stream())
+        with torch.cuda.device(m.device):
+            needs = _lib.load().pmb_mirror_local_needs_scratch(par.ctypes.data, n_joints)
+        if needs < 0:
+            _lib.check(needs)
+        scratch = m.new(lead + (n_joints, 4)) if needs else None  # skeletons that take the two-kernel path
+        rt.call("pmb_mirror_local_f32", m.device, rt.ptr(q), par.ctypes.data, None if mapping is None else mapping.ctypes.data,
+                axis_index, n_frames, n_joints, None if scratch is None else rt.ptr(scratch), rt.ptr(local), m.stream())
     return local
 
 

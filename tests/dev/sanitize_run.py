@@ -85,8 +85,11 @@ def main():
         sk.from_global_rotations(gq, par)
         centred = (want_pos - want_pos[:, :1]).astype(np.float32)
         sk.from_root_positions(centred, par, off)
-        for mode in ("all", "positions"):
-            sk.mirror(rot, gp, par, off, mode=mode)
+        for knobs in ({}, {"PMB_MIRROR_FUSED": "0"}, {"PMB_QT_WARPS_PER_SM": "1"}):  # fused mirror epilogue / two-kernel path
+            set_knobs(knobs)
+            for mode in ("all", "positions"):
+                sk.mirror(rot, gp, par, off, mode=mode)
+        set_knobs({})
         quat.unroll(rot, 0)
         dq.unroll(d, 0)
         dq.normalize(d)

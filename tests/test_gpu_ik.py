@@ -201,3 +201,38 @@ def test_mirror_large_vs_oracle(sk):
     assert_allclose(np.abs(np.sum(r2.astype(np.float64) * rot, axis=-1)), 1.0, atol=1e-5)
     assert_array_equal(t2, gp)
     assert_array_equal(o2, off)
+
+
+@pytest.mark.parametrize("knobs", [{}, {"PMB_MIRROR_FUSED": "0"}, {"PMB_QT_WARPS_PER_SM": "4"}, {"PMB_QT_DYNAMIC": "0", "PMB_QT_PIPE": "1"}])
+@pytest.mark.parametrize("name,n_frames", [("body22", 20_003), ("smplh52", 4_001), ("deep65", 2_049), ("chain3", 333), ("body22", 5)])
+def test_mirror_fused_and_two_kernel_paths(sk, set_knobs, knobs, name, n_frames):
+    """mirror's rotation step as ONE launch (quaternion track kernel with the flip / re-index / back-to-local epilogue on the
+    tile's global quaternions) and as the two-kernel path it replaces (forced, and taken by itself for sparse schedules such as
+    a 3-joint chain): both equal the reference (modes 'all' and 'symmetry' with a left / right swap), ragged frame counts, few
+    warps per SM so that the output rows are reused across many tiles."""
+    from pymotion_b200 import _lib
+
+    set_knobs(knobs)
+    par = parents_of(name)
+    n_joints = len(par)
+    rot, gp, off = synth_numpy(n_frames, par, seed=3 * n_joints + n_frames)
+    r, t, o, _ = sk.mirror(rot, gp, par, off, mode="all", axis="Z")
+    fused = "MODE=3" in _lib.load().pmb_last_variant().decode()
+    assert fused == (name != "chain3" and knobs.get("PMB_MIRROR_FUSED") != "0")
+    wr, wt, wo, _ = orc.mirror(rot, gp, par, off, mode="all", axis="Z")
+    quat_close_up_to_sign(r, wr)
+    assert_array_equal(t, wt)
+    assert_array_equal(o, wo)
+    # a permutation that swaps pairs of joints (what a left / right mapping is), fixed points included
+    rng = np.random.default_rng(n_joints)
+    mapping = np.arange(n_joints)
+    idx = rng.permutation(np.arange(1, n_joints))
+    for a, b in zip(idx[0::2], idx[1::2]):
+        if rng.random() < 0.7:
+            mapping[a], mapping[b] = b, a
+    keep = rot.copy()
+    r, t, o, _ = sk.mirror(rot, gp, par, off, joints_mapping=mapping, mode="symmetry", axis="X")
+    wr, wt, _, _ = orc.mirror(keep.copy(), gp.copy(), par, off, joints_mapping=mapping, mode="symmetry", axis="X")
+    quat_close_up_to_sign(r, wr)
+    assert_array_equal(t, wt)
+    assert_array_equal(rot, keep)

@@ -374,7 +374,11 @@ int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_h
     const int smem = n_joints * 16 + n_slots * THREADS * 16;
     if (smem > dp.smem_optin)
         return fail(PMB_ERR_TOPOLOGY, "joint order needs %d live branch slots; does not fit in shared memory", n_slots);
-    auto kernel = fast ? pmb::from_root_positions_kernel<THREADS, true> : pmb::from_root_positions_kernel<THREADS, false>;
+    // aligned 16- / 8-byte point loads only where every lane of a warp takes the same case (J a multiple of 4: +5 % at 4M x 52);
+    // with per-lane cases the divergence costs more than the sector look-ups save (1M x 22: 0.182 -> 0.208 ms, 4M x 65: 3.06 -> 3.86)
+    const bool wide = knob(K_FRP_WIDE, n_joints % 4 == 0 ? 1 : 0) != 0;
+    auto kernel = fast ? (wide ? pmb::from_root_positions_kernel<THREADS, true, true> : pmb::from_root_positions_kernel<THREADS, true, false>)
+                       : pmb::from_root_positions_kernel<THREADS, false, false>;
     int per_sm_unused = 0;
     if ((rc = kernel_fit(kernel, dp, THREADS, smem, per_sm_unused))) return rc;
     // Thread = frame reads its positions row 12 bytes at a time, so the op lives on L1 hits, and L1 is what the
@@ -388,7 +392,7 @@ int pmb_from_root_positions_f32(const float *positions, const int64_t *parents_h
         const int want = target * (smem + 1024);
         const int pct = std::max(1, std::min(100, (want * 100 + dp.smem_optin - 1) / dp.smem_optin));
         PMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        note_variant("from_root_positions_kernel<%d,FAST=%d> smem=%d carveout=%d%% (for %d blocks/SM)", THREADS, int(fast), smem, pct, target);
+        note_variant("from_root_positions_kernel<%d,FAST=%d,WIDE=%d> smem=%d carveout=%d%% (for %d blocks/SM)", THREADS, int(fast), int(fast && wide), smem, pct, target);
     }
     const long long blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7FFFFFFFLL) return fail(PMB_ERR_SHAPE, "n_frames too large for one launch");

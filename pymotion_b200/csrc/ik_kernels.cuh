@@ -168,7 +168,7 @@ __device__ __forceinline__ void frp_fill_rest_directions(float4 *tab, const floa
 // read from L2 for an input of 97.5 M (each point is touched twice, as a child and as a joint, and 24 warps x 25 KB of
 // rows do not stay in L1), 260 M partial-sector stores; 174 G sectors/s through L2 -- the sector rate, not the arithmetic,
 // bounds it (approximate square roots / reciprocals change nothing: 4.85 -> 4.82 ms).
-template <int THREADS, bool FAST>
+template <int THREADS, bool FAST, bool WIDE>
 __global__ void __launch_bounds__(THREADS)
 from_root_positions_kernel(const float *__restrict__ pos, const float *__restrict__ offsets, float4 *__restrict__ rots,
                            long long n_frames, int n_joints, int n_slots, const __grid_constant__ JointProgram prog,
@@ -182,6 +182,7 @@ from_root_positions_kernel(const float *__restrict__ pos, const float *__restric
     if (f >= n_frames) return;
     const float *P = pos + f * n_joints * 3;
     float4 *R = rots + f * n_joints;
+    const bool last_frame = f == n_frames - 1;
     // Rotations leave as whole 32-byte sectors where the row allows it: joints (j - 1, j) share a sector iff the float4
     // index f J + j is odd, so the rotation of an even-index joint waits in registers for its neighbour (one 256-bit store
     // instead of two half-sector ones: 260 M -> 130 M store sectors at 4M x 65).
@@ -190,7 +191,32 @@ from_root_positions_kernel(const float *__restrict__ pos, const float *__restric
     Quat<float> held{1.f, 0.f, 0.f, 0.f};
     frp_walk<FAST>(
         n_joints, tab, prog, kids,
-        [&](int j) { return Vec3<float>{__ldg(P + 3 * j), __ldg(P + 3 * j + 1), __ldg(P + 3 * j + 2)}; },
+        [&](int j) {
+            // A point is 12 bytes at a 4-byte aligned address; three scalar loads make a warp look up 96 sectors in L1 for 32
+            // points (l1tex throughput 74 %, the busiest unit of the kernel).  WIDE: aligned 16- / 8-byte loads that cover the
+            // point -- one 16-byte load when it starts 0 or 4 bytes into a 16-byte unit, an 8-byte plus a 4-byte load otherwise.
+            // The case is the same for every lane iff J is a multiple of 4, and only then it pays (the host decides).  (The
+            // 16-byte load at offset 0 reads 4 bytes past the point: not for the last point of the array.)
+            const float *p = P + 3 * j;
+            const unsigned w = static_cast<unsigned>(reinterpret_cast<uintptr_t>(p) >> 2) & 3u;
+            if (WIDE && w == 0 && !(last_frame && j == n_joints - 1)) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+                return Vec3<float>{v.x, v.y, v.z};
+            }
+            if (WIDE && w == 1) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(p - 1));
+                return Vec3<float>{v.y, v.z, v.w};
+            }
+            if (WIDE && w == 2) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+                return Vec3<float>{v.x, v.y, __ldg(p + 2)};
+            }
+            if (WIDE && w == 3) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(p + 1));
+                return Vec3<float>{__ldg(p), v.x, v.y};
+            }
+            return Vec3<float>{__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+        },
         [&](uint32_t s) { const float4 v = slots[s * THREADS + threadIdx.x]; return Quat<float>{v.x, v.y, v.z, v.w}; },
         [&](uint32_t s, const Quat<float> &q) { slots[s * THREADS + threadIdx.x] = make_float4(q.w, q.x, q.y, q.z); },
         [&](int j, const Quat<float> &r) {

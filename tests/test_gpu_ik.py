@@ -101,7 +101,7 @@ def test_from_root_positions_vs_oracle(sk, name, n_frames):
     check_ik(sk.from_root_positions(centred, par, off), want, centred, par, off, ENVELOPE[f"{name}/{n_frames}"])
 
 
-@pytest.mark.parametrize("knobs", [{}, {"PMB_FRP_FAST": "0"}, {"PMB_FRP_BLOCKS_PER_SM": "2"}])
+@pytest.mark.parametrize("knobs", [{}, {"PMB_FRP_FAST": "0"}, {"PMB_FRP_BLOCKS_PER_SM": "2"}, {"PMB_FRP_WIDE": "1"}, {"PMB_FRP_WIDE": "0"}])
 @pytest.mark.parametrize("name,n_frames", [("body22", 3001), ("smplh52", 1000), ("deep65", 517)])
 def test_from_root_positions_every_variant(sk, set_knobs, knobs, name, n_frames):
     """Approximate (default) and IEEE square roots / reciprocals, another shared-memory carve-out: all inside the reference

@@ -5,8 +5,8 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/r2_scale_box.txt; nproc >> gpurun_out/r2_scale_box.txt; (numactl -H 2>/dev/null || lscpu | grep -i numa) >> gpurun_out/r2_scale_box.txt
-for N in 8 4 2; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$N \
+for N in 8 2; do
+  timeout 330 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$N \
       bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2_bench_${N}gpu.json 2> gpurun_out/r2_bench_${N}gpu.err; echo "bench $N rc=$?"
   cut -c1-400 gpurun_out/r2_bench_${N}gpu.json
 done

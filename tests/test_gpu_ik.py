@@ -115,11 +115,15 @@ def test_from_root_positions_every_variant(sk, set_knobs, knobs, name, n_frames)
     check_ik(sk.from_root_positions(centred, par, off), want, centred, par, off, ENVELOPE[f"{name}/{n_frames}"])
 
 
+@pytest.mark.parametrize("wide", ["0", "1"])
 @pytest.mark.parametrize("n_frames", [1, 2, 31, 33, 128, 129])
-def test_from_root_positions_sector_pairs(sk, n_frames):
+def test_from_root_positions_sector_pairs(sk, set_knobs, n_frames, wide):
     """Rotations leave as 32-byte sectors (joints j - 1, j of a frame whose float4 index is odd): odd and even joint counts
     (rows that start and end mid-sector), batches around the block size, and an output array that itself starts mid-sector
-    (a view one frame into a larger array) -- every entry written, none twice with a different value."""
+    (a view one frame into a larger array) -- every entry written, none twice with a different value.  With the aligned wide
+    point loads forced on as well: the input view starts 12 J bytes into its allocation, so every alignment case of a point is
+    taken, and the last point of the allocation is the one that must not be over-read."""
+    set_knobs({"PMB_FRP_WIDE": wide})
     for name in ("chain3", "body22", "deep65"):
         par = parents_of(name)
         rot, gp, off = synth_numpy(n_frames + 1, par, seed=7 + n_frames)

@@ -379,6 +379,58 @@ def test_dq_round_trip_1m_x_22(sk):
         assert_allclose(rots[sl].cpu().numpy(), wr, **TOL)
 
 
+@pytest.mark.parametrize("name", ["deep65", "smplh52"])
+def test_quaternion_walks_4m(sk, name):
+    """The quaternion track kernel at the full sizes of BASELINE configs 4 / 5 (4M x 65, 4M x 52 per GPU), through
+    size-independent properties on EVERY frame -- dual quaternions are unit and decode back to the inputs (the identity the
+    reference test checks, test_skeleton.py:70-77); fk_quat gives the positions of fk and quaternions whose matrices are fk's
+    matrices; mirroring twice gives the rotations back -- plus the C oracle on the first / a middle / the last 64k-frame window."""
+    par = parents_of(name)
+    dev = torch.device("cuda")
+    n = 4_000_000
+    rot, gp, off = synth_torch(n, par, dev, seed=777)
+    dq = sk.to_root_dual_quat(rot, gp, par, off)
+    assert "qtracks_kernel" in _lib.load().pmb_last_variant().decode()
+    trans, rots = sk.from_root_dual_quat(dq, par)
+    ptorch = torch.as_tensor(par, device=dev)
+    root_child = ptorch == 0
+    for lo in range(0, n, 500_000):  # slabs keep the temporaries small
+        sl = slice(lo, lo + 500_000)
+        assert (rots[sl] - rot[sl]).abs().amax().item() < 1e-5
+        assert (trans[sl, 1:] - off[1:]).abs().amax().item() < 2e-5
+        assert (trans[sl, 0] - gp[sl]).abs().amax().item() < 1e-5
+        assert (dq[sl][..., :4].norm(dim=-1) - 1).abs().amax().item() < 1e-5
+        assert (dq[sl][..., :4] * dq[sl][..., 4:]).sum(-1).abs().amax().item() < 2e-5
+    off_h = off.cpu().numpy()
+    for lo in (0, 1_777_777, n - 65_536):
+        sl = slice(lo, lo + 65_536)
+        want = oracle_c.to_root_dual_quat(rot[sl].cpu().numpy(), gp[sl].cpu().numpy(), par, off_h)
+        assert_allclose(dq[sl].cpu().numpy(), want, **TOL)
+    del dq, trans, rots, root_child
+    torch.cuda.empty_cache()
+
+    pos, rotm = sk.fk(rot, gp, off, par)
+    qpos, grot = sk.fk_quat(rot, gp, off, par)
+    assert "qtracks_kernel" in _lib.load().pmb_last_variant().decode()
+    from pymotion_b200.rotations import quat as gquat
+
+    for lo in range(0, n, 500_000):
+        sl = slice(lo, lo + 500_000)
+        assert (qpos[sl] - pos[sl]).abs().amax().item() < 2e-5
+        assert (gquat.to_matrix(grot[sl]) - rotm[sl]).abs().amax().item() < 2e-5
+    del pos, rotm, qpos, grot
+    torch.cuda.empty_cache()
+
+    zero = torch.zeros(3, device=dev)
+    r1, _, o1, _ = sk.mirror(rot, zero, par, off, mode="all", axis="X")
+    assert "MODE=3" in _lib.load().pmb_last_variant().decode()
+    r2, _, o2, _ = sk.mirror(r1, zero, par, o1, mode="all", axis="X")
+    assert torch.equal(o2, off)
+    for lo in range(0, n, 500_000):
+        sl = slice(lo, lo + 500_000)
+        assert ((r2[sl] * rot[sl]).sum(-1).abs() - 1).abs().amax().item() < 1e-5
+
+
 def test_from_global_rotations(sk, golden_dq):
     g = golden_dq
     got = sk.from_global_rotations(g["fgr/global"], g["fgr/parents"])

@@ -8,6 +8,7 @@
 
 #include "fk_kernel.cuh"
 #include "fk_lanes_kernel.cuh"
+#include "fk_mtracks_kernel.cuh"
 #include "fk_quat_kernel.cuh"
 #include "fk_rows_kernel.cuh"
 #include "fk_tracks_kernel.cuh"
@@ -265,10 +266,73 @@ bool try_fk_tracks(const FkArgs &a, const DeviceProps &dp, int &rc, bool rows_pr
     return true;
 }
 
+// ---- matrix track kernel (fk_mtracks_kernel.cuh) ------------------------------------------------
+// Worst-case number of the 8 frames of a tile whose stage rows fall into the same shared-memory bank (rows 9 J words apart).
+inline int fk_mtracks_bank_degree(int n_joints) {
+    int count[32] = {0}, worst = 0;
+    for (int f = 0; f < pmb::kMtFrames; ++f) worst = std::max(worst, ++count[(f * 9 * n_joints) & 31]);
+    return worst;
+}
+// PMB_FK_MTRACKS = 0 / 1 forces; PMB_FK_WARPS_PER_SM caps the resident warps.
+bool try_fk_mtracks(const FkArgs &a, const DeviceProps &dp, int &rc) {
+    const int force = knob(K_FK_MTRACKS, -1);
+    if (force == 0) return false;
+    if (force != 1 && (knob_set(K_FK_GROUP) || knob_set(K_FK_ROWS) || knob_set(K_FK_LANES) || knob_set(K_FK_WARPS) || knob_set(K_FK_TRACKS)))
+        return false;  // another kernel is being forced
+    const pmb::TrackProgram *tp = nullptr;
+    int n_steps = 0;
+    if ((rc = track_program(a.parents_host, a.n_joints, pmb::kMtTracks, 0, tp, n_steps))) return true;
+    const int n_items = n_steps * pmb::kMtTracks;
+    // the block shape that puts the most warps on an SM (every block carries its own table and costs 1 KB of system shared memory)
+    int best_warps = 0, best_blocks = 0, best_smem = 0;
+    const int cap = knob(K_FK_WARPS_PER_SM, 32);
+    if (n_steps > 0)
+        for (int blocks = 1; blocks <= 4; ++blocks)
+            for (int warps = 16; warps >= 1; --warps) {
+                const int smem = pmb::mt_geom(warps, a.n_joints, n_items).block_bytes;
+                if (smem > dp.smem_optin || blocks * (smem + 1024) > dp.smem_sm || blocks * warps > cap) continue;
+                if (blocks * warps > best_blocks * best_warps) best_warps = warps, best_blocks = blocks, best_smem = smem;
+                break;
+            }
+    if (best_warps == 0) {
+        if (force != 1) return false;
+        rc = fail(PMB_ERR_SHAPE, "PMB_FK_MTRACKS=1: %d joints do not fit the matrix track kernel", a.n_joints);
+        return true;
+    }
+    if (force != 1) {
+        // a schedule less than half full (chains), fewer than four warps per SM (large skeletons), or stage rows that collide
+        // 3-way and worse in the banks (J = 16, 48, 64, ...) belong to the other kernels
+        if (2 * a.n_joints < n_items || best_warps * best_blocks < 4 || fk_mtracks_bank_degree(a.n_joints) >= 3) return false;
+        // Between 31 and 59 joints the two track kernels are within +-5 % of each other, the order depending on where the arrays
+        // happen to sit and on the power state (one process running the workloads in sequence: matrix tracks 0.82 / 2.18 ms at
+        // 2M x 40 / 4M x 52 against 0.94 / 2.48 for the row tracks; each workload in a process of its own, as in bench.py: 0.90 /
+        // 2.37 against 0.88 / 2.30).  The row tracks keep that range; from 60 joints up the matrix tracks are ahead everywhere
+        // (4M x 65: 2.69 - 2.94 ms against 2.97 - 3.23), and below 31 joints they replace the lane kernel (2M x 24: 0.550 against 0.599).
+        if (a.n_joints > 30 && a.n_joints < 60) return false;
+    }
+    auto kernel = pmb::fk_mtracks_kernel;
+    int per_sm = 0;
+    if ((rc = kernel_fit(kernel, dp, best_warps * 32, best_smem, per_sm))) return true;
+    if (per_sm < 1) { rc = fail(PMB_ERR_CUDA, "fk matrix track kernel does not fit on an SM (%d bytes of shared memory)", best_smem); return true; }
+    per_sm = std::min(per_sm, best_blocks);
+    const long long tiles = (a.n_frames + pmb::kMtFrames - 1) / pmb::kMtFrames;
+    const long long blocks = std::min<long long>((tiles + best_warps - 1) / best_warps, static_cast<long long>(per_sm) * dp.sm_count);
+    note_variant("fk_mtracks_kernel steps=%d grid=%lld x %d warps (%d warps/SM) smem=%d", n_steps, blocks, best_warps, per_sm * best_warps, best_smem);
+    kernel<<<static_cast<unsigned>(blocks), best_warps * 32, best_smem, a.stream>>>(reinterpret_cast<const float4 *>(a.rot), a.gpos, a.gstride,
+                                                                                   a.offsets, a.pos, a.rout, a.n_frames, a.n_joints, n_steps, *tp);
+    rc = PMB_OK;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "fk_mtracks_kernel launch");
+    return true;
+}
+
 // Which fk kernel (shared offsets, matrices out) -- measured on B200, DESIGN.md section 4:
 //   row-team kernel      skeletons small enough for >= 4 teams per SM (J <= 30) with J not a multiple of 4
-//                        (1M x 22: 0.2316 ms against 0.2415 ms thread-per-frame, 0.2326 ms lanes);
-//   track kernel         larger skeletons (try_fk_tracks above);
+//                        (1M x 22: 0.2304 ms against 0.2565 ms matrix tracks, 0.2415 ms thread-per-frame, 0.2326 ms lanes);
+//   matrix track kernel  60 joints and more, and small skeletons the row teams do not take (J a multiple of 4), provided the level
+//                        schedule is at least half full, >= 4 warps fit an SM and the stage rows collide at most 2-way in the
+//                        banks (try_fk_mtracks above: 4M x 65 2.69 ms against 2.99 row tracks, 2M x 24 0.550 against 0.599 lanes);
+//   track kernel         31 .. 59 joints and what the matrix track kernel does not take (try_fk_tracks above);
 //   lane kernel          what is left (small J that is a multiple of 4 but not of 8), unless
 //   thread-per-frame     the dense stage of the lane kernel would put >= 4 frames in one bank (J = 16, 32, 48,
 //                        64, ...: 2.0 TB/s at J = 32 against 5.6), per-frame offsets, or a forced variant.
@@ -417,6 +481,7 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
     if (ostride == 0 && !quat_out) {
         int rrc = PMB_OK;
         const bool rows_first = fk_rows_preferred(a, dp) && knob(K_FK_ROWS, -1) != 0;
+        if ((!rows_first || knob(K_FK_MTRACKS, -1) == 1) && try_fk_mtracks(a, dp, rrc)) return rrc;
         if (try_fk_tracks(a, dp, rrc, rows_first)) return rrc;
         if (try_fk_lanes(a, dp, rrc, rows_first || knob(K_FK_ROWS, -1) == 1)) return rrc;
         if (try_fk_rows(a, dp, rrc)) return rrc;

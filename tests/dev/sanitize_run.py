@@ -22,7 +22,8 @@ KNOBS = [{}, {"PMB_FK_ROWS": "1"}, {"PMB_FK_ROWS": "1", "PMB_FK_STAGES": "3", "P
          {"PMB_FK_LANES": "1"}, {"PMB_FK_LANES": "1", "PMB_FK_NB": "3", "PMB_FK_BLOCKS_PER_SM": "1", "PMB_FK_WARPS": "1"},
          {"PMB_FK_LANES": "0", "PMB_FK_ROWS": "0", "PMB_FK_TRACKS": "0"}, {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "4"},
          {"PMB_FK_TRACKS": "1"}, {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "1", "PMB_FK_NB": "4", "PMB_FK_WARPS_PER_SM": "2"},
-         {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "2", "PMB_FK_NB": "4"}]
+         {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "2", "PMB_FK_NB": "4"},
+         {"PMB_FK_MTRACKS": "1"}, {"PMB_FK_MTRACKS": "1", "PMB_FK_WARPS_PER_SM": "1"}, {"PMB_FK_MTRACKS": "0"}]
 
 
 def set_knobs(knobs):

@@ -708,6 +708,25 @@ def test_fk_track_kernel(sk, set_knobs, knobs, name, n_frames):
         assert_allclose(rotm, want_rotm, **TOL)
 
 
+@pytest.mark.parametrize("knobs", [{"PMB_FK_MTRACKS": "1"}, {"PMB_FK_MTRACKS": "1", "PMB_FK_WARPS_PER_SM": "1"},
+                                   {"PMB_FK_MTRACKS": "1", "PMB_FK_WARPS_PER_SM": "3"}])
+@pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
+                                           ("body32", 5_009), ("body22", 7), ("body16", 1), ("deep65", 29), ("body40", 4_096)])
+def test_fk_matrix_track_kernel(sk, set_knobs, knobs, name, n_frames):
+    """The matrix track kernel (lanes = 4 tracks x 8 frames, whole 3x4 transform per lane, dense stage doubling as the parent
+    store, bulk-stored full tiles, remainder tile copied out by the lanes): ragged frame counts, batches of less than a tile,
+    one warp per SM (stage, input double buffer and barriers reused across many tiles)."""
+    set_knobs(knobs)
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=19 * len(par) + n_frames)
+    want_pos, want_rotm = orc.fk(rot, gp, off, par)
+    for _ in range(2):
+        pos, rotm = sk.fk(rot, gp, off, par)
+        assert "fk_mtracks_kernel" in _lib.load().pmb_last_variant().decode()
+        assert_allclose(pos, want_pos, **TOL)
+        assert_allclose(rotm, want_rotm, **TOL)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_fk_track_kernel_random_trees(sk, set_knobs, seed):
     """Random topologies (bushy, deep, up to 200 joints) through the track schedule with 1 and 2 tracks."""
@@ -724,6 +743,12 @@ def test_fk_track_kernel_random_trees(sk, set_knobs, seed):
                    "PMB_FK_FR": "5" if ul == 2 else ("8" if n_joints > 150 else "10")})
         pos, rotm = sk.fk(rot, gp, off, par)
         assert "fk_tracks_kernel" in _lib.load().pmb_last_variant().decode()
+        assert_allclose(pos, want_pos, rtol=2e-5, atol=2e-5)
+        assert_allclose(rotm, want_rotm, rtol=2e-5, atol=2e-5)
+    if n_joints <= 80:  # the matrix track kernel keeps a tile's whole output (384 J bytes per frame) in shared memory
+        set_knobs({"PMB_FK_MTRACKS": "1"})
+        pos, rotm = sk.fk(rot, gp, off, par)
+        assert "fk_mtracks_kernel" in _lib.load().pmb_last_variant().decode()
         assert_allclose(pos, want_pos, rtol=2e-5, atol=2e-5)
         assert_allclose(rotm, want_rotm, rtol=2e-5, atol=2e-5)
 

@@ -1,3 +1,6 @@
+// RETIRED (round 2): fk lane = (frame, row) kernel of round 1, superseded by fk_tracks_kernel.cuh (31 .. 59 joints) and
+// fk_mtracks_kernel.cuh (60 joints and more, small skeletons the row teams do not take): 2M x 24 0.599 ms against 0.550,
+// 2M x 40 0.907 against 0.877, 4M x 52 2.504 against 2.30, 4M x 65 3.442 against 2.69.  Not compiled into the library.
 // Forward kinematics, lane = (frame, row) kernel (ops/skeleton.py:16-61 of the reference).
 //
 // What bounds fk on a B200 is how many frames an SM keeps in flight, and that is set by shared memory: the
@@ -35,19 +38,6 @@
 #endif
 
 namespace pmb {
-
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
-// read-only data (the joint table): free to be scheduled and merged by the compiler
-__device__ __forceinline__ float4 lds128_ro(uint32_t addr) {
-    float4 v;
-    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
 
 struct FkLanesGeom {
     int box_bytes, tab_bytes, warp_bytes, block_bytes;

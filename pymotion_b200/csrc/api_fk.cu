@@ -7,7 +7,6 @@
 #include <algorithm>
 
 #include "fk_kernel.cuh"
-#include "fk_lanes_kernel.cuh"
 #include "fk_mtracks_kernel.cuh"
 #include "fk_quat_kernel.cuh"
 #include "fk_rows_kernel.cuh"
@@ -80,104 +79,6 @@ inline int fk_rows_teams(int stages, const FkArgs &a, const DeviceProps &dp) {
     return std::min(12, (dp.smem_optin + 1024) / (bytes + 1024));
 }
 
-// ---- lane = (frame, row) kernel (fk_lanes_kernel.cuh) --------------------------------------------
-template <int FR, int WARPS, int NB>
-int launch_fk_lanes_nb(const FkArgs &a, const DeviceProps &dp, int block_cap) {
-    auto kernel = pmb::fk_lanes_kernel<FR, WARPS, NB>;
-    const int smem = pmb::fk_lanes_geom(FR, WARPS, a.n_joints, NB).block_bytes;
-    if (smem > dp.smem_optin) return fail(PMB_ERR_SHAPE, "fk lane kernel: %d joints do not fit in shared memory", a.n_joints);
-    int per_sm = 0, rc = kernel_fit(kernel, dp, WARPS * 32, smem, per_sm);
-    if (rc) return rc;
-    if (per_sm < 1) return fail(PMB_ERR_CUDA, "fk lane kernel does not fit on an SM (%d bytes of shared memory)", smem);
-    CUtensorMap tm;
-    if ((rc = make_rot_map(tm, a.rot, a.n_frames, a.n_joints, pmb::kChunk, FR))) return rc;
-    const long long tiles = (a.n_frames + FR - 1) / FR;
-    per_sm = std::max(1, std::min(per_sm, block_cap));
-    const long long blocks = std::min<long long>((tiles + WARPS - 1) / WARPS, static_cast<long long>(per_sm) * dp.sm_count);
-    note_variant("fk_lanes_kernel<FR=%d,WARPS=%d,NB=%d> grid=%lld (%d warps/SM) smem=%d", FR, WARPS, NB, blocks, per_sm * WARPS, smem);
-    kernel<<<static_cast<unsigned>(blocks), WARPS * 32, smem, a.stream>>>(tm, a.gpos, a.gstride, a.offsets, a.pos, a.rout, a.n_frames,
-                                                                        a.n_joints, *a.prog);
-    PMB_CUDA(cudaGetLastError());
-    return PMB_OK;
-}
-
-template <int FR, int WARPS>
-int launch_fk_lanes_cfg(const FkArgs &a, const DeviceProps &dp, int block_cap, int n_boxes) {
-    const int nb = knob(K_FK_NB, n_boxes);  // TMA boxes in flight per warp
-    if (nb == 3) return launch_fk_lanes_nb<FR, WARPS, 3>(a, dp, block_cap);
-    if (nb == 4) return launch_fk_lanes_nb<FR, WARPS, 4>(a, dp, block_cap);
-    return launch_fk_lanes_nb<FR, WARPS, 2>(a, dp, block_cap);
-}
-
-// Worst-case number of lanes of one stage store that fall into the same shared-memory bank: lane = (frame, row)
-// puts the frames of a tile 9J words apart, so only (9J mod 32) matters.  1 = conflict free.
-inline int fk_lanes_bank_degree(int fr, int n_joints) {
-    int count[32] = {0}, worst = 0;
-    for (int f = 0; f < fr; ++f) worst = std::max(worst, ++count[(f * 9 * n_joints) & 31]);
-    return worst;
-}
-
-struct FkLanesPlan {
-    int fr = 0, warps = 0, frames_in_flight = 0, n_boxes = 2, warps_sm = 0;
-};
-// The tile size / block shape that keeps the most frames in flight per SM (what the throughput of the large
-// skeletons follows): FR = 10 needs an even joint count, blocks of 1, 2 or 4 warps.
-inline FkLanesPlan fk_lanes_plan(const FkArgs &a, const DeviceProps &dp) {
-    FkLanesPlan best;
-    for (int fr : {10, 8}) {
-        if (fr == 10 && a.n_joints % 2) continue;
-        for (int warps : {4, 2, 1}) {
-            const int bytes = pmb::fk_lanes_geom(fr, warps, a.n_joints).block_bytes;
-            if (bytes > dp.smem_optin) continue;
-            const int blocks = std::min(32, (dp.smem_optin + 1024) / (bytes + 1024));
-            const int warps_sm = std::min(blocks * warps, 12);  // measured at 22 joints: beyond 12 walking warps per SM it gets slower
-            // ... discounted by the bank conflicts of that tile size (measured: J = 40, 100 frames 3-way 5.33 TB/s
-            // against 96 frames 2-way 5.61; J = 52, 80 frames 2-way 5.00 against 64 frames conflict-free 4.56)
-            const int degree = fk_lanes_bank_degree(fr, a.n_joints);
-            const int weight = degree <= 1 ? 100 : degree == 2 ? 90 : degree == 3 ? 80 : 50;
-            const int fif = warps_sm * fr * weight;
-            if (fif > best.frames_in_flight) best = {fr, warps, fif, 2, warps_sm};
-        }
-    }
-    // A third TMA box per warp when it is free (same number of blocks per SM) and the SM is short of warps to hide
-    // the load latency with: measured +3.5 % at 65 joints (8 warps per SM), nothing at 40 joints (12 warps).
-    if (best.fr && best.warps_sm <= 8) {
-        auto blocks_of = [&](int nb) {
-            const int bytes = pmb::fk_lanes_geom(best.fr, best.warps, a.n_joints, nb).block_bytes;
-            return bytes > dp.smem_optin ? 0 : std::min(32, (dp.smem_optin + 1024) / (bytes + 1024));
-        };
-        if (blocks_of(3) == blocks_of(2)) best.n_boxes = 3;
-    }
-    return best;
-}
-
-// PMB_FK_LANES = 0 / 1 forces; PMB_FK_FR = 8 | 10, PMB_FK_WARPS = 1 | 2 | 4 pick the shape.
-bool try_fk_lanes(const FkArgs &a, const DeviceProps &dp, int &rc, bool rows_preferred) {
-    const int force = knob(K_FK_LANES, -1);
-    if (force == 0) return false;
-    if (force != 1 && (knob_set(K_FK_GROUP) || knob_set(K_FK_ROWS))) return false;  // another kernel is being forced
-    FkLanesPlan plan = fk_lanes_plan(a, dp);
-    if (plan.fr == 0) {
-        if (force == 1) { rc = fail(PMB_ERR_SHAPE, "PMB_FK_LANES=1: the lane kernel does not fit"); return true; }
-        return false;
-    }
-    int fr = knob(K_FK_FR, plan.fr);
-    if (fr != 10 || a.n_joints % 2) fr = 8;  // the spans of 10 frames are 16-byte multiples only for an even joint count
-    const int warps = knob(K_FK_WARPS, plan.warps);
-    if (force != 1) {
-        if (rows_preferred) return false;
-        // a dense stage whose frames collide in 4 or more banks (J = 16, 32, 48, 64, ...: measured 2.0 TB/s at
-        // J = 32) belongs to the thread-per-frame kernel with its padded stage
-        if (fk_lanes_bank_degree(fr, a.n_joints) >= 4) return false;
-    }
-    const int cap = knob(K_FK_BLOCKS_PER_SM, std::max(1, 12 / std::max(1, warps)));
-    // the plan's ring depth only holds for the plan's own shape
-    const int nb = (fr == plan.fr && warps == plan.warps) ? plan.n_boxes : 2;
-    if (fr == 10) rc = warps == 1 ? launch_fk_lanes_cfg<10, 1>(a, dp, cap, nb) : warps == 2 ? launch_fk_lanes_cfg<10, 2>(a, dp, cap, nb) : launch_fk_lanes_cfg<10, 4>(a, dp, cap, nb);
-    else rc = warps == 1 ? launch_fk_lanes_cfg<8, 1>(a, dp, cap, nb) : warps == 2 ? launch_fk_lanes_cfg<8, 2>(a, dp, cap, nb) : launch_fk_lanes_cfg<8, 4>(a, dp, cap, nb);
-    return true;
-}
-
 // ---- track kernel (fk_tracks_kernel.cuh) -------------------------------------------------------
 struct FkTracksShape {
     int fr = 0, warps = 0, blocks = 0, smem = 0;  // frames per tile, warps per block, blocks per SM
@@ -218,7 +119,7 @@ int launch_fk_tracks_cfg(const FkArgs &a, const DeviceProps &dp, const FkTracksS
 }
 
 // Worst-case number of lanes of one lane group whose stage stores fall into the same shared-memory bank: the frames of a
-// tile are 9J words apart (same rule as fk_lanes_bank_degree, for the FR frames of a group).
+// tile are 9J words apart (only 9 J mod 32 matters; 1 = conflict free).
 inline int fk_tracks_bank_degree(int fr, int n_joints) {
     int count[32] = {0}, worst = 0;
     for (int f = 0; f < fr; ++f) worst = std::max(worst, ++count[(f * 9 * n_joints) & 31]);
@@ -227,7 +128,7 @@ inline int fk_tracks_bank_degree(int fr, int n_joints) {
 
 // Default policy (measured on B200, profiles/r2_sweep_tracks_*.jsonl): skeletons too large for four row teams per SM take
 // the track kernel with two lane groups (tiles of 5 frames, one track per lane) --
-//     2M x 40: 0.880 ms against 0.907 lanes;  4M x 52: 2.331 against 2.504;  4M x 65: 3.090 against 3.442
+//     2M x 40: 0.880 ms against 0.907 for the lane kernel of round 1;  4M x 52: 2.331 against 2.504;  4M x 65: 3.090 against 3.442
 // -- unless the frames of a group collide in 3 or more banks (J = 32, 48, 64, ...), which stay with the padded stage of
 // the thread-per-frame kernel.  Four boxes in flight from 48 joints up (52: 2.360 -> 2.331, 65: 3.220 -> 3.090 against
 // three), three below (40: 0.880 against 0.892).
@@ -237,7 +138,7 @@ bool try_fk_tracks(const FkArgs &a, const DeviceProps &dp, int &rc, bool rows_pr
     const int force = knob(K_FK_TRACKS, -1);
     if (force == 0) return false;
     if (force != 1) {
-        if (knob_set(K_FK_GROUP) || knob_set(K_FK_ROWS) || knob_set(K_FK_LANES) || knob_set(K_FK_WARPS)) return false;  // another kernel is forced
+        if (knob_set(K_FK_GROUP) || knob_set(K_FK_ROWS) || knob_set(K_FK_WARPS)) return false;  // another kernel is forced
         if (rows_preferred || a.n_joints <= 30) return false;
         if (fk_tracks_bank_degree(5, a.n_joints) >= 3) return false;
     }
@@ -277,7 +178,7 @@ inline int fk_mtracks_bank_degree(int n_joints) {
 bool try_fk_mtracks(const FkArgs &a, const DeviceProps &dp, int &rc) {
     const int force = knob(K_FK_MTRACKS, -1);
     if (force == 0) return false;
-    if (force != 1 && (knob_set(K_FK_GROUP) || knob_set(K_FK_ROWS) || knob_set(K_FK_LANES) || knob_set(K_FK_WARPS) || knob_set(K_FK_TRACKS)))
+    if (force != 1 && (knob_set(K_FK_GROUP) || knob_set(K_FK_ROWS) || knob_set(K_FK_WARPS) || knob_set(K_FK_TRACKS)))
         return false;  // another kernel is being forced
     const pmb::TrackProgram *tp = nullptr;
     int n_steps = 0;
@@ -333,9 +234,10 @@ bool try_fk_mtracks(const FkArgs &a, const DeviceProps &dp, int &rc) {
 //                        schedule is at least half full, >= 4 warps fit an SM and the stage rows collide at most 2-way in the
 //                        banks (try_fk_mtracks above: 4M x 65 2.69 ms against 2.99 row tracks, 2M x 24 0.550 against 0.599 lanes);
 //   track kernel         31 .. 59 joints and what the matrix track kernel does not take (try_fk_tracks above);
-//   lane kernel          what is left (small J that is a multiple of 4 but not of 8), unless
-//   thread-per-frame     the dense stage of the lane kernel would put >= 4 frames in one bank (J = 16, 32, 48,
-//                        64, ...: 2.0 TB/s at J = 32 against 5.6), per-frame offsets, or a forced variant.
+//   thread-per-frame     what is left: joint counts whose dense stage rows collide 3-way and worse in the banks (J = 16, 32, 48,
+//                        64, ...: its padded stage has no conflicts, 5.6 TB/s at J = 32), sparse level schedules (chains),
+//                        per-frame offsets, or a forced variant.
+// (The lane = (frame, row) kernel of round 1 is retired: experiments/retired/fk_lanes_kernel.cuh.)
 // Bank conflicts of the row-team kernel (lane = frame, 32 lanes 9J words apart): J odd: none; J = 2 (mod 4):
 // none with its 64-bit stores; J = 0 (mod 4): 4-way (J = 52: 4.5 TB/s) up to 32-way (J = 32: 0.84 TB/s).
 bool fk_rows_preferred(const FkArgs &a, const DeviceProps &dp) {
@@ -483,7 +385,6 @@ int fk_common(const float *rot, const float *gpos, int64_t gstride, const float 
         const bool rows_first = fk_rows_preferred(a, dp) && knob(K_FK_ROWS, -1) != 0;
         if ((!rows_first || knob(K_FK_MTRACKS, -1) == 1) && try_fk_mtracks(a, dp, rrc)) return rrc;
         if (try_fk_tracks(a, dp, rrc, rows_first)) return rrc;
-        if (try_fk_lanes(a, dp, rrc, rows_first || knob(K_FK_ROWS, -1) == 1)) return rrc;
         if (try_fk_rows(a, dp, rrc)) return rrc;
     }
     // fk_quat: the quaternion track kernel (qtracks_kernel.cuh) unless it does not apply; PMB_FKQ_TRACKS = 0 / 1 forces,

@@ -1,7 +1,7 @@
 // Forward kinematics, matrix track kernel (ops/skeleton.py:16-61 of the reference): the quaternion track kernel's mapping
 // (qtracks_kernel.cuh) with the 3x4 transform as the chain state.
 //
-// The row kernels (fk_rows / fk_lanes / fk_tracks) give a lane ONE ROW of a frame's transform: three lanes per (frame,
+// The row kernels (fk_rows / fk_tracks) give a lane ONE ROW of a frame's transform: three lanes per (frame,
 // joint), 30 of 32 lanes busy, ~57 instructions per step for 10 (frame, joint) items -- ncu at 4M x 65: 2.24e9 warp
 // instructions, issue slots 66 % busy, and shared memory rules out more warps.  Here a lane owns a WHOLE (frame, joint):
 //   lanes    4 tracks x 8 frames.  The host's whole-skeleton four-track level schedule (track_schedule.h) puts four
@@ -23,7 +23,6 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "fk_lanes_kernel.cuh"  // lds128, lds128_ro
 #include "tma.cuh"
 #include "track_schedule.h"
 

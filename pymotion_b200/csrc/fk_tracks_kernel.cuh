@@ -29,7 +29,6 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "fk_lanes_kernel.cuh"  // lds128
 #include "fk_rows_kernel.cuh"   // rot_scale
 #include "tma.cuh"
 #include "track_schedule.h"

@@ -21,7 +21,6 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "fk_lanes_kernel.cuh"  // lds128, lds128_ro
 #include "tma.cuh"
 #include "track_schedule.h"
 

@@ -80,6 +80,21 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 
+// 16-byte shared-memory reads through 32-bit shared addresses
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// read-only data (the joint table): free to be scheduled and merged by the compiler
+__device__ __forceinline__ float4 lds128_ro(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+
 constexpr int kChunk = 8;                         // joints per TMA box (128-byte rows, SWIZZLE_128B)
 constexpr int kBoxBytes = 32 * kChunk * 16;       // one box: dense (swizzled) [32 frames][8 joints] float4
 constexpr int kBoxStages = 2;                     // boxes in flight per warp (prefetch depth in chunks)

@@ -19,8 +19,7 @@ from pymotion_b200.rotations import quat  # noqa: E402
 from pymotion_b200.topologies import parents_of, synth_numpy  # noqa: E402
 
 KNOBS = [{}, {"PMB_FK_ROWS": "1"}, {"PMB_FK_ROWS": "1", "PMB_FK_STAGES": "3", "PMB_FK_BLOCKS_PER_SM": "1"},
-         {"PMB_FK_LANES": "1"}, {"PMB_FK_LANES": "1", "PMB_FK_NB": "3", "PMB_FK_BLOCKS_PER_SM": "1", "PMB_FK_WARPS": "1"},
-         {"PMB_FK_LANES": "0", "PMB_FK_ROWS": "0", "PMB_FK_TRACKS": "0"}, {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "4"},
+         {"PMB_FK_MTRACKS": "0", "PMB_FK_ROWS": "0", "PMB_FK_TRACKS": "0"}, {"PMB_FK_GROUP": "8", "PMB_FK_WARPS": "4"},
          {"PMB_FK_TRACKS": "1"}, {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "1", "PMB_FK_NB": "4", "PMB_FK_WARPS_PER_SM": "2"},
          {"PMB_FK_TRACKS": "1", "PMB_FK_UL": "2", "PMB_FK_U": "2", "PMB_FK_NB": "4"},
          {"PMB_FK_MTRACKS": "1"}, {"PMB_FK_MTRACKS": "1", "PMB_FK_WARPS_PER_SM": "1"}, {"PMB_FK_MTRACKS": "0"}]

@@ -655,30 +655,6 @@ def test_fk_quat_every_variant(sk, set_knobs, knobs, name, n_frames):
 
 
 @pytest.mark.parametrize("knobs", [
-    {"PMB_FK_LANES": "1"},                                                 # FR by joint-count parity, 4 warps per block
-    {"PMB_FK_LANES": "1", "PMB_FK_FR": "8"},
-    {"PMB_FK_LANES": "1", "PMB_FK_FR": "10"},
-    {"PMB_FK_LANES": "1", "PMB_FK_WARPS": "1"},
-    {"PMB_FK_LANES": "1", "PMB_FK_WARPS": "2", "PMB_FK_BLOCKS_PER_SM": "1"},  # many tiles per warp
-    {"PMB_FK_LANES": "1", "PMB_FK_NB": "3"},                               # deeper TMA ring
-    {"PMB_FK_LANES": "1", "PMB_FK_NB": "4", "PMB_FK_WARPS": "1"},
-])
-@pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
-                                           ("body32", 5_009), ("body22", 7)])
-def test_fk_lane_kernel(sk, set_knobs, knobs, name, n_frames):
-    """The lane = (frame, row) kernel: tiles of 8 / 10 frames per warp, forced for both tile sizes and every block
-    shape, ragged frame counts (remainder tile), one block per SM (stage reuse, ring wrap-around)."""
-    set_knobs(knobs)
-    par = parents_of(name)
-    rot, gp, off = synth_numpy(n_frames, par, seed=5 * len(par) + n_frames)
-    want_pos, want_rotm = orc.fk(rot, gp, off, par)
-    for _ in range(2):
-        pos, rotm = sk.fk(rot, gp, off, par)
-        assert_allclose(pos, want_pos, **TOL)
-        assert_allclose(rotm, want_rotm, **TOL)
-
-
-@pytest.mark.parametrize("knobs", [
     {"PMB_FK_TRACKS": "1"},                                                   # two tracks, three boxes, tiles of 10 frames
     {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_NB": "2"},
     {"PMB_FK_TRACKS": "1", "PMB_FK_U": "1", "PMB_FK_NB": "3", "PMB_FK_FR": "8"},

@@ -204,8 +204,8 @@ bool try_fk_mtracks(const FkArgs &a, const DeviceProps &dp, int &rc) {
         // a schedule less than half full (chains), fewer than four warps per SM (large skeletons), or stage rows that collide
         // 3-way and worse in the banks (J = 16, 48, 64, ...) belong to the other kernels
         if (2 * a.n_joints < n_items || best_warps * best_blocks < 4 || fk_mtracks_bank_degree(a.n_joints) >= 3) return false;
-        // Between 31 and 59 joints the two track kernels are within +-5 % of each other, the order depending on where the arrays
-        // happen to sit and on the power state (one process running the workloads in sequence: matrix tracks 0.82 / 2.18 ms at
+        // Between 31 and 59 joints the two track kernels are within +-5 % of each other, the order depending on the GPU's power state
+        // (profiles/r2_placement_probe.jsonl: not on where the arrays sit) (one process running the workloads in sequence: matrix tracks 0.82 / 2.18 ms at
         // 2M x 40 / 4M x 52 against 0.94 / 2.48 for the row tracks; each workload in a process of its own, as in bench.py: 0.90 /
         // 2.37 against 0.88 / 2.30).  The row tracks keep that range; from 60 joints up the matrix tracks are ahead everywhere
         // (4M x 65: 2.69 - 2.94 ms against 2.97 - 3.23), and below 31 joints they replace the lane kernel (2M x 24: 0.550 against 0.599).

@@ -549,6 +549,14 @@ def run_ours(args):
                lambda: (b.to_dq(), b.from_dq()), 2)
         record("to_root_dual_quat_1m_x_22", "configs[2], first half", b, "to_dq", b.to_dq, 1)
         record("from_root_dual_quat_1m_x_22", "configs[2], second half", b, "from_dq", b.from_dq, 1)
+        # SURVEY 8f rank 2 on the headline shape: positions -> local rotations, and mirror's rotation step (one fused launch)
+        b.alloc("rotm")
+        b.fk()
+        del b.rotm
+        record("from_root_positions_1m_x_22", "SURVEY 8f rank 2: from_root_positions on the fk positions of configs[1]", b,
+               "from_root_positions", b.from_root_positions, 1)
+        record("mirror_rotations_1m_x_22", "SURVEY 8f rank 2: mirror(mode='all') rotation step (fk -> flip -> local, fused)", b,
+               "mirror_all", b.mirror_all, 1)
         del b
         torch.cuda.empty_cache()
         for name, cfg in (("fk_4m_x_65", "configs[3]: fk 4M x 65 deep hierarchy"),
@@ -562,6 +570,10 @@ def run_ours(args):
                 b.alloc("dq", "rots")
                 record("to_root_dual_quat_4m_x_65", "configs[3] shape, to_root_dual_quat", b, "to_dq", b.to_dq, 1)
                 record("fk_quat_4m_x_65", "configs[3] shape, fk emitting global quaternions (SURVEY 8f rank 1)", b, "fk_quat", b.fk_quat, 1)
+                record("from_root_positions_4m_x_65", "configs[3] shape, from_root_positions on the fk_quat positions (SURVEY 8f rank 2)", b,
+                       "from_root_positions", b.from_root_positions, 1)
+                record("mirror_rotations_4m_x_65", "configs[3] shape, mirror(mode='all') rotation step (SURVEY 8f rank 2)", b,
+                       "mirror_all", b.mirror_all, 1)
             if name == "fk_4m_x_52" and world > 1:
                 extra.append({"name": "all_gather_positions_4m_x_52", "baseline_config": "configs[4], OPTIONAL exchange, never part of poses/s",
                               **all_gather_leg(b, timer, world, rank, dev, stream)})

@@ -138,7 +138,7 @@ struct ProgEntry {
 };
 template <typename P>
 struct ProgCache {
-    static constexpr int N = 4;
+    static constexpr int N = 8;
     ProgEntry<P> e[N];
     uint64_t clock = 0;
     ProgEntry<P> *find(const int64_t *parents, int n_joints, int variant) {

@@ -428,9 +428,11 @@ bool mirror_fused_applies(const int64_t *parents_host, int32_t n_joints, const D
     if (knob(K_MIRROR_FUSED, 1) == 0) return false;
     const pmb::TrackProgram *tp = nullptr;
     int n_steps = 0;
-    if (track_program(parents_host, n_joints, pmb::kQtTracks, 0, tp, n_steps) || n_steps == 0) return false;
-    const QtShape sh = qt_shape(pmb::kQtMirror, n_joints, n_steps * pmb::kQtTracks, knob(K_QT_WARPS_PER_SM, 32), dp);
-    return sh.warps * sh.blocks >= 4 && 2 * n_joints >= n_steps * pmb::kQtTracks;
+    bool three = false;
+    if (qt_pick_shape(pmb::kQtMirror, parents_host, n_joints, tp, n_steps, three) || n_steps == 0) return false;
+    const int nt = three ? 3 : 4, fq = three ? 10 : 8;
+    const QtShape sh = qt_shape(pmb::kQtMirror, n_joints, n_steps * nt, knob(K_QT_WARPS_PER_SM, 32), dp, nt, fq);
+    return sh.warps * sh.blocks >= 4 && 2 * n_joints >= n_steps * nt;
 }
 }  // namespace
 

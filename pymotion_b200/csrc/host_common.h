@@ -38,7 +38,7 @@ inline bool aligned32(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
     X(FK_ROWS) X(FK_TRACKS) X(FK_MTRACKS) X(FK_STAGES) X(FK_FR) X(FK_WARPS) X(FK_GROUP) X(FK_BLOCKS_PER_SM) X(FK_NB) \
     X(FK_U) X(FK_UL) X(FK_WARPS_PER_SM) X(FK_L2_PREFETCH) X(TMA_L2PROMO) X(FKQ_GROUP) X(FKQ_BLOCKS_PER_SM)         \
     X(FKQ_MATRIX) X(DQ_GROUP) X(DQ_BLOCKS_PER_SM) X(FRDQ_ELEMS) X(FRP_BLOCKS_PER_SM) X(UNROLL_CHUNK_APPLY)        \
-    X(VEC3_X4) X(HOST_CHUNK_MB) X(HOST_THREADS) X(DQ_TRACKS) X(FKQ_TRACKS) X(QT_WARPS_PER_SM) X(QT_PIPE) X(QT_DYNAMIC) X(FRP_FAST) X(FRP_WIDE) X(MIRROR_FUSED)
+    X(VEC3_X4) X(HOST_CHUNK_MB) X(HOST_THREADS) X(DQ_TRACKS) X(FKQ_TRACKS) X(QT_WARPS_PER_SM) X(QT_PIPE) X(QT_DYNAMIC) X(QT_SHAPE) X(FRP_FAST) X(FRP_WIDE) X(MIRROR_FUSED)
 enum Knob {
 #define X(name) K_##name,
     PMB_KNOB_LIST(X)

@@ -40,20 +40,24 @@ struct QtMirrorTable {
 struct QtNoMirror {};
 template <int MODE> struct QtMirrorArg { using type = QtNoMirror; };
 template <> struct QtMirrorArg<kQtMirror> { using type = QtMirrorTable; };
+// Lane shapes: NT tracks x FQ frames <= 32 lanes.  4 x 8 is the general one; 3 x 10 fills the steps of skeletons whose level
+// schedule is no shorter with four tracks than with three (the 22-joint body: 8 steps either way, 22 of 24 slots used instead of
+// 22 of 32) -- the walk at 22 joints is ISSUE bound (ncu: 78 % of the issue slots, 'not selected' the top stall), so the
+// instructions per frame, steps / FQ, are what counts there.
 constexpr int kQtFrames = 8, kQtTracks = 4;
 
 struct QtGeom {
     int in_pitch, in_bytes, q_pitch, q_bytes, p_bytes, o_bytes, tab_bytes, warp_bytes, block_bytes;
 };
-__host__ __device__ inline QtGeom qt_geom(int mode, int warps, int n_joints, int n_items) {
+__host__ __device__ inline QtGeom qt_geom(int mode, int warps, int n_joints, int n_items, int n_tracks = kQtTracks, int tile_frames = kQtFrames) {
     QtGeom g;
     g.in_pitch = 16 * (n_joints | 1);                                        // odd number of 16-byte units per frame row
-    g.in_bytes = kQtFrames * g.in_pitch;
+    g.in_bytes = tile_frames * g.in_pitch;
     g.q_pitch = mode == kQtDq ? 32 * (n_joints + 1) + 16 : 16 * ((n_joints + 1) | 1);  // + the identity record (dq) / padding
-    g.q_bytes = kQtFrames * g.q_pitch;
-    g.p_bytes = mode == kQtFkQuat ? ((kQtFrames * 12 * n_joints + 16 + 15) & ~15) : 0;  // dense, + 16 bytes of phase slack
+    g.q_bytes = tile_frames * g.q_pitch;
+    g.p_bytes = mode == kQtFkQuat ? ((tile_frames * 12 * n_joints + 16 + 15) & ~15) : 0;  // dense, + 16 bytes of phase slack
     g.o_bytes = mode == kQtMirror ? g.in_bytes : 0;                          // mirrored local rotations of the tile, rows like the input's
-    g.tab_bytes = (((n_items + kQtTracks) * 16 + 127) & ~127) + 128;  // + one step of no-ops (prefetch overrun) + the tile counter
+    g.tab_bytes = (((n_items + n_tracks) * 16 + 127) & ~127) + 128;  // + one step of no-ops (prefetch overrun) + the tile counter
     if (mode == kQtMirror) g.tab_bytes += (n_joints * 4 + 127) & ~127;       // + the mirror table
     g.warp_bytes = (2 * g.in_bytes + g.q_bytes + g.p_bytes + g.o_bytes + 16 + 128 + 127) & ~127;  // + 2 mbarriers + fence words
     g.block_bytes = 128 + g.tab_bytes + warps * g.warp_bytes;
@@ -108,13 +112,13 @@ __device__ __forceinline__ Quat<float> qt_from_matrix_sign(const Quat<float> &q)
     return pivot < 0.f ? Quat<float>{-q.w, -q.x, -q.y, -q.z} : q;
 }
 
-template <int MODE, bool PIPE>
+template <int MODE, bool PIPE, int NT = kQtTracks, int FQ = kQtFrames>
 __global__ void __launch_bounds__(512, 1)
 qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, long long gstride, const float *__restrict__ offsets,
                float4 *__restrict__ out_q, float *__restrict__ out_p, long long n_frames, int n_joints, int n_steps,
                int dynamic_claims, const __grid_constant__ TrackProgram prog,
                const __grid_constant__ typename QtMirrorArg<MODE>::type mir) {
-    constexpr int FQ = kQtFrames, NT = kQtTracks;
+    static_assert(NT * FQ <= 32 && NT >= 1 && FQ >= 1, "lanes = tracks x frames");
     constexpr bool POS = MODE == kQtFkQuat;
     constexpr bool MIRROR = MODE == kQtMirror;
     extern __shared__ __align__(128) unsigned char smem_qt[];
@@ -122,7 +126,7 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
     const int warps = blockDim.x >> 5;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int n_items = n_steps * NT;
-    const QtGeom geo = qt_geom(MODE, warps, n_joints, n_items);
+    const QtGeom geo = qt_geom(MODE, warps, n_joints, n_items, NT, FQ);
 
     // Item table, 16 bytes per item: offset (x, y, z) | word: bits 0-9 joint, 10-19 parent, 30 = parent in the track's
     // registers, 31 + 30 = no-op.  to_root_dual_quat: the children of the root get the identity record (joint index J).
@@ -157,7 +161,10 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
         mbar_init(bar0, 1), mbar_init(bar0 + 8, 1);
         fence_barrier_init();
     }
-    const int trk = lane >> 3, f = lane & 7;
+    // lane -> (track, frame); lanes past NT * FQ shadow lane 0 (same addresses: a broadcast) and never store
+    const bool idle = lane >= NT * FQ;
+    const int trk = idle ? 0 : lane / FQ, f = idle ? 0 : lane - (lane / FQ) * FQ;
+    const uint32_t idle_mask = idle ? 0x80000000u : 0u;
     if (MODE == kQtDq && lane < FQ) {  // the identity record of this frame's stage row: rotation (1, 0, 0, 0), dual part 0
         float4 *rec = reinterpret_cast<float4 *>(mine + 2 * geo.in_bytes + lane * geo.q_pitch + 32 * n_joints);
         rec[0] = make_float4(1.f, 0.f, 0.f, 0.f), rec[1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -291,8 +298,8 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
                 R = q_mul(Rp, Quat<float>{qv.x, qv.y, qv.z, qv.w});                // :241
                 const Quat<float> d = q_mul(Quat<float>{0.f, t0, t1, t2}, R);      // dual_quat.py:28-35
                 D = make_float4(0.5f * d.w, 0.5f * d.x, 0.5f * d.y, 0.5f * d.z);
-                qt_sts128_if(w, q_row + 32 * j, R.w, R.x, R.y, R.z);
-                qt_sts128_if(w, q_row + 32 * j + 16, D.x, D.y, D.z, D.w);
+                qt_sts128_if(w | idle_mask, q_row + 32 * j, R.w, R.x, R.y, R.z);
+                qt_sts128_if(w | idle_mask, q_row + 32 * j + 16, D.x, D.y, D.z, D.w);
             } else {
                 float4 a = make_float4(R.w, R.x, R.y, R.z);
                 qt_lds128_if(w << 1, q_row + 16 * p, a);
@@ -306,8 +313,8 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
                     t0 += v.x, t1 += v.y, t2 += v.z;
                 }
                 R = qt_from_matrix_sign(q_mul(Qp, r));
-                qt_sts128_if(w, q_row + 16 * j, R.w, R.x, R.y, R.z);
-                if (POS) qt_sts3_if(w, p_row + 12 * j, t0, t1, t2);
+                qt_sts128_if(w | idle_mask, q_row + 16 * j, R.w, R.x, R.y, R.z);
+                if (POS) qt_sts3_if(w | idle_mask, p_row + 12 * j, t0, t1, t2);
             }
             __syncwarp();  // a parent may have been stored by another track
             if (PIPE) e = e_next, qv = qv_next;
@@ -327,7 +334,7 @@ qtracks_kernel(const float4 *__restrict__ rot, const float *__restrict__ gpos, l
             if (draining) bulk_wait_read0();  // (lanes that stored) the previous tile has left the output rows
             __syncwarp();
             const uint32_t o_row = ost + f * geo.in_pitch;
-            for (int j = trk; j < n_joints; j += NT) {
+            for (int j = idle ? n_joints : trk; j < n_joints; j += NT) {
                 const uint32_t m = mtab[j];
                 const float4 a = lds128(q_row + 16 * (m & 0xFFFFu));
                 Quat<float> r{a.x, mir.fx * a.y, mir.fy * a.z, mir.fz * a.w};

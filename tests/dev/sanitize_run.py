@@ -68,6 +68,8 @@ def main():
         for knobs in ({"PMB_DQ_TRACKS": "1", "PMB_FKQ_TRACKS": "1"},
                       {"PMB_DQ_TRACKS": "1", "PMB_FKQ_TRACKS": "1", "PMB_QT_DYNAMIC": "0", "PMB_QT_PIPE": "1", "PMB_QT_WARPS_PER_SM": "2"},
                       {"PMB_DQ_TRACKS": "1", "PMB_FKQ_TRACKS": "1", "PMB_QT_PIPE": "0", "PMB_QT_WARPS_PER_SM": "1"},
+                      {"PMB_DQ_TRACKS": "1", "PMB_FKQ_TRACKS": "1", "PMB_QT_SHAPE": "1"},
+                      {"PMB_DQ_TRACKS": "1", "PMB_FKQ_TRACKS": "1", "PMB_QT_SHAPE": "2", "PMB_QT_PIPE": "1"},
                       {"PMB_DQ_TRACKS": "0", "PMB_FKQ_TRACKS": "0"}, {}):
             set_knobs(knobs)
             try:

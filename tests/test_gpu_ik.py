@@ -207,7 +207,8 @@ def test_mirror_large_vs_oracle(sk):
     assert_array_equal(o2, off)
 
 
-@pytest.mark.parametrize("knobs", [{}, {"PMB_MIRROR_FUSED": "0"}, {"PMB_QT_WARPS_PER_SM": "4"}, {"PMB_QT_DYNAMIC": "0", "PMB_QT_PIPE": "1"}])
+@pytest.mark.parametrize("knobs", [{}, {"PMB_MIRROR_FUSED": "0"}, {"PMB_QT_WARPS_PER_SM": "4"}, {"PMB_QT_DYNAMIC": "0", "PMB_QT_PIPE": "1"},
+                                   {"PMB_QT_SHAPE": "1"}, {"PMB_QT_SHAPE": "2"}])
 @pytest.mark.parametrize("name,n_frames", [("body22", 20_003), ("smplh52", 4_001), ("deep65", 2_049), ("chain3", 333), ("body22", 5)])
 def test_mirror_fused_and_two_kernel_paths(sk, set_knobs, knobs, name, n_frames):
     """mirror's rotation step as ONE launch (quaternion track kernel with the flip / re-index / back-to-local epilogue on the

@@ -633,6 +633,8 @@ def test_fk_row_team_kernel(sk, set_knobs, knobs, name, n_frames):
                                    {"PMB_FKQ_BLOCKS_PER_SM": "1"}, {"PMB_FKQ_MATRIX": "1"},
                                    {"PMB_FKQ_TRACKS": "1"}, {"PMB_FKQ_TRACKS": "1", "PMB_QT_WARPS_PER_SM": "1"},
                                    {"PMB_FKQ_TRACKS": "1", "PMB_QT_PIPE": "0", "PMB_QT_DYNAMIC": "0"},
+                                   {"PMB_FKQ_TRACKS": "1", "PMB_QT_SHAPE": "1"}, {"PMB_FKQ_TRACKS": "1", "PMB_QT_SHAPE": "2"},
+                                   {"PMB_FKQ_TRACKS": "1", "PMB_QT_SHAPE": "2", "PMB_QT_PIPE": "1", "PMB_QT_WARPS_PER_SM": "2"},
                                    {"PMB_FKQ_TRACKS": "1", "PMB_QT_PIPE": "1", "PMB_QT_WARPS_PER_SM": "3"}])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 6_050), ("deep65", 5_031), ("chain3", 777),
                                            ("body40", 2_049)])
@@ -762,7 +764,9 @@ def test_to_root_dual_quat_every_group(sk, set_knobs, group, name, n_frames):
 
 
 @pytest.mark.parametrize("knobs", [{"PMB_DQ_TRACKS": "1"}, {"PMB_DQ_TRACKS": "1", "PMB_QT_WARPS_PER_SM": "1"},
-                                   {"PMB_DQ_TRACKS": "1", "PMB_QT_DYNAMIC": "0", "PMB_QT_WARPS_PER_SM": "3"}, {"PMB_DQ_TRACKS": "0"}])
+                                   {"PMB_DQ_TRACKS": "1", "PMB_QT_DYNAMIC": "0", "PMB_QT_WARPS_PER_SM": "3"}, {"PMB_DQ_TRACKS": "0"},
+                                   {"PMB_DQ_TRACKS": "1", "PMB_QT_SHAPE": "1"}, {"PMB_DQ_TRACKS": "1", "PMB_QT_SHAPE": "2"},
+                                   {"PMB_DQ_TRACKS": "1", "PMB_QT_SHAPE": "2", "PMB_QT_WARPS_PER_SM": "1"}])
 @pytest.mark.parametrize("name,n_frames", [("body22", 40_003), ("smplh52", 20_051), ("deep65", 10_031), ("chain3", 777),
                                            ("body32", 5_009), ("body22", 7), ("body16", 1), ("deep65", 29)])
 def test_to_root_dual_quat_track_kernel(sk, set_knobs, knobs, name, n_frames):

@@ -42,7 +42,6 @@ public:
         cv_.notify_all();
         for (auto &t : workers_) t.join();
     }
-    int threads() const { return static_cast<int>(workers_.size()) + 1; }
     // copies [src, src + bytes) to dst in slices; the caller works too and returns when every slice is done
     void copy(void *dst, const void *src, size_t bytes) {
         const size_t slice = 1u << 20;

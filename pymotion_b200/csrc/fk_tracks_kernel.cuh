@@ -94,8 +94,8 @@ fk_tracks_kernel(const __grid_constant__ CUtensorMap tm_rot, const float *__rest
     static_assert(UL == 1 || UL == 2, "one or two lane groups");
     static_assert(NB >= 2 && NB <= 8, "ring depth");
     constexpr int C = kChunk;
-    extern __shared__ __align__(128) unsigned char smem_dyn[];
-    unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    extern __shared__ __align__(128) unsigned char smem_trk[];
+    unsigned char *smem_raw = smem_trk + ((128u - (smem_u32(smem_trk) & 127u)) & 127u);
     const int warps = blockDim.x >> 5;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int n_items = n_steps * U * UL;

@@ -337,7 +337,11 @@ def mirror(local_rotations, global_translation, parents, offsets, end_sites=None
 
 
 # ---- host-buffer pipeline (the reference's own calling convention: arrays in host memory) -----------------------
-_HOST_PATH_MIN_BYTES = 8 << 20  # below this a single copy in / kernel / copy out is as fast as the chunked pipeline
+# Host arrays always take the host pipeline: even one chunk of it (page-locked staging ring, no per-array torch copies) is twice
+# as fast as copy in / kernel / copy out through torch -- 100 x 22: 0.080 against 0.172 ms, 1000 x 22 (BASELINE config 1): 0.128
+# against 0.266, 16000 x 22: 1.03 against 1.77 (tools/small_host_probe.py, profiles/r2_small_host_probe.jsonl).  Raise to force
+# the single-shot path below a size.
+_HOST_PATH_MIN_BYTES = 0
 
 
 def _is_host(x) -> bool:

@@ -681,6 +681,13 @@ def e2e_legs(main, sk, lib, timer, world, dev, sampler, args):
     # (3) fk_quat: global quaternions back instead of matrices (28 J instead of 48 J bytes per frame over PCIe)
     t_q, (q_pos, q_rot) = timed(lambda: sk.fk_quat(h_rot, h_gpos, h_off, par))
     del q_pos, q_rot
+    # (4) BASELINE configs[2] called the reference's way: to_root_dual_quat then from_root_dual_quat on pageable NumPy arrays
+    def round_trip():
+        dq = sk.to_root_dual_quat(n_rot, n_gpos, par, n_off)
+        return sk.from_root_dual_quat(dq, par)
+    t_rt, (rt_t, rt_r) = timed(round_trip)
+    same_rt = bool(np.abs(rt_r[-4096:] - n_rot[-4096:]).max() < 1e-5)
+    del rt_t, rt_r
     lib.pmb_release_workspace()
     chunks = -(-frames // max(1, ((48 << 20) // (64 * n_joints + 12) + 31) // 32 * 32))
     return {
@@ -696,7 +703,11 @@ def e2e_legs(main, sk, lib, timer, world, dev, sampler, args):
                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_fk},
         "fk_quat": {"value": world * frames / t_q, "ms_per_step": 1e3 * t_q, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_fkq,
                     "api": "skeleton.fk_quat(page-locked CPU tensors): global quaternions instead of rotation matrices"},
-        "gpu_launches": 3 * (steps + 2) * chunks,
+        "round_trip_numpy": {"value": world * frames / t_rt, "ms_per_step": 1e3 * t_rt, "recovers_rotations": same_rt,
+                             "api": "skeleton.to_root_dual_quat(pageable NumPy) -> skeleton.from_root_dual_quat(...) -> NumPy (configs[2] "
+                                    "through the drop-in calls; both through the host pipeline)",
+                             "h2d_bytes_per_step": h2d + frames * n_joints * 32, "d2h_bytes_per_step": frames * n_joints * 60},
+        "gpu_launches": 5 * (steps + 2) * chunks,
     }
 
 

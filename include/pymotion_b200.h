@@ -125,6 +125,14 @@ int pmb_fk_f32_host(const float *rot_host, const float *global_pos_host, const f
 int pmb_fk_quat_f32_host(const float *rot_host, const float *global_pos_host, const float *offsets_host,
                          const int64_t *parents_host, int64_t n_frames, int32_t n_joints,
                          float *positions_host, float *global_rots_host, int64_t chunk_frames);
+
+/* The dual-quaternion pair on HOST arrays, same pipeline: ops/skeleton.py:207 `to_root_dual_quat(rotations, global_pos, parents,
+ * offsets) -> dq` and :173 `from_root_dual_quat(dq, parents) -> (translations, rotations)` called the reference's way, NumPy in /
+ * NumPy out.  offsets_host[0] must be zero (PMB_ERR_ROOT_OFFSET, the reference's assert at :227). */
+int pmb_to_root_dual_quat_f32_host(const float *rotations_host, const float *global_pos_host, const int64_t *parents_host,
+                                   const float *offsets_host, int64_t n_frames, int32_t n_joints, float *dq_host, int64_t chunk_frames);
+int pmb_from_root_dual_quat_f32_host(const float *dq_host, const int64_t *parents_host, int64_t n_frames, int32_t n_joints,
+                                     float *translations_host, float *rotations_host, int64_t chunk_frames);
 void pmb_release_workspace(void);
 
 /* ---- element-wise quaternion primitives (n = number of quaternions) ----- */

@@ -35,6 +35,8 @@ SIGNATURES = {
     "pmb_from_global_rotations_f32": [_vp, _vp, _i64, _i32, _vp, _vp],
     "pmb_fk_f32_host": [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64],
     "pmb_fk_quat_f32_host": [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64],
+    "pmb_to_root_dual_quat_f32_host": [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64],
+    "pmb_from_root_dual_quat_f32_host": [_vp, _vp, _i64, _i32, _vp, _vp, _i64],
     "pmb_release_workspace": [],
     "pmb_quat_mul_f32": [_vp, _vp, _vp, _i64, _vp],
     "pmb_quat_mul_vec_f32": [_vp, _vp, _vp, _i64, _vp],

@@ -203,22 +203,17 @@ bool is_pinned(const void *p) {
     return attr.type == cudaMemoryTypeHost;
 }
 
-// kind 0: fk (rotation matrices out, 36 J bytes per frame); kind 1: fk_quat (global quaternions, 16 J)
-int fk_host_common(int kind, const float *rot_host, const float *gpos_host, const float *offsets_host, const int64_t *parents_host,
-                   int64_t n_frames, int32_t n_joints, float *pos_host, float *rout_host, int64_t chunk_frames) {
-    if (!rot_host || !gpos_host || !offsets_host || !pos_host || !rout_host) return fail(PMB_ERR_NULL, "fk_host: NULL array pointer");
-    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "n_frames < 0");
-    if (n_joints < 1 || n_joints > PMB_MAX_JOINTS) return fail(PMB_ERR_SHAPE, "n_joints = %d out of range", n_joints);
-    {   // validate the topology before any allocation or copy
-        const pmb::JointProgram *prog = nullptr;
-        int n_slots = 0;
-        int rc = joint_program(parents_host, n_joints, false, prog, n_slots);
-        if (rc) return rc;
-    }
-    if (n_frames == 0) return PMB_OK;
+// One pipelined pass of a per-frame op over HOST arrays: up to two per-frame inputs (in_a, in_b bytes per frame) and up to two
+// per-frame outputs (out_a, out_b bytes per frame); `launch(d_in_a, d_in_b, d_out_a, d_out_b, d_offsets, n, stream)` enqueues the
+// op for n frames of device-resident staging.  offsets_host (n_joints x 3 floats, or NULL) is uploaded once.
+struct HostOp {
+    size_t in_a, in_b, out_a, out_b;
+};
+template <class Launch>
+int host_pipeline(const HostOp &op, const char *in_a_host, const char *in_b_host, const float *offsets_host, int32_t n_joints,
+                  int64_t n_frames, char *out_a_host, char *out_b_host, int64_t chunk_frames, Launch launch) {
     const size_t J = static_cast<size_t>(n_joints);
-    const size_t rot_w = kind == 0 ? 9 : 4;                           // floats per joint of the rotation output
-    const size_t in_frame = J * 16 + 12, out_frame = J * 12 + J * rot_w * 4;  // bytes per frame, in / out
+    const size_t in_frame = op.in_a + op.in_b, out_frame = op.out_a + op.out_b;  // bytes per frame, in / out
     if (chunk_frames <= 0) {
         // chunks are sized in bytes: ~48 MB of traffic (in + out) each, so that the pipeline fills after a few per cent
         // of a large batch whatever the joint count, and the device staging stays ~100 MB
@@ -233,23 +228,25 @@ int fk_host_common(int kind, const float *rot_host, const float *gpos_host, cons
     PipeLease lease{acquire_pipe(dev, rc)};
     if (!lease.p) return rc;
     HostPipe &w = *lease.p;
-    // device staging of one chunk: [rot | gpos] in, [positions | rotations] out (sub-buffers 256-byte aligned)
-    const size_t rot_bytes = (F * J * 16 + 255) & ~size_t(255), pos_bytes = (F * J * 12 + 255) & ~size_t(255);
-    if ((rc = w.grow_dev(rot_bytes + F * 12, pos_bytes + F * J * rot_w * 4))) return rc;
-    const bool in_pinned = is_pinned(rot_host) && is_pinned(gpos_host);
-    const bool out_pinned = is_pinned(pos_host) && is_pinned(rout_host);
-    if (!in_pinned && (rc = w.grow_pin(w.pin_in, w.pin_in_cap, rot_bytes + F * 12))) return rc;
-    if (!out_pinned && (rc = w.grow_pin(w.pin_out, w.pin_out_cap, pos_bytes + F * J * rot_w * 4))) return rc;
+    // device staging of one chunk: [in_a | in_b] and [out_a | out_b] (sub-buffers 256-byte aligned)
+    const size_t ia_bytes = (F * op.in_a + 255) & ~size_t(255), oa_bytes = (F * op.out_a + 255) & ~size_t(255);
+    if ((rc = w.grow_dev(ia_bytes + F * op.in_b + 256, oa_bytes + F * op.out_b + 256))) return rc;
+    const bool in_pinned = is_pinned(in_a_host) && (!op.in_b || is_pinned(in_b_host));
+    const bool out_pinned = is_pinned(out_a_host) && (!op.out_b || is_pinned(out_b_host));
+    if (!in_pinned && (rc = w.grow_pin(w.pin_in, w.pin_in_cap, ia_bytes + F * op.in_b + 256))) return rc;
+    if (!out_pinned && (rc = w.grow_pin(w.pin_out, w.pin_out_cap, oa_bytes + F * op.out_b + 256))) return rc;
     if ((!in_pinned || !out_pinned) && !w.pool) {
         const int hw = static_cast<int>(std::thread::hardware_concurrency());
         const int n = std::max(1, std::min(knob(K_HOST_THREADS, 4), hw > 0 ? hw : 1));
         w.pool.reset(new CopyPool(n - 1));
     }
 
-    PMB_CUDA(cudaMemcpyAsync(w.offsets, offsets_host, J * 12, cudaMemcpyHostToDevice, w.stream[0]));
-    PMB_CUDA(cudaEventRecord(w.offsets_ready, w.stream[0]));
-    PMB_CUDA(cudaStreamWaitEvent(w.stream[1], w.offsets_ready, 0));
-    PMB_CUDA(cudaStreamSynchronize(w.stream[0]));  // offsets_host may be a temporary of the caller
+    if (offsets_host) {
+        PMB_CUDA(cudaMemcpyAsync(w.offsets, offsets_host, J * 12, cudaMemcpyHostToDevice, w.stream[0]));
+        PMB_CUDA(cudaEventRecord(w.offsets_ready, w.stream[0]));
+        PMB_CUDA(cudaStreamWaitEvent(w.stream[1], w.offsets_ready, 0));
+        PMB_CUDA(cudaStreamSynchronize(w.stream[0]));  // offsets_host may be a temporary of the caller
+    }
 
     struct Pending {  // a chunk whose results sit in the output ring and still have to reach the caller's memory
         bool live = false;
@@ -259,8 +256,8 @@ int fk_host_common(int kind, const float *rot_host, const float *gpos_host, cons
         Pending &pd = pending[slot];
         if (!pd.live) return PMB_OK;
         PMB_CUDA(cudaEventSynchronize(w.d2h_done[slot]));
-        w.pool->copy(pos_host + pd.f0 * J * 3, w.pin_out[slot], pd.n * J * 12);
-        w.pool->copy(rout_host + pd.f0 * J * rot_w, w.pin_out[slot] + pos_bytes, pd.n * J * rot_w * 4);
+        w.pool->copy(out_a_host + pd.f0 * op.out_a, w.pin_out[slot], pd.n * op.out_a);
+        if (op.out_b) w.pool->copy(out_b_host + pd.f0 * op.out_b, w.pin_out[slot] + oa_bytes, pd.n * op.out_b);
         pd.live = false;
         return PMB_OK;
     };
@@ -269,29 +266,27 @@ int fk_host_common(int kind, const float *rot_host, const float *gpos_host, cons
     for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, slot ^= 1) {
         const size_t n = static_cast<size_t>(std::min<int64_t>(chunk_frames, n_frames - f0));
         cudaStream_t st = w.stream[slot];  // stream order makes the slot's device buffers safe to reuse
-        float *d_rot = reinterpret_cast<float *>(w.dev_in[slot]), *d_gpos = reinterpret_cast<float *>(w.dev_in[slot] + rot_bytes);
-        float *d_pos = reinterpret_cast<float *>(w.dev_out[slot]), *d_rout = reinterpret_cast<float *>(w.dev_out[slot] + pos_bytes);
+        char *d_ia = w.dev_in[slot], *d_ib = w.dev_in[slot] + ia_bytes;
+        char *d_oa = w.dev_out[slot], *d_ob = w.dev_out[slot] + oa_bytes;
         if (in_pinned) {
-            PMB_CUDA(cudaMemcpyAsync(d_rot, rot_host + f0 * J * 4, n * J * 16, cudaMemcpyHostToDevice, st));
-            PMB_CUDA(cudaMemcpyAsync(d_gpos, gpos_host + f0 * 3, n * 12, cudaMemcpyHostToDevice, st));
+            PMB_CUDA(cudaMemcpyAsync(d_ia, in_a_host + f0 * op.in_a, n * op.in_a, cudaMemcpyHostToDevice, st));
+            if (op.in_b) PMB_CUDA(cudaMemcpyAsync(d_ib, in_b_host + f0 * op.in_b, n * op.in_b, cudaMemcpyHostToDevice, st));
         } else {
             PMB_CUDA(cudaEventSynchronize(w.h2d_done[slot]));  // the ring slot's previous chunk has left for the device
-            w.pool->copy(w.pin_in[slot], rot_host + f0 * J * 4, n * J * 16);
-            memcpy(w.pin_in[slot] + rot_bytes, gpos_host + f0 * 3, n * 12);
-            PMB_CUDA(cudaMemcpyAsync(d_rot, w.pin_in[slot], n * J * 16, cudaMemcpyHostToDevice, st));
-            PMB_CUDA(cudaMemcpyAsync(d_gpos, w.pin_in[slot] + rot_bytes, n * 12, cudaMemcpyHostToDevice, st));
+            w.pool->copy(w.pin_in[slot], in_a_host + f0 * op.in_a, n * op.in_a);
+            if (op.in_b) memcpy(w.pin_in[slot] + ia_bytes, in_b_host + f0 * op.in_b, n * op.in_b);
+            PMB_CUDA(cudaMemcpyAsync(d_ia, w.pin_in[slot], n * op.in_a, cudaMemcpyHostToDevice, st));
+            if (op.in_b) PMB_CUDA(cudaMemcpyAsync(d_ib, w.pin_in[slot] + ia_bytes, n * op.in_b, cudaMemcpyHostToDevice, st));
             PMB_CUDA(cudaEventRecord(w.h2d_done[slot], st));
         }
-        rc = kind == 0 ? pmb_fk_f32(d_rot, d_gpos, 3, w.offsets, 0, parents_host, static_cast<int64_t>(n), n_joints, d_pos, d_rout, st)
-                       : pmb_fk_quat_f32(d_rot, d_gpos, 3, w.offsets, 0, parents_host, static_cast<int64_t>(n), n_joints, d_pos, d_rout, st);
-        if (rc) return rc;  // (the lease drains both streams)
+        if ((rc = launch(d_ia, d_ib, d_oa, d_ob, w.offsets, static_cast<int64_t>(n), st))) return rc;  // (the lease drains both streams)
         if (out_pinned) {
-            PMB_CUDA(cudaMemcpyAsync(pos_host + f0 * J * 3, d_pos, n * J * 12, cudaMemcpyDeviceToHost, st));
-            PMB_CUDA(cudaMemcpyAsync(rout_host + f0 * J * rot_w, d_rout, n * J * rot_w * 4, cudaMemcpyDeviceToHost, st));
+            PMB_CUDA(cudaMemcpyAsync(out_a_host + f0 * op.out_a, d_oa, n * op.out_a, cudaMemcpyDeviceToHost, st));
+            if (op.out_b) PMB_CUDA(cudaMemcpyAsync(out_b_host + f0 * op.out_b, d_ob, n * op.out_b, cudaMemcpyDeviceToHost, st));
         } else {
             if ((rc = copy_out(slot))) return rc;  // the ring slot must be empty before the GPU refills it (normally done below)
-            PMB_CUDA(cudaMemcpyAsync(w.pin_out[slot], d_pos, n * J * 12, cudaMemcpyDeviceToHost, st));
-            PMB_CUDA(cudaMemcpyAsync(w.pin_out[slot] + pos_bytes, d_rout, n * J * rot_w * 4, cudaMemcpyDeviceToHost, st));
+            PMB_CUDA(cudaMemcpyAsync(w.pin_out[slot], d_oa, n * op.out_a, cudaMemcpyDeviceToHost, st));
+            if (op.out_b) PMB_CUDA(cudaMemcpyAsync(w.pin_out[slot] + oa_bytes, d_ob, n * op.out_b, cudaMemcpyDeviceToHost, st));
             PMB_CUDA(cudaEventRecord(w.d2h_done[slot], st));
             pending[slot] = {true, static_cast<size_t>(f0), n};
             if ((rc = copy_out(slot ^ 1))) return rc;  // the previous chunk's results, while the GPU works on this one
@@ -303,6 +298,32 @@ int fk_host_common(int kind, const float *rot_host, const float *gpos_host, cons
         for (int s = 0; s < 2; ++s)
             if ((rc = copy_out(s))) return rc;
     return PMB_OK;
+}
+
+int validate_host_call(const char *what, const int64_t *parents_host, int64_t n_frames, int32_t n_joints, bool detach) {
+    if (n_frames < 0) return fail(PMB_ERR_SHAPE, "%s: n_frames < 0", what);
+    if (n_joints < 1 || n_joints > PMB_MAX_JOINTS) return fail(PMB_ERR_SHAPE, "%s: n_joints = %d out of range", what, n_joints);
+    const pmb::JointProgram *prog = nullptr;  // validate the topology before any allocation or copy
+    int n_slots = 0;
+    return joint_program(parents_host, n_joints, detach, prog, n_slots);
+}
+
+// kind 0: fk (rotation matrices out, 36 J bytes per frame); kind 1: fk_quat (global quaternions, 16 J)
+int fk_host_common(int kind, const float *rot_host, const float *gpos_host, const float *offsets_host, const int64_t *parents_host,
+                   int64_t n_frames, int32_t n_joints, float *pos_host, float *rout_host, int64_t chunk_frames) {
+    if (!rot_host || !gpos_host || !offsets_host || !pos_host || !rout_host) return fail(PMB_ERR_NULL, "fk_host: NULL array pointer");
+    int rc = validate_host_call("fk_host", parents_host, n_frames, n_joints, false);
+    if (rc) return rc;
+    if (n_frames == 0) return PMB_OK;
+    const size_t J = static_cast<size_t>(n_joints);
+    const HostOp op{J * 16, 12, J * 12, J * (kind == 0 ? 36u : 16u)};
+    return host_pipeline(op, reinterpret_cast<const char *>(rot_host), reinterpret_cast<const char *>(gpos_host), offsets_host, n_joints,
+                         n_frames, reinterpret_cast<char *>(pos_host), reinterpret_cast<char *>(rout_host), chunk_frames,
+                         [&](char *d_rot, char *d_gpos, char *d_pos, char *d_rout, float *d_off, int64_t n, cudaStream_t st) {
+                             auto fn = kind == 0 ? pmb_fk_f32 : pmb_fk_quat_f32;
+                             return fn(reinterpret_cast<float *>(d_rot), reinterpret_cast<float *>(d_gpos), 3, d_off, 0, parents_host, n, n_joints,
+                                       reinterpret_cast<float *>(d_pos), reinterpret_cast<float *>(d_rout), st);
+                         });
 }
 
 }  // namespace
@@ -335,6 +356,42 @@ int pmb_fk_quat_f32_host(const float *rot_host, const float *global_pos_host, co
                          int64_t n_frames, int32_t n_joints, float *positions_host, float *global_rots_host, int64_t chunk_frames) {
     return fk_host_common(1, rot_host, global_pos_host, offsets_host, parents_host, n_frames, n_joints, positions_host,
                           global_rots_host, chunk_frames);
+}
+
+// to_root_dual_quat / from_root_dual_quat on HOST arrays (ops/skeleton.py:207, :173 with the reference's own calling convention,
+// NumPy in / NumPy out): the same chunked, two-stream pipeline.
+int pmb_to_root_dual_quat_f32_host(const float *rotations_host, const float *global_pos_host, const int64_t *parents_host,
+                                   const float *offsets_host, int64_t n_frames, int32_t n_joints, float *dq_host, int64_t chunk_frames) {
+    if (!rotations_host || !global_pos_host || !offsets_host || !dq_host) return fail(PMB_ERR_NULL, "to_root_dual_quat_host: NULL array pointer");
+    if (offsets_host[0] != 0.f || offsets_host[1] != 0.f || offsets_host[2] != 0.f)
+        return fail(PMB_ERR_ROOT_OFFSET, "offsets[0] must be zero (ops/skeleton.py:227)");
+    int rc = validate_host_call("to_root_dual_quat_host", parents_host, n_frames, n_joints, true);
+    if (rc) return rc;
+    if (n_frames == 0) return PMB_OK;
+    const size_t J = static_cast<size_t>(n_joints);
+    const HostOp op{J * 16, 12, J * 32, 0};
+    return host_pipeline(op, reinterpret_cast<const char *>(rotations_host), reinterpret_cast<const char *>(global_pos_host), offsets_host,
+                         n_joints, n_frames, reinterpret_cast<char *>(dq_host), nullptr, chunk_frames,
+                         [&](char *d_rot, char *d_gpos, char *d_dq, char *, float *d_off, int64_t n, cudaStream_t st) {
+                             return pmb_to_root_dual_quat_f32(reinterpret_cast<float *>(d_rot), reinterpret_cast<float *>(d_gpos), 3, parents_host,
+                                                              d_off, offsets_host, n, n_joints, reinterpret_cast<float *>(d_dq), st);
+                         });
+}
+
+int pmb_from_root_dual_quat_f32_host(const float *dq_host, const int64_t *parents_host, int64_t n_frames, int32_t n_joints,
+                                     float *translations_host, float *rotations_host, int64_t chunk_frames) {
+    if (!dq_host || !translations_host || !rotations_host) return fail(PMB_ERR_NULL, "from_root_dual_quat_host: NULL array pointer");
+    int rc = validate_host_call("from_root_dual_quat_host", parents_host, n_frames, n_joints, true);
+    if (rc) return rc;
+    if (n_frames == 0) return PMB_OK;
+    const size_t J = static_cast<size_t>(n_joints);
+    const HostOp op{J * 32, 0, J * 12, J * 16};
+    return host_pipeline(op, reinterpret_cast<const char *>(dq_host), nullptr, nullptr, n_joints, n_frames,
+                         reinterpret_cast<char *>(translations_host), reinterpret_cast<char *>(rotations_host), chunk_frames,
+                         [&](char *d_dq, char *, char *d_t, char *d_r, float *, int64_t n, cudaStream_t st) {
+                             return pmb_from_root_dual_quat_f32(reinterpret_cast<float *>(d_dq), parents_host, n, n_joints,
+                                                                reinterpret_cast<float *>(d_t), reinterpret_cast<float *>(d_r), st);
+                         });
 }
 
 }  // extern "C"

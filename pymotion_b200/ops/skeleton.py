@@ -143,6 +143,9 @@ def to_root_dual_quat(rotations, global_pos, parents, offsets):
     Raises ``AssertionError`` if ``offsets[0] != 0`` (ops/skeleton.py:227).
     Returns ``dq`` of shape [..., n_joints, 8].
     """
+    routed = _dq_host_route_to(rotations, global_pos, parents, offsets)
+    if routed is not None:
+        return routed
     m = rt.Marshal(rotations, global_pos, offsets)
     q = m.dev(rotations)
     if q.dim() < 2 or q.shape[-1] != 4:
@@ -174,6 +177,9 @@ def from_root_dual_quat(dq, parents):
     in that order, which is what the reference returns (:204) even though its
     docstring lists them the other way round.
     """
+    routed = _dq_host_route_from(dq, parents)
+    if routed is not None:
+        return routed
     m = rt.Marshal(dq)
     d = m.dev(dq)
     if d.dim() < 2 or d.shape[-1] != 8:
@@ -362,6 +368,62 @@ def _pinned_empty(shape) -> torch.Tensor:
     # page-locked, from torch's caching host allocator: the D2H copies land in it by DMA, and the block is
     # recycled when the caller drops the result
     return torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
+
+
+def _dq_host_route_to(rotations, global_pos, parents, offsets):
+    """to_root_dual_quat called the reference's way -- NumPy / CPU tensors in, the same kind out -- through the host pipeline
+    (pmb_to_root_dual_quat_f32_host).  None = not plain host arrays of the contract shapes: the general path handles them."""
+    from .. import _lib
+
+    if not (_is_host(rotations) and _is_host(global_pos) and _is_host(offsets)):
+        return None
+    shape = tuple(np.shape(rotations))
+    if len(shape) < 2 or shape[-1] != 4 or tuple(np.shape(offsets)) != (shape[-2], 3) or tuple(np.shape(global_pos)) != shape[:-2] + (3,):
+        return None
+    lead, n_joints = shape[:-2], int(shape[-2])
+    par = rt.host_parents(parents)
+    if par.shape[0] != n_joints:
+        return None  # the general path raises the reference-style error
+    m = rt.Marshal(rotations, global_pos, offsets)  # array kind / dtype of the result, float64 warning
+    for x in (rotations, global_pos, offsets):
+        if isinstance(x, torch.Tensor):
+            m.dev_check(x)
+    q, gp, off = _host_f32(rotations), _host_f32(global_pos), _host_f32(offsets)
+    dq = _pinned_empty(lead + (n_joints, 8))
+    n_frames = _lead_frames(lead)
+    if n_frames > 0:
+        with torch.cuda.device(rt.default_device()):
+            _lib.check(_lib.load().pmb_to_root_dual_quat_f32_host(q.data_ptr(), gp.data_ptr(), par.ctypes.data, off.data_ptr(), n_frames,
+                                                                   n_joints, dq.data_ptr(), 0))
+    elif bool((off[0] != 0).any()):
+        raise AssertionError("offsets[0] must be zero (ops/skeleton.py:227)")
+    return m.out_host(dq)
+
+
+def _dq_host_route_from(dq, parents):
+    """from_root_dual_quat on host arrays through the host pipeline (pmb_from_root_dual_quat_f32_host)."""
+    from .. import _lib
+
+    if not _is_host(dq):
+        return None
+    shape = tuple(np.shape(dq))
+    if len(shape) < 2 or shape[-1] != 8:
+        return None
+    lead, n_joints = shape[:-2], int(shape[-2])
+    par = rt.host_parents(parents)
+    if par.shape[0] != n_joints:
+        return None
+    m = rt.Marshal(dq)
+    if isinstance(dq, torch.Tensor):
+        m.dev_check(dq)
+    d = _host_f32(dq)
+    trans, rots = _pinned_empty(lead + (n_joints, 3)), _pinned_empty(lead + (n_joints, 4))
+    n_frames = _lead_frames(lead)
+    if n_frames > 0:
+        with torch.cuda.device(rt.default_device()):
+            _lib.check(_lib.load().pmb_from_root_dual_quat_f32_host(d.data_ptr(), par.ctypes.data, n_frames, n_joints, trans.data_ptr(),
+                                                                     rots.data_ptr(), 0))
+    return m.out_host(trans), m.out_host(rots)
 
 
 def _fk_host_pipeline(kind: str, rot, global_pos, offsets, parents, out=None, chunk_frames: int = 0):

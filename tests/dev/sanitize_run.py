@@ -106,6 +106,9 @@ def main():
             # large host batches take the chunked pipeline; force it on this small one through fk_host
             hp, hr = sk.fk_host(rot, gp, off, par, chunk_frames=64)
             np.testing.assert_allclose(hp, want_pos, rtol=1e-5, atol=1e-5 * scale)
+            hd = sk.to_root_dual_quat(rot, gp, par, off)   # NumPy in: the host pipeline of the dual-quaternion pair
+            np.testing.assert_allclose(hd, want_dq, rtol=1e-5, atol=5e-5 * scale)
+            sk.from_root_dual_quat(hd, par)
             hp, hq = sk.fk_quat_host(rot, gp, off, par, chunk_frames=64)
             np.testing.assert_allclose(hp, want_pos, rtol=1e-5, atol=1e-5 * scale)
             n_checked += 3

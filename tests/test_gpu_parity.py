@@ -4,6 +4,8 @@ real reference and against the oracle on seeded inputs.  Needs a B200: -m gpu.
 Tolerance: BASELINE.json's north_star asks for positions / rotmats within 1e-5
 relative in fp32 of the reference's NumPy output; RTOL = ATOL = 1e-5 below.  The
 reference tests' hand-written goldens are checked at their own atol (1e-6)."""
+import warnings
+
 import numpy as np
 import pytest
 import torch
@@ -823,3 +825,37 @@ def test_frame_shards_on_two_devices(sk):
         assert pos.device == dev
         assert torch.equal(pos.cpu(), full_pos[lo:hi].cpu())
         assert torch.equal(rotm.cpu(), full_rotm[lo:hi].cpu())
+
+
+@pytest.mark.parametrize("name,n_frames", [("body22", 1), ("body22", 1000), ("deep65", 2_049), ("body22", 120_001)])
+def test_dual_quat_pair_on_host_arrays(sk, name, n_frames):
+    """to_root_dual_quat / from_root_dual_quat called the reference's way -- NumPy in, NumPy out -- take the host pipeline
+    (pmb_*_f32_host: chunked copies in / kernel / copies out on two streams; 120 001 x 22 is several chunks with a ragged last
+    one) and give the bits of the device-resident path; float64 in -> float64 out; CPU tensors in -> CPU tensors out; the
+    reference's offsets[0] assert (skeleton.py:227) survives; inputs are not modified."""
+    par = parents_of(name)
+    rot, gp, off = synth_numpy(n_frames, par, seed=23 * len(par) + n_frames)
+    keep = [a.copy() for a in (rot, gp, off)]
+    dq = sk.to_root_dual_quat(rot, gp, par, off)
+    assert isinstance(dq, np.ndarray) and dq.dtype == np.float32 and dq.shape == (n_frames, len(par), 8)
+    dev = [torch.from_numpy(a).cuda() for a in (rot, gp, off)]
+    want = sk.to_root_dual_quat(dev[0], dev[1], par, dev[2])
+    assert np.array_equal(dq, want.cpu().numpy())
+    trans, rots = sk.from_root_dual_quat(dq, par)
+    wt, wr = sk.from_root_dual_quat(want, par)
+    assert isinstance(trans, np.ndarray) and np.array_equal(trans, wt.cpu().numpy()) and np.array_equal(rots, wr.cpu().numpy())
+    for a, b in zip((rot, gp, off), keep):
+        assert np.array_equal(a, b)
+    if n_frames <= 2_049:
+        assert_allclose(dq, orc.to_root_dual_quat(rot, gp, par, off), **TOL)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            d64 = sk.to_root_dual_quat(rot.astype(np.float64), gp.astype(np.float64), par, off.astype(np.float64))
+        assert d64.dtype == np.float64
+        assert_allclose(d64, dq, rtol=0, atol=0)
+        t_cpu = sk.to_root_dual_quat(torch.from_numpy(rot), torch.from_numpy(gp), par, torch.from_numpy(off))
+        assert isinstance(t_cpu, torch.Tensor) and not t_cpu.is_cuda and torch.equal(t_cpu, torch.from_numpy(dq))
+        bad = off.copy()
+        bad[0, 1] = 0.25
+        with pytest.raises(AssertionError):
+            sk.to_root_dual_quat(rot, gp, par, bad)

@@ -24,5 +24,10 @@ for n in (100, 1000, 4000, 16000, 64000):
     sk._HOST_PATH_MIN_BYTES = old
     b = best(piped)
     p1, r1 = single(); p2, r2 = piped()
+    dq = sk.to_root_dual_quat(rot, gp, par, off)
+    c = best(lambda: sk.to_root_dual_quat(rot, gp, par, off))
+    d = best(lambda: sk.from_root_dual_quat(dq, par))
+    print(json.dumps({"frames": n, "to_root_dual_quat_ms_best_median": [round(x, 4) for x in c],
+                      "from_root_dual_quat_ms_best_median": [round(x, 4) for x in d]}), flush=True)
     print(json.dumps({"frames": n, "bytes": n * (64 * 22 + 12), "single_shot_ms_best_median": [round(x, 4) for x in a],
                       "host_pipeline_ms_best_median": [round(x, 4) for x in b], "equal": bool(np.array_equal(p1, p2) and np.array_equal(r1, r2))}), flush=True)
